@@ -1,0 +1,123 @@
+/*
+ * sg2b200 — C ABI of the B200-native (sm_100a) StackGAN-v2 train-step kernels.
+ *
+ * The reference (smallflyingpig/speech-to-image-translation-without-text) has no FFI: its hot path is
+ * torch.nn modules in StackGAN_v2/model.py that dispatch to cuDNN/cuBLAS. Each entry point below replaces
+ * the library call(s) that one reference construct triggers; the reference file:line is cited per function.
+ * Every pointer is a raw CUDA device pointer owned by the caller (PyTorch's caching allocator); `stream` is a
+ * cudaStream_t passed as void*. All functions return 0 on success, a negative SG2_E* code for a rejected shape,
+ * or a positive cudaError_t. Nothing here allocates, synchronises, or falls back to the CPU.
+ *
+ * Internal activation layout: NHWC, bf16.  Weight packs: bf16, see sg2_pack_weights.
+ */
+#ifndef SG2B200_H
+#define SG2B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG2_EINVAL (-1)  /* unsupported shape / argument */
+#define SG2_EDRIVER (-2) /* cuTensorMapEncodeTiled unavailable or failed */
+
+/* Convolution kinds on the path. */
+enum {
+  SG2_CONV3x3 = 0,   /* conv3x3 s1 p1, no bias            model.py:125-128 */
+  SG2_UPCONV3x3 = 1, /* nearest 2x upsample + conv3x3     model.py:133-140 (nn.Upsample folded into addressing) */
+  SG2_CONV4x4S2 = 2, /* conv4x4 s2 p1, no bias            model.py:369-398 */
+  SG2_GEMM = 3,      /* 1x1 / plain matmul                model.py:179, 217 */
+  SG2_STEM4x4 = 4    /* pack-only: conv4x4 s2 on 3 channels as a K=48(->64) GEMM over sg2_stem_im2col rows, model.py:383 */
+};
+enum { SG2_ACT_NONE = 0, SG2_ACT_GLU = 1, SG2_ACT_LRELU = 2 };
+enum { SG2_OUT_BF16 = 0, SG2_OUT_F32_ATOMIC = 1, SG2_OUT_F32_STORE = 2 };
+
+int sg2_version(void);
+const char* sg2_last_error(void);
+
+/* ---- weights ------------------------------------------------------------------------------------------
+ * fp32 OIHW master weights (the nn.Conv2d .weight the optimiser owns) -> bf16 operand packs.
+ *   wpk  : fprop operand  [groups][Cout][taps][Cin]      wpkT : dgrad operand [groups'][Cin][taps'][Cout]
+ *   CONV3x3   wpk [1][Cout][9][Cin]   wpkT [1][Cin][9][Cout]
+ *   UPCONV3x3 wpk [4][Cout][4][Cin]   wpkT [1][Cin][16][Cout]   (3x3 taps pre-summed per output parity)
+ *   CONV4x4S2 wpk [1][Cout][16][Cin]  wpkT [4][Cin][4][Cout]
+ *   GEMM      wpk [Cout][Cin]         wpkT [Cin][Cout]
+ * Cout_pad/Cin_pad >= Cout/Cin give the padded operand extents (zero filled). Either output may be NULL. */
+int sg2_pack_weights(int kind, const float* w_oihw, void* wpk, void* wpkT, int Cout, int Cin, int Cout_pad,
+                     int Cin_pad, void* stream);
+/* dwpk [Cout_pad][jobs][Cin_pad] fp32 (what sg2_conv_wgrad accumulates) -> OIHW fp32 gradient (+= if accumulate). */
+int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad_oihw, int Cout, int Cin, int Cout_pad, int Cin_pad,
+                     int accumulate, void* stream);
+
+/* ---- convolutions (tcgen05 implicit GEMM, TMA operands) ------------------------------------------------
+ * B,H,W,Cin are the FORWARD input extents of the layer; Cout its output channels. Replaces cuDNN fprop /
+ * dgrad / wgrad behind nn.Conv2d (+ nn.Upsample) at model.py:125-140, 358-398.
+ *   fprop : x [B][H][W][Cin] -> y  (CONV3x3: [B][H][W][Cout]; UPCONV3x3: [B][2H][2W][Cout]; CONV4x4S2: [B][H/2][W/2][Cout])
+ *   dgrad : dy (shape of y) -> dx [B][H][W][Cin]
+ *   wgrad : dwpk[Cout][jobs][Cin] += dy^T (x) im2col(x)   (fp32, red.global.add)
+ * out_mode: SG2_OUT_BF16 store, SG2_OUT_F32_ATOMIC (split-K accumulate into a zeroed fp32 buffer), SG2_OUT_F32_STORE. */
+int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mode, int B, int H, int W, int Cin,
+                   int Cout, int splitk, void* stream);
+int sg2_conv_dgrad(int kind, const void* dy, const void* wpkT, void* dx, int out_mode, int B, int H, int W, int Cin,
+                   int Cout, int splitk, void* stream);
+int sg2_conv_wgrad(int kind, const void* x, const void* dy, float* dwpk, int B, int H, int W, int Cin, int Cout,
+                   int splitk, void* stream);
+
+/* ---- BatchNorm (+ GLU / LeakyReLU(0.2) / residual) on [P pixels][C channels] bf16 ---------------------
+ * nn.BatchNorm2d/1d train mode (model.py:137,147,158,161,218,361,372,387-394): batch mean, biased variance,
+ * eps, momentum; running_var gets the unbiased variance; num_batches_tracked += 1.
+ * sums: fp64 workspace [2][C], must be zero on entry, is left zero on exit of finalize / bwd. */
+int sg2_bn_stats(const void* x, long long P, int C, double* sums, void* stream);
+int sg2_bn_finalize(double* sums, long long P, int C, float eps, float momentum, float* mean, float* rstd,
+                    float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
+int sg2_bn_eval_prepare(const float* running_mean, const float* running_var, float eps, float* mean, float* rstd,
+                        int C, void* stream);
+/* out = act(bn(x)) (+ residual, ACT_NONE only). GLU (model.py:112-122) halves the channel count. mean==NULL: no BN. */
+int sg2_bn_act_fwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                   const void* residual, void* out, long long P, int C, int act, void* stream);
+/* dx (shape of x) from dout (shape of out); dgamma/dbeta (=|+=). Two passes + a finalize. */
+int sg2_bn_act_bwd(const void* x, const void* dout, const float* mean, const float* rstd, const float* gamma,
+                   const float* beta, double* sums, void* dx, float* dgamma, float* dbeta, int accumulate,
+                   long long P, int C, int act, void* stream);
+int sg2_lrelu_bwd(const void* x, const void* dout, void* dx, long long n, void* stream);
+int sg2_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
+int sg2_f32_to_bf16(const float* in, void* out, long long n, void* stream);
+
+/* ---- broadcast c_code concat (model.py:274-277, 431-434): out[b,y,x,:] = (c[b,:E] | h[b,y,x,:Ch]) -------- */
+int sg2_concat_c(const float* c, const void* h, void* out, int B, int HW, int E, int Ch, void* stream);
+int sg2_concat_c_bwd(const void* dcat, void* dh, float* dc /* += */, int B, int HW, int E, int Ch, void* stream);
+
+/* ---- image heads (model.py:287-298) and D stems (model.py:383) --------------------------------------------- */
+int sg2_head_tanh_fwd(const void* y /* [P][CP] bf16 */, float* img /* NCHW fp32 */, int B, int HW, int CP, void* stream);
+int sg2_head_tanh_bwd(const float* dimg, const float* img, void* dy, int B, int HW, int CP, void* stream);
+int sg2_stem_im2col(const float* img /* NCHW fp32 [B][3][S][S] */, void* col /* [B*(S/2)^2][64] bf16 */, int B, int S,
+                    void* stream);
+int sg2_stem_col2im(const void* dcol, float* dimg, int B, int S, void* stream);
+int sg2_nhwc_to_nchw_f32(const void* in, float* out, int B, int HW, int C, void* stream);
+int sg2_nchw_f32_to_nhwc(const float* in, void* out, int B, int HW, int C, void* stream);
+
+/* ---- small fp32 operators ---------------------------------------------------------------------------------
+ * nn.Linear with M = batch rows (model.py:179, 217); x = cat(x1[M][K1], x2[M][K2]) (x2 may be NULL, K2 = 0). */
+int sg2_linear_fwd(const float* x1, int K1, const float* x2, int K2, const float* w, const float* bias, void* out,
+                   int out_bf16, int M, int N, void* stream);
+int sg2_linear_bwd_w(const void* dy, int dy_bf16, const float* x1, int K1, const float* x2, int K2, float* dw,
+                     float* dbias, int M, int N, int accumulate, void* stream);
+int sg2_linear_bwd_x(const void* dy, int dy_bf16, const float* w, float* dx /* [M][Kout], overwritten */, int M, int N,
+                     int K, int Kout, void* stream);
+/* CA_NET GLU + reparameterisation (model.py:183-195): fc [B][4E] -> mu, logvar, c = eps*exp(.5 logvar)+mu */
+int sg2_ca_glu_reparam_fwd(const float* fc, const float* eps, float* mu, float* logvar, float* c, int B, int E,
+                           void* stream);
+int sg2_ca_glu_reparam_bwd(const float* fc, const float* eps, const float* dmu, const float* dlogvar, const float* dc,
+                           float* dfc, int B, int E, void* stream);
+int sg2_chw_hwc_bf16(const void* in, void* out, int B, int C, int HW, int to_hwc, void* stream);
+/* D logits: conv k4 s4 C->1 + bias + sigmoid on a 4x4 map (model.py:414-422) */
+int sg2_logits_fwd(const void* x, const float* w, const float* bias, float* prob, int B, int HW, int C, void* stream);
+int sg2_logits_bwd(const float* dprob, const float* prob, const void* x, const float* w, void* dx, int dx_accumulate,
+                   float* dw /* += */, float* dbias /* += */, int B, int HW, int C, void* stream);
+/* Adam (betas from trainer.py:236-252) fused with the generator EMA (trainer.py:571-572; avg may be NULL) */
+int sg2_adam_ema(float* p, const float* g, float* m, float* v, float* avg, long long n, float lr, float beta1,
+                 float beta2, float eps, int step, float ema_decay, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,513 @@
+// Host side of the convolution entry points: tap tables, TMA tensor maps, launch geometry.
+// Reference constructs replaced: nn.Conv2d 3x3 (model.py:125-128), nn.Upsample+conv3x3 (model.py:133-140),
+// nn.Conv2d 4x4 s2 (model.py:369-398) — forward, data gradient and weight gradient.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/sg2b200.h"
+#include "common.cuh"
+#include "igemm.cuh"
+
+namespace sg2 {
+
+thread_local char g_err[512] = "";
+
+// ------------------------------------------------------------------------------------------ driver entry
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// A strided NHWC view: element (b, y, x, c) lives at base[b*sb + y*sy + x*sx + c] (bf16 elements).
+struct View {
+  const __nv_bfloat16* base;
+  int C, W, H, B;
+  long long sx, sy, sb;
+};
+static View dense_view(const void* p, int B, int H, int W, int C) {
+  return View{reinterpret_cast<const __nv_bfloat16*>(p), C, W, H, B, (long long)C, (long long)W * C,
+              (long long)H * W * C};
+}
+// Parity plane (py, px) of a view with even H, W: pixels (2i+py, 2j+px).
+static View plane_view(const View& v, int py, int px) {
+  View r = v;
+  r.base = v.base + py * v.sy + px * v.sx;
+  r.W = v.W / 2;
+  r.H = v.H / 2;
+  r.sx = 2 * v.sx;
+  r.sy = 2 * v.sy;
+  return r;
+}
+
+static CUtensorMapSwizzle sw_enum(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                      : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                     : (bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
+}
+
+static int make_act_map(CUtensorMap* m, const View& v, int boxC, int tw, int th, int nb) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) SG2_FAIL(SG2_EDRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.B};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sx * 2, (cuuint64_t)v.sy * 2, (cuuint64_t)v.sb * 2};
+  cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(v.base) & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15))
+    SG2_FAIL(SG2_EINVAL, "activation view not 16-byte aligned (C=%d)", v.C);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(v.base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw_enum(boxC * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    SG2_FAIL(SG2_EDRIVER, "cuTensorMapEncodeTiled(act) failed: %d (C=%d W=%d H=%d B=%d box=%d,%d,%d,%d)", (int)r,
+             v.C, v.W, v.H, v.B, boxC, tw, th, nb);
+  return 0;
+}
+
+static int make_w_map(CUtensorMap* m, const void* w, long long rows, long long K, int bk, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) SG2_FAIL(SG2_EDRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw_enum(bk * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    SG2_FAIL(SG2_EDRIVER, "cuTensorMapEncodeTiled(weights) failed: %d (rows=%lld K=%lld box=%d,%d)", (int)r, rows, K,
+             bk, bn);
+  return 0;
+}
+
+// Pipeline depth: as many stages as fit the per-CTA shared-memory budget (default 100 KB so that two CTAs
+// co-reside per SM and one's epilogue overlaps the other's main loop); SG2_SMEM_BUDGET_KB overrides.
+static int max_stages(int stage_bytes) {
+  static int budget_kb = [] {
+    const char* e = getenv("SG2_SMEM_BUDGET_KB");
+    int v = e ? atoi(e) : 100;
+    return v < 16 ? 16 : (v > 220 ? 220 : v);
+  }();
+  int s = budget_kb * 1024 / stage_bytes;
+  return s > 8 ? 8 : (s < 2 ? 2 : s);
+}
+
+// pixel tile {tw, th, nb} with tw*th*nb == npix over a Wg x Hg grid
+static int pick_tile(int Wg, int Hg, int npix, int* tw, int* th, int* nb) {
+  int w = (Hg == 1) ? (Wg < npix ? Wg : npix) : (Wg < 16 ? Wg : 16);
+  int h = npix / w;
+  if (h > Hg) h = Hg;
+  if (w <= 0 || h <= 0 || npix % (w * h)) SG2_FAIL(SG2_EINVAL, "no %d-pixel tile for a %dx%d grid", npix, Wg, Hg);
+  *tw = w;
+  *th = h;
+  *nb = npix / (w * h);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ gather launch
+struct GatherDesc {
+  View a[4];
+  int nmaps;
+  TapF taps[4][16];
+  int ntaps, ngroups;
+  int Cin;  // channels per tap (K per tap)
+  const void* w;
+  int N;          // output channels (weight rows per group)
+  int Wg, Hg, B;  // logical output grid per group
+  void* out;
+  long long out_off[4], osx, osy, osb;
+  int out_mode, splitk;
+};
+
+template <int BN, int BK>
+static int launch_fprop_t(const GatherDesc& d, cudaStream_t st) {
+  using Cfg = FpropCfg<BN, BK>;
+  FpropParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = pick_tile(d.Wg, d.Hg, kBlockM, &p.tw, &p.th, &p.nb))) return rc;
+  for (int i = 0; i < d.nmaps; ++i)
+    if ((rc = make_act_map(&p.tmA[i], d.a[i], BK, p.tw, p.th, p.nb))) return rc;
+  const long long K = (long long)d.ntaps * d.Cin;
+  if ((rc = make_w_map(&p.tmB, d.w, (long long)d.ngroups * d.N, K, BK, BN))) return rc;
+  memcpy(p.taps, d.taps, sizeof(p.taps));
+  p.ntaps = d.ntaps;
+  p.kchunks = d.Cin / BK;
+  p.ngroups = d.ngroups;
+  const int KB = p.ntaps * p.kchunks;
+  p.splitk = d.splitk < 1 ? 1 : (d.splitk > KB ? KB : d.splitk);
+  if (p.splitk > 1 && d.out_mode != OUT_F32_ATOMIC) SG2_FAIL(SG2_EINVAL, "split-K needs SG2_OUT_F32_ATOMIC");
+  p.tiles_x = (d.Wg + p.tw - 1) / p.tw;
+  p.tiles_y = (d.Hg + p.th - 1) / p.th;
+  p.tiles_b = (d.B + p.nb - 1) / p.nb;
+  p.Wo = d.Wg;
+  p.Ho = d.Hg;
+  p.B = d.B;
+  p.N = d.N;
+  for (int g = 0; g < 4; ++g) p.out_off[g] = d.out_off[g];
+  p.sb = d.osb;
+  p.sy = d.osy;
+  p.sx = d.osx;
+  p.out = d.out;
+  p.out_mode = d.out_mode;
+  const int smax = max_stages(Cfg::kStageBytes);
+  int stages = smax;
+  if (stages > KB / p.splitk + 1) stages = KB / p.splitk + 1;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = Cfg::smem_bytes(stages);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::smem_bytes(smax));
+    if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(fprop<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  dim3 grid(p.tiles_x * p.tiles_y * p.tiles_b, d.N / BN, p.ngroups * p.splitk);
+  igemm_fprop_kernel<BN, BK><<<grid, kNumThreads, smem, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) SG2_FAIL((int)e, "fprop<%d,%d> launch: %s", BN, BK, cudaGetErrorString(e));
+  return 0;
+}
+
+static int launch_fprop(const GatherDesc& d, cudaStream_t st) {
+  if (d.Cin % 16) SG2_FAIL(SG2_EINVAL, "K per tap (%d) must be a multiple of 16", d.Cin);
+  if (d.N % 16) SG2_FAIL(SG2_EINVAL, "N (%d) must be a multiple of 16", d.N);
+  const int bk = (d.Cin % 64 == 0) ? 64 : ((d.Cin % 32 == 0) ? 32 : 16);
+  const int bn = (d.N % 256 == 0) ? 256 : ((d.N % 128 == 0) ? 128 : ((d.N % 64 == 0) ? 64 : ((d.N % 32 == 0) ? 32 : 16)));
+#define SG2_CASE(BN_, BK_) \
+  if (bn == BN_ && bk == BK_) return launch_fprop_t<BN_, BK_>(d, st);
+  SG2_CASE(256, 64) SG2_CASE(128, 64) SG2_CASE(64, 64) SG2_CASE(32, 64)
+  SG2_CASE(256, 32) SG2_CASE(128, 32) SG2_CASE(64, 32) SG2_CASE(32, 32)
+  SG2_CASE(256, 16) SG2_CASE(128, 16) SG2_CASE(64, 16) SG2_CASE(32, 16)
+  SG2_CASE(16, 64) SG2_CASE(16, 32) SG2_CASE(16, 16)
+#undef SG2_CASE
+  SG2_FAIL(SG2_EINVAL, "no fprop instance for BN=%d BK=%d", bn, bk);
+}
+
+static inline int fdiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }  // floor(v/2)
+
+// ------------------------------------------------------------------------------------------ wgrad launch
+struct WgradDesc {
+  View a[4], b[4];
+  int namaps, nbmaps;
+  JobW jobs[16];
+  int njobs;
+  int Wg, Hg, B;  // pixel grid of the dy views
+  int Cout, Cin;
+  float* dw;
+  int splitk;
+};
+
+template <int BN, int CWA, int CWB>
+static int launch_wgrad_t(const WgradDesc& d, cudaStream_t st) {
+  using Cfg = WgradCfg<BN, CWA, CWB>;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = pick_tile(d.Wg, d.Hg, kWgradBKP, &p.tw, &p.th, &p.nb))) return rc;
+  for (int i = 0; i < d.namaps; ++i)
+    if ((rc = make_act_map(&p.tmA[i], d.a[i], CWA, p.tw, p.th, p.nb))) return rc;
+  for (int i = 0; i < d.nbmaps; ++i)
+    if ((rc = make_act_map(&p.tmB[i], d.b[i], CWB, p.tw, p.th, p.nb))) return rc;
+  memcpy(p.jobs, d.jobs, sizeof(p.jobs));
+  p.njobs = d.njobs;
+  p.tiles_x = (d.Wg + p.tw - 1) / p.tw;
+  p.tiles_y = (d.Hg + p.th - 1) / p.th;
+  p.tiles_b = (d.B + p.nb - 1) / p.nb;
+  const int PT = p.tiles_x * p.tiles_y * p.tiles_b;
+  p.splitk = d.splitk < 1 ? 1 : (d.splitk > PT ? PT : d.splitk);
+  p.Cout = d.Cout;
+  p.Cin = d.Cin;
+  p.dw = d.dw;
+  const int smax = max_stages(Cfg::kStageBytes);
+  int stages = smax;
+  if (stages > PT / p.splitk + 1) stages = PT / p.splitk + 1;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_kernel<BN, CWA, CWB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes(smax));
+    if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  const int m_tiles = (d.Cout + kBlockM - 1) / kBlockM, n_tiles = (d.Cin + BN - 1) / BN;
+  dim3 grid(m_tiles * n_tiles, d.njobs, p.splitk);
+  igemm_wgrad_kernel<BN, CWA, CWB><<<grid, kNumThreads, Cfg::smem_bytes(stages), st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) SG2_FAIL((int)e, "wgrad<%d,%d,%d> launch: %s", BN, CWA, CWB, cudaGetErrorString(e));
+  return 0;
+}
+
+static int launch_wgrad(const WgradDesc& d, cudaStream_t st) {
+  if (d.Cout % 32 || d.Cin % 16) SG2_FAIL(SG2_EINVAL, "wgrad needs Cout %% 32 == 0 and Cin %% 16 == 0 (%d, %d)", d.Cout, d.Cin);
+  const int cwa = (d.Cout % 64 == 0) ? 64 : 32;
+  const int cwb = (d.Cin % 64 == 0) ? 64 : ((d.Cin % 32 == 0) ? 32 : 16);
+  const int bn = d.Cin <= 16 ? 16 : (d.Cin <= 32 ? 32 : (d.Cin <= 64 ? 64 : (d.Cin <= 128 ? 128 : 256)));
+#define SG2_CASE(BN_, A_, B_) \
+  if (bn == BN_ && cwa == A_ && cwb == B_) return launch_wgrad_t<BN_, A_, B_>(d, st);
+  SG2_CASE(256, 64, 64) SG2_CASE(128, 64, 64) SG2_CASE(64, 64, 64)
+  SG2_CASE(256, 64, 32) SG2_CASE(128, 64, 32) SG2_CASE(64, 64, 32) SG2_CASE(32, 64, 32)
+  SG2_CASE(256, 32, 64) SG2_CASE(128, 32, 64) SG2_CASE(64, 32, 64)
+  SG2_CASE(256, 32, 32) SG2_CASE(128, 32, 32) SG2_CASE(64, 32, 32) SG2_CASE(32, 32, 32)
+  SG2_CASE(16, 64, 16) SG2_CASE(16, 32, 16)
+#undef SG2_CASE
+  SG2_FAIL(SG2_EINVAL, "no wgrad instance for BN=%d CWA=%d CWB=%d", bn, cwa, cwb);
+}
+
+// kh of the 4x4-s2 filter that connects input parity p (row 2i+p) with output row i + d:  see dgrad below.
+static const int kS2_kh[2][2] = {{1, 3}, {2, 0}};   // [parity][a]
+static const int kS2_dy[2][2] = {{0, -1}, {0, 1}};  // [parity][a] : output row = i + dy
+
+}  // namespace sg2
+
+using namespace sg2;
+
+extern "C" {
+
+int sg2_version(void) { return 1; }
+const char* sg2_last_error(void) { return g_err; }
+
+int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mode, int B, int H, int W, int Cin,
+                   int Cout, int splitk, void* stream) {
+  GatherDesc d;
+  memset(&d, 0, sizeof(d));
+  d.Cin = Cin;
+  d.w = wpk;
+  d.N = Cout;
+  d.B = B;
+  d.out = y;
+  d.out_mode = out_mode;
+  d.splitk = splitk;
+  const View xv = dense_view(x, B, H, W, Cin);
+  switch (kind) {
+    case SG2_CONV3x3:
+    case SG2_GEMM: {
+      d.a[0] = xv;
+      d.nmaps = 1;
+      d.ngroups = 1;
+      if (kind == SG2_GEMM) {
+        d.ntaps = 1;
+        d.taps[0][0] = TapF{0, 0, 0, 0};
+      } else {
+        d.ntaps = 9;
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw) d.taps[0][kh * 3 + kw] = TapF{0, (int8_t)(kh - 1), (int8_t)(kw - 1), 0};
+      }
+      d.Wg = W;
+      d.Hg = H;
+      d.osx = Cout;
+      d.osy = (long long)W * Cout;
+      d.osb = (long long)H * W * Cout;
+      break;
+    }
+    case SG2_UPCONV3x3: {
+      // y[2i+py, 2j+px] = sum_{a,b in {0,1}} Wc[py,px][a,b] . x[i+py-1+a, j+px-1+b]
+      d.a[0] = xv;
+      d.nmaps = 1;
+      d.ngroups = 4;
+      d.ntaps = 4;
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          const int g = py * 2 + px;
+          for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b) d.taps[g][a * 2 + b] = TapF{0, (int8_t)(py - 1 + a), (int8_t)(px - 1 + b), 0};
+          d.out_off[g] = ((long long)py * 2 * W + px) * Cout;
+        }
+      d.Wg = W;
+      d.Hg = H;
+      d.osx = 2LL * Cout;
+      d.osy = 2LL * (2 * W) * Cout;
+      d.osb = 4LL * H * W * Cout;
+      break;
+    }
+    case SG2_CONV4x4S2: {
+      if ((H | W) & 1) SG2_FAIL(SG2_EINVAL, "conv4x4s2 needs even H, W");
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) d.a[py * 2 + px] = plane_view(xv, py, px);
+      d.nmaps = 4;
+      d.ngroups = 1;
+      d.ntaps = 16;
+      for (int kh = 0; kh < 4; ++kh)
+        for (int kw = 0; kw < 4; ++kw) {
+          const int ry = kh - 1, rx = kw - 1;  // input row = 2*oy + ry
+          d.taps[0][kh * 4 + kw] = TapF{(int8_t)((ry & 1) * 2 + (rx & 1)), (int8_t)fdiv2(ry), (int8_t)fdiv2(rx), 0};
+        }
+      d.Wg = W / 2;
+      d.Hg = H / 2;
+      d.osx = Cout;
+      d.osy = (long long)(W / 2) * Cout;
+      d.osb = (long long)(H / 2) * (W / 2) * Cout;
+      break;
+    }
+    default:
+      SG2_FAIL(SG2_EINVAL, "unknown conv kind %d", kind);
+  }
+  return launch_fprop(d, (cudaStream_t)stream);
+}
+
+int sg2_conv_dgrad(int kind, const void* dy, const void* wpkT, void* dx, int out_mode, int B, int H, int W, int Cin,
+                   int Cout, int splitk, void* stream) {
+  GatherDesc d;
+  memset(&d, 0, sizeof(d));
+  d.Cin = Cout;  // contraction runs over the forward output channels
+  d.w = wpkT;
+  d.N = Cin;
+  d.B = B;
+  d.out = dx;
+  d.out_mode = out_mode;
+  d.splitk = splitk;
+  switch (kind) {
+    case SG2_CONV3x3:
+    case SG2_GEMM: {
+      d.a[0] = dense_view(dy, B, H, W, Cout);
+      d.nmaps = 1;
+      d.ngroups = 1;
+      if (kind == SG2_GEMM) {
+        d.ntaps = 1;
+        d.taps[0][0] = TapF{0, 0, 0, 0};
+      } else {
+        // dx[y,x] = sum_{kh,kw} W[:, :, kh, kw]^T . dy[y-(kh-1), x-(kw-1)]
+        d.ntaps = 9;
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw) d.taps[0][kh * 3 + kw] = TapF{0, (int8_t)(1 - kh), (int8_t)(1 - kw), 0};
+      }
+      d.Wg = W;
+      d.Hg = H;
+      d.osx = Cin;
+      d.osy = (long long)W * Cin;
+      d.osb = (long long)H * W * Cin;
+      break;
+    }
+    case SG2_UPCONV3x3: {
+      // dx[u,v] = sum_{py,px,a,b} Wc[py,px][a,b]^T . P_{py,px}[u+1-py-a, v+1-px-b],  P = parity planes of dy (2H x 2W)
+      const View dv = dense_view(dy, B, 2 * H, 2 * W, Cout);
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) d.a[py * 2 + px] = plane_view(dv, py, px);
+      d.nmaps = 4;
+      d.ngroups = 1;
+      d.ntaps = 16;
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px)
+          for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b)
+              d.taps[0][(py * 2 + px) * 4 + a * 2 + b] =
+                  TapF{(int8_t)(py * 2 + px), (int8_t)(1 - py - a), (int8_t)(1 - px - b), 0};
+      d.Wg = W;
+      d.Hg = H;
+      d.osx = Cin;
+      d.osy = (long long)W * Cin;
+      d.osb = (long long)H * W * Cin;
+      break;
+    }
+    case SG2_CONV4x4S2: {
+      // dx[2i+py, 2j+px] = sum_{a,b} W[:, :, kh(py,a), kw(px,b)]^T . dy[i+dy(py,a), j+dx(px,b)]
+      if ((H | W) & 1) SG2_FAIL(SG2_EINVAL, "conv4x4s2 needs even H, W");
+      d.a[0] = dense_view(dy, B, H / 2, W / 2, Cout);
+      d.nmaps = 1;
+      d.ngroups = 4;
+      d.ntaps = 4;
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          const int g = py * 2 + px;
+          for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b)
+              d.taps[g][a * 2 + b] = TapF{0, (int8_t)kS2_dy[py][a], (int8_t)kS2_dy[px][b], 0};
+          d.out_off[g] = ((long long)py * W + px) * Cin;
+        }
+      d.Wg = W / 2;
+      d.Hg = H / 2;
+      d.osx = 2LL * Cin;
+      d.osy = 2LL * W * Cin;
+      d.osb = (long long)H * W * Cin;
+      break;
+    }
+    default:
+      SG2_FAIL(SG2_EINVAL, "unknown conv kind %d", kind);
+  }
+  return launch_fprop(d, (cudaStream_t)stream);
+}
+
+int sg2_conv_wgrad(int kind, const void* x, const void* dy, float* dwpk, int B, int H, int W, int Cin, int Cout,
+                   int splitk, void* stream) {
+  WgradDesc d;
+  memset(&d, 0, sizeof(d));
+  d.B = B;
+  d.Cout = Cout;
+  d.Cin = Cin;
+  d.dw = dwpk;
+  d.splitk = splitk;
+  const View xv = dense_view(x, B, H, W, Cin);
+  switch (kind) {
+    case SG2_CONV3x3:
+    case SG2_GEMM: {
+      d.a[0] = dense_view(dy, B, H, W, Cout);
+      d.b[0] = xv;
+      d.namaps = d.nbmaps = 1;
+      if (kind == SG2_GEMM) {
+        d.njobs = 1;
+        d.jobs[0] = JobW{0, 0, 0, 0};
+      } else {
+        d.njobs = 9;
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw) d.jobs[kh * 3 + kw] = JobW{0, 0, (int8_t)(kh - 1), (int8_t)(kw - 1)};
+      }
+      d.Wg = W;
+      d.Hg = H;
+      break;
+    }
+    case SG2_UPCONV3x3: {
+      const View dv = dense_view(dy, B, 2 * H, 2 * W, Cout);
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) d.a[py * 2 + px] = plane_view(dv, py, px);
+      d.b[0] = xv;
+      d.namaps = 4;
+      d.nbmaps = 1;
+      d.njobs = 16;
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px)
+          for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b)
+              d.jobs[(py * 2 + px) * 4 + a * 2 + b] =
+                  JobW{(int8_t)(py * 2 + px), 0, (int8_t)(py - 1 + a), (int8_t)(px - 1 + b)};
+      d.Wg = W;
+      d.Hg = H;
+      break;
+    }
+    case SG2_CONV4x4S2: {
+      if ((H | W) & 1) SG2_FAIL(SG2_EINVAL, "conv4x4s2 needs even H, W");
+      d.a[0] = dense_view(dy, B, H / 2, W / 2, Cout);
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) d.b[py * 2 + px] = plane_view(xv, py, px);
+      d.namaps = 1;
+      d.nbmaps = 4;
+      d.njobs = 16;
+      for (int kh = 0; kh < 4; ++kh)
+        for (int kw = 0; kw < 4; ++kw) {
+          const int ry = kh - 1, rx = kw - 1;
+          d.jobs[kh * 4 + kw] = JobW{0, (int8_t)((ry & 1) * 2 + (rx & 1)), (int8_t)fdiv2(ry), (int8_t)fdiv2(rx)};
+        }
+      d.Wg = W / 2;
+      d.Hg = H / 2;
+      break;
+    }
+    default:
+      SG2_FAIL(SG2_EINVAL, "unknown conv kind %d", kind);
+  }
+  return launch_wgrad(d, (cudaStream_t)stream);
+}
+
+}  // extern "C"

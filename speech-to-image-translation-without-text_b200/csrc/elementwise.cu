@@ -1,0 +1,776 @@
+// Bandwidth-bound kernels around the convolutions: weight packing, BatchNorm statistics / apply fused with
+// GLU / LeakyReLU / residual (forward and backward), c_code concat, image-head tanh, layout casts.
+// All activations are NHWC bf16 viewed as [P pixels][C channels]; every thread moves 128-bit vectors
+// (8 channels) and consecutive threads touch consecutive 16-byte segments (fully coalesced).
+// Reference constructs: nn.BatchNorm2d/1d + GLU (model.py:112-122,133-150), LeakyReLU (model.py:358-376),
+// torch.cat of the broadcast c_code (model.py:274-277,431-434), nn.Tanh heads (model.py:291-294).
+#include <cstdio>
+
+#include "../../include/sg2b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+#define EW_FAIL SG2_FAIL
+
+namespace sg2 {
+
+static inline int launch_ok(const char* what) { SG2_LAUNCH_OK(what); }
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+  v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// Column-vector geometry shared by the [P][C] kernels: a block covers `cpb` 8-channel columns x `rpb` pixel rows.
+struct Geo {
+  int vc, cpb, rpb;
+  dim3 grid, block;
+};
+static Geo make_geo(long long P, int C, int max_row_blocks) {
+  Geo g;
+  g.vc = C / 8;
+  g.cpb = g.vc < 256 ? g.vc : 256;
+  // round cpb down to a power of two that divides vc? vc is a multiple of 4 for every layer here; keep generic:
+  while (g.vc % g.cpb) --g.cpb;
+  g.rpb = 256 / g.cpb;
+  if (g.rpb < 1) g.rpb = 1;
+  long long rb = (P + g.rpb - 1) / g.rpb;
+  if (rb > max_row_blocks) rb = max_row_blocks;
+  if (rb < 1) rb = 1;
+  g.grid = dim3(g.vc / g.cpb, (unsigned)rb);
+  g.block = dim3(g.cpb * g.rpb);
+  return g;
+}
+
+// ============================================================================================ weights
+// kinds as in sg2b200.h; SG2_STEM4x4 = 4: conv4x4 s2 on 3 channels packed as a K=48(->64) GEMM.
+__device__ __forceinline__ int up_lo(int p, int a) { return (p == 0) ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2); }
+__device__ __forceinline__ int up_hi(int p, int a) { return (p == 0) ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2); }
+__device__ __forceinline__ int s2_kh(int p, int a) { return (p == 0) ? (a == 0 ? 1 : 3) : (a == 0 ? 2 : 0); }
+
+__global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk,
+                                    __nv_bfloat16* __restrict__ wpkT, int Cout, int Cin, int CoP, int CiP) {
+  // one thread per (co, slot, ci) of the padded fprop pack; writes both packs
+  const int slots = (kind == SG2_CONV3x3) ? 9 : ((kind == SG2_GEMM || kind == SG2_STEM4x4) ? 1 : 16);
+  const long long total = (long long)CoP * slots * CiP;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % CiP);
+    const int slot = (int)((i / CiP) % slots);
+    const int co = (int)(i / ((long long)CiP * slots));
+    const bool in = (co < Cout) && (ci < Cin);
+    float v = 0.f;
+    long long fo, to;  // offsets in wpk / wpkT
+    if (kind == SG2_STEM4x4) {
+      // GEMM over im2col rows: k = (kh*4+kw)*3 + c  (Cin == 48 == 3*16 here, CiP == 64)
+      if (in) { const int c = ci % 3, t = ci / 3; v = w[((long long)co * 3 + c) * 16 + t]; }
+      fo = (long long)co * CiP + ci;
+      to = (long long)ci * CoP + co;
+    } else if (kind == SG2_CONV3x3) {
+      if (in) v = w[((long long)co * Cin + ci) * 9 + slot];
+      fo = ((long long)co * 9 + slot) * CiP + ci;
+      to = ((long long)ci * 9 + slot) * CoP + co;
+    } else if (kind == SG2_GEMM) {
+      if (in) v = w[(long long)co * Cin + ci];
+      fo = (long long)co * CiP + ci;
+      to = (long long)ci * CoP + co;
+    } else if (kind == SG2_CONV4x4S2) {
+      const int kh = slot >> 2, kw = slot & 3;
+      if (in) v = w[((long long)co * Cin + ci) * 16 + slot];
+      fo = ((long long)co * 16 + slot) * CiP + ci;
+      // dgrad pack [g=(py,px)][ci][a*2+b][co] with kh = s2_kh(py,a)
+      const int py = (kh == 1 || kh == 3) ? 0 : 1, a = (kh == 1 || kh == 2) ? 0 : 1;
+      const int px = (kw == 1 || kw == 3) ? 0 : 1, b = (kw == 1 || kw == 2) ? 0 : 1;
+      to = ((((long long)(py * 2 + px) * CiP + ci) * 4) + a * 2 + b) * CoP + co;
+    } else {  // SG2_UPCONV3x3: slot = (py*2+px)*4 + a*2+b
+      const int g = slot >> 2, a = (slot >> 1) & 1, b = slot & 1, py = g >> 1, px = g & 1;
+      if (in) {
+        const float* wp = w + ((long long)co * Cin + ci) * 9;
+        for (int kh = up_lo(py, a); kh <= up_hi(py, a); ++kh)
+          for (int kw = up_lo(px, b); kw <= up_hi(px, b); ++kw) v += wp[kh * 3 + kw];
+      }
+      fo = ((((long long)g * CoP + co) * 4) + (a * 2 + b)) * CiP + ci;
+      to = ((long long)ci * 16 + slot) * CoP + co;
+    }
+    const __nv_bfloat16 bv = __float2bfloat16_rn(v);
+    if (wpk) wpk[fo] = bv;
+    if (wpkT) wpkT[to] = bv;
+  }
+}
+
+__global__ void unpack_wgrad_kernel(int kind, const float* __restrict__ dwpk, float* __restrict__ grad, int Cout,
+                                    int Cin, int CoP, int CiP, int accumulate) {
+  const int kk = (kind == SG2_CONV3x3 || kind == SG2_UPCONV3x3) ? 9 : ((kind == SG2_GEMM) ? 1 : 16);
+  const int jobs = (kind == SG2_CONV3x3) ? 9 : ((kind == SG2_GEMM || kind == SG2_STEM4x4) ? 1 : 16);
+  const long long total = (kind == SG2_STEM4x4) ? (long long)Cout * 48 : (long long)Cout * Cin * kk;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (kind == SG2_STEM4x4) {  // grad[co][c][t] <- dwpk[co][0][t*3 + c]
+      const int t = (int)(i % 16), c = (int)((i / 16) % 3), co = (int)(i / 48);
+      const float v = dwpk[(long long)co * CiP + t * 3 + c];
+      if (accumulate) grad[i] += v; else grad[i] = v;
+      continue;
+    }
+    const int t = (int)(i % kk);
+    const int ci = (int)((i / kk) % Cin);
+    const int co = (int)(i / ((long long)kk * Cin));
+    const float* row = dwpk + (long long)co * jobs * CiP + ci;
+    float v = 0.f;
+    if (kind == SG2_UPCONV3x3) {
+      const int kh = t / 3, kw = t % 3;
+      for (int py = 0; py < 2; ++py)
+        for (int a = 0; a < 2; ++a) {
+          if (kh < up_lo(py, a) || kh > up_hi(py, a)) continue;
+          for (int px = 0; px < 2; ++px)
+            for (int b = 0; b < 2; ++b) {
+              if (kw < up_lo(px, b) || kw > up_hi(px, b)) continue;
+              v += row[(long long)((py * 2 + px) * 4 + a * 2 + b) * CiP];
+            }
+        }
+    } else {
+      v = row[(long long)t * CiP];
+    }
+    if (accumulate) grad[i] += v; else grad[i] = v;
+  }
+}
+
+// ============================================================================================ BN statistics
+__global__ void bn_stats_kernel(const uint4* __restrict__ x, long long P, int vc, int cpb, int rpb,
+                                double* __restrict__ sums, int C) {
+  const int col = blockIdx.x * cpb + threadIdx.x % cpb;
+  const int rl = threadIdx.x / cpb;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += (long long)gridDim.y * rpb) {
+    float f[8];
+    unpack8(x[r * vc + col], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+  }
+  __shared__ float sh[2][256][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sh[0][threadIdx.x][j] = s[j]; sh[1][threadIdx.x][j] = q[j]; }
+  __syncthreads();
+  if (rl == 0) {
+    for (int k = 1; k < rpb; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += sh[0][threadIdx.x + k * cpb][j]; q[j] += sh[1][threadIdx.x + k * cpb][j]; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sums[col * 8 + j], (double)s[j]);
+      atomicAdd(&sums[C + col * 8 + j], (double)q[j]);
+    }
+  }
+}
+
+// mean / rstd from the fp64 sums; updates running stats the way nn.BatchNorm does (momentum, unbiased var);
+// zeroes the sums for the next user.
+__global__ void bn_finalize_kernel(double* __restrict__ sums, long long P, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ rmean,
+                                   float* __restrict__ rvar, long long* __restrict__ nbt) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  const double m = sums[c] / (double)P;
+  double var = sums[C + c] / (double)P - m * m;
+  if (var < 0) var = 0;
+  mean[c] = (float)m;
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (rmean) {
+    const double unb = P > 1 ? var * (double)P / (double)(P - 1) : var;
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)m;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+  }
+  sums[c] = 0.0;
+  sums[C + c] = 0.0;
+}
+
+__global__ void bn_eval_prepare_kernel(const float* rmean, const float* rvar, float eps, float* mean, float* rstd,
+                                       int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { mean[c] = rmean[c]; rstd[c] = rsqrtf(rvar[c] + eps); }
+}
+
+// ============================================================================================ BN apply (+act)
+enum { ACT_NONE = 0, ACT_GLU = 1, ACT_LRELU = 2 };
+
+// out = act(bn(x)) (+ residual).  GLU: out[:, c] = bn(x)[:, c] * sigmoid(bn(x)[:, c + C/2]), out has C/2 channels.
+template <int ACT>
+__global__ void bn_act_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ mean,
+                                  const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, const uint4* __restrict__ residual,
+                                  uint4* __restrict__ out, long long P, int vc_in, int vc_out, int cpb, int rpb,
+                                  int has_bn) {
+  const int col = blockIdx.x * cpb + threadIdx.x % cpb;  // output vector column
+  const int rl = threadIdx.x / cpb;
+  float sc0[8], sh0[8], sc1[8], sh1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = col * 8 + j;
+    if (has_bn) {
+      sc0[j] = gamma[c] * rstd[c];
+      sh0[j] = beta[c] - mean[c] * sc0[j];
+    } else {
+      sc0[j] = 1.f; sh0[j] = 0.f;
+    }
+    if (ACT == ACT_GLU) {
+      const int c2 = c + vc_out * 8;
+      sc1[j] = gamma[c2] * rstd[c2];
+      sh1[j] = beta[c2] - mean[c2] * sc1[j];
+    }
+  }
+  for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += (long long)gridDim.y * rpb) {
+    float a[8], o[8];
+    unpack8(x[r * vc_in + col], a);
+    if (ACT == ACT_GLU) {
+      float g[8];
+      unpack8(x[r * vc_in + col + vc_out], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (a[j] * sc0[j] + sh0[j]) * sigmoidf_(g[j] * sc1[j] + sh1[j]);
+    } else if (ACT == ACT_LRELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float z = a[j] * sc0[j] + sh0[j]; o[j] = z > 0.f ? z : 0.2f * z; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = a[j] * sc0[j] + sh0[j];
+      if (residual) {
+        float rr[8];
+        unpack8(residual[r * vc_out + col], rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += rr[j];
+      }
+    }
+    out[r * vc_out + col] = pack8(o);
+  }
+}
+
+// dz = d(bn output) for one output vector column. Returns dz (and for GLU the gate half's dz in dz2), xhat's.
+template <int ACT>
+__device__ __forceinline__ void bn_act_dz(const float (&a)[8], const float (&g)[8], const float (&d)[8],
+                                          const float (&sc0)[8], const float (&sh0)[8], const float (&sc1)[8],
+                                          const float (&sh1)[8], float (&dz0)[8], float (&dz1)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (ACT == ACT_GLU) {
+      const float za = a[j] * sc0[j] + sh0[j];
+      const float s = sigmoidf_(g[j] * sc1[j] + sh1[j]);
+      dz0[j] = d[j] * s;
+      dz1[j] = d[j] * za * s * (1.f - s);
+    } else if (ACT == ACT_LRELU) {
+      const float z = a[j] * sc0[j] + sh0[j];
+      dz0[j] = z > 0.f ? d[j] : 0.2f * d[j];
+    } else {
+      dz0[j] = d[j];
+    }
+  }
+}
+
+// pass 1: sums[0][c] = sum dz, sums[1][c] = sum dz * xhat   (per input channel c, fp64 atomics)
+template <int ACT>
+__global__ void bn_act_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dout,
+                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta, long long P,
+                                         int vc_in, int vc_out, int cpb, int rpb, double* __restrict__ sums, int C) {
+  const int col = blockIdx.x * cpb + threadIdx.x % cpb;
+  const int rl = threadIdx.x / cpb;
+  float sc0[8], sh0[8], sc1[8], sh1[8], m0[8], r0[8], m1[8], r1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = col * 8 + j;
+    m0[j] = mean[c]; r0[j] = rstd[c];
+    sc0[j] = gamma[c] * r0[j]; sh0[j] = beta[c] - m0[j] * sc0[j];
+    if (ACT == ACT_GLU) {
+      const int c2 = c + vc_out * 8;
+      m1[j] = mean[c2]; r1[j] = rstd[c2];
+      sc1[j] = gamma[c2] * r1[j]; sh1[j] = beta[c2] - m1[j] * sc1[j];
+    } else { m1[j] = r1[j] = sc1[j] = sh1[j] = 0.f; }
+  }
+  float s0[8], t0[8], s1[8], t1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s0[j] = t0[j] = s1[j] = t1[j] = 0.f;
+  for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += (long long)gridDim.y * rpb) {
+    float a[8], g[8], d[8], dz0[8], dz1[8];
+    unpack8(x[r * vc_in + col], a);
+    if (ACT == ACT_GLU) unpack8(x[r * vc_in + col + vc_out], g);
+    unpack8(dout[r * vc_out + col], d);
+    bn_act_dz<ACT>(a, g, d, sc0, sh0, sc1, sh1, dz0, dz1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s0[j] += dz0[j]; t0[j] += dz0[j] * (a[j] - m0[j]) * r0[j];
+      if (ACT == ACT_GLU) { s1[j] += dz1[j]; t1[j] += dz1[j] * (g[j] - m1[j]) * r1[j]; }
+    }
+  }
+  __shared__ float sh[4][256][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sh[0][threadIdx.x][j] = s0[j]; sh[1][threadIdx.x][j] = t0[j];
+    if (ACT == ACT_GLU) { sh[2][threadIdx.x][j] = s1[j]; sh[3][threadIdx.x][j] = t1[j]; }
+  }
+  __syncthreads();
+  if (rl == 0) {
+    for (int k = 1; k < rpb; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s0[j] += sh[0][threadIdx.x + k * cpb][j]; t0[j] += sh[1][threadIdx.x + k * cpb][j];
+        if (ACT == ACT_GLU) { s1[j] += sh[2][threadIdx.x + k * cpb][j]; t1[j] += sh[3][threadIdx.x + k * cpb][j]; }
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = col * 8 + j;
+      atomicAdd(&sums[c], (double)s0[j]);
+      atomicAdd(&sums[C + c], (double)t0[j]);
+      if (ACT == ACT_GLU) {
+        const int c2 = c + vc_out * 8;
+        atomicAdd(&sums[c2], (double)s1[j]);
+        atomicAdd(&sums[C + c2], (double)t1[j]);
+      }
+    }
+  }
+}
+
+// pass 2: dx = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat))
+template <int ACT>
+__global__ void bn_act_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dout,
+                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        const double* __restrict__ sums, long long P, int vc_in, int vc_out, int cpb,
+                                        int rpb, uint4* __restrict__ dx, int C) {
+  const int col = blockIdx.x * cpb + threadIdx.x % cpb;
+  const int rl = threadIdx.x / cpb;
+  const float invP = 1.f / (float)P;
+  float sc0[8], sh0[8], sc1[8], sh1[8], m0[8], r0[8], m1[8], r1[8], k0[8], k1[8], l0[8], l1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = col * 8 + j;
+    m0[j] = mean[c]; r0[j] = rstd[c];
+    sc0[j] = gamma[c] * r0[j]; sh0[j] = beta[c] - m0[j] * sc0[j];
+    k0[j] = (float)sums[c] * invP; l0[j] = (float)sums[C + c] * invP;
+    if (ACT == ACT_GLU) {
+      const int c2 = c + vc_out * 8;
+      m1[j] = mean[c2]; r1[j] = rstd[c2];
+      sc1[j] = gamma[c2] * r1[j]; sh1[j] = beta[c2] - m1[j] * sc1[j];
+      k1[j] = (float)sums[c2] * invP; l1[j] = (float)sums[C + c2] * invP;
+    } else { m1[j] = r1[j] = sc1[j] = sh1[j] = k1[j] = l1[j] = 0.f; }
+  }
+  for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += (long long)gridDim.y * rpb) {
+    float a[8], g[8], d[8], dz0[8], dz1[8], o[8];
+    unpack8(x[r * vc_in + col], a);
+    if (ACT == ACT_GLU) unpack8(x[r * vc_in + col + vc_out], g);
+    unpack8(dout[r * vc_out + col], d);
+    bn_act_dz<ACT>(a, g, d, sc0, sh0, sc1, sh1, dz0, dz1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = sc0[j] * (dz0[j] - k0[j] - (a[j] - m0[j]) * r0[j] * l0[j]);
+    dx[r * vc_in + col] = pack8(o);
+    if (ACT == ACT_GLU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = sc1[j] * (dz1[j] - k1[j] - (g[j] - m1[j]) * r1[j] * l1[j]);
+      dx[r * vc_in + col + vc_out] = pack8(o);
+    }
+  }
+}
+
+// dgamma = sum dz*xhat, dbeta = sum dz; zero the sums
+__global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, int C, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float db = (float)sums[c], dg = (float)sums[C + c];
+  if (accumulate) { dgamma[c] += dg; dbeta[c] += db; } else { dgamma[c] = dg; dbeta[c] = db; }
+  sums[c] = 0.0;
+  sums[C + c] = 0.0;
+}
+
+// LeakyReLU without BN (D stem): backward is dx = dout * (x > 0 ? 1 : 0.2)
+__global__ void lrelu_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dout, uint4* __restrict__ dx,
+                                 long long nvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float a[8], d[8];
+    unpack8(x[i], a);
+    unpack8(dout[i], d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = a[j] > 0.f ? d[j] : 0.2f * d[j];
+    dx[i] = pack8(d);
+  }
+}
+
+__global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
+                                long long nvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float x[8], y[8];
+    unpack8(a[i], x);
+    unpack8(b[i], y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    out[i] = pack8(x);
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = in[i];
+    out[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// ============================================================================================ c_code concat
+// out[b, y, x, :E] = c[b, :] ; out[b, y, x, E:] = h[b, y, x, :]     (model.py:274-277, 431-434)
+__global__ void concat_c_kernel(const float* __restrict__ c, const uint4* __restrict__ h, uint4* __restrict__ out,
+                                int B, int HW, int E, int Ch) {
+  const int ve = E / 8, vh = Ch / 8, vo = ve + vh;
+  const long long total = (long long)B * HW * vo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vo);
+    const long long pix = i / vo;
+    if (v < ve) {
+      const int b = (int)(pix / HW);
+      const float* cp = c + (long long)b * E + v * 8;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = cp[j];
+      out[i] = pack8(f);
+    } else {
+      out[i] = h[pix * vh + (v - ve)];
+    }
+  }
+}
+// dh = dcat[..., E:] ; dc[b, e] += sum_{pixels} dcat[b, pixel, e]
+__global__ void concat_c_bwd_kernel(const uint4* __restrict__ dcat, uint4* __restrict__ dh, float* __restrict__ dc,
+                                    int B, int HW, int E, int Ch) {
+  const int ve = E / 8, vh = Ch / 8, vo = ve + vh;
+  // blockIdx.y = batch sample; threads sweep that sample's pixels
+  const int b = blockIdx.y;
+  const long long base = (long long)b * HW * vo;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  // thread's fixed vector column: (threadIdx.x % vo) requires blockDim.x % vo == 0 -> handled by generic loop below
+  const long long total = (long long)HW * vo;
+  int my_v = -1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vo);
+    const long long pix = i / vo;
+    const uint4 val = dcat[base + i];
+    if (v < ve) {
+      float f[8];
+      unpack8(val, f);
+      if (my_v != v && my_v >= 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(&dc[(long long)b * E + my_v * 8 + j], acc[j]); acc[j] = 0.f; }
+      }
+      my_v = v;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    } else if (dh) {
+      dh[((long long)b * HW + pix) * vh + (v - ve)] = val;
+    }
+  }
+  if (my_v >= 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&dc[(long long)b * E + my_v * 8 + j], acc[j]);
+  }
+}
+
+// ============================================================================================ image heads / stems
+// y: [P][CP] bf16 conv output (first 3 channels valid) -> img fp32 NCHW = tanh(y)      (model.py:291-294)
+__global__ void head_tanh_fwd_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ img, int B, int HW,
+                                     int CP) {
+  const long long total = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const int p = (int)(i % HW);
+    const uint2 v = *reinterpret_cast<const uint2*>(y + i * CP);
+    img[((long long)b * 3 + 0) * HW + p] = tanhf(bf16_lo(v.x));
+    img[((long long)b * 3 + 1) * HW + p] = tanhf(bf16_hi(v.x));
+    img[((long long)b * 3 + 2) * HW + p] = tanhf(bf16_lo(v.y));
+  }
+}
+// dy[P][CP] bf16 = dimg * (1 - img^2) in channels 0..2, zero elsewhere
+__global__ void head_tanh_bwd_kernel(const float* __restrict__ dimg, const float* __restrict__ img,
+                                     __nv_bfloat16* __restrict__ dy, int B, int HW, int CP) {
+  const int vpp = CP / 8;
+  const long long total = (long long)B * HW * vpp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpp);
+    const long long pix = i / vpp;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    if (v == 0) {
+      const int b = (int)(pix / HW);
+      const int p = (int)(pix % HW);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const long long o = ((long long)b * 3 + c) * HW + p;
+        const float t = img[o];
+        f[c] = dimg[o] * (1.f - t * t);
+      }
+    }
+    reinterpret_cast<uint4*>(dy)[i] = pack8(f);
+  }
+}
+
+// D stem: conv4x4 s2 p1 on a 3-channel fp32 NCHW image == GEMM over im2col rows [P][64] (k = (kh*4+kw)*3 + c, 48 used)
+__global__ void stem_im2col_kernel(const float* __restrict__ img, uint4* __restrict__ col, int B, int S) {
+  const int So = S / 2;
+  const long long total = (long long)B * So * So * 8;  // 8 vectors of 8 bf16 per row
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i & 7);
+    const long long pix = i >> 3;
+    const int ox = (int)(pix % So);
+    const int oy = (int)((pix / So) % So);
+    const int b = (int)(pix / ((long long)So * So));
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = v * 8 + j;
+      float val = 0.f;
+      if (k < 48) {
+        const int c = k % 3, t = k / 3, kh = t >> 2, kw = t & 3;
+        const int y = 2 * oy + kh - 1, x = 2 * ox + kw - 1;
+        if (y >= 0 && y < S && x >= 0 && x < S) val = img[(((long long)b * 3 + c) * S + y) * S + x];
+      }
+      f[j] = val;
+    }
+    col[i] = pack8(f);
+  }
+}
+// dimg fp32 NCHW (=, not +=) from dcol [P][64] bf16 (gather form: no atomics)
+__global__ void stem_col2im_kernel(const __nv_bfloat16* __restrict__ dcol, float* __restrict__ dimg, int B, int S) {
+  const int So = S / 2;
+  const long long total = (long long)B * 3 * S * S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % S);
+    const int y = (int)((i / S) % S);
+    const int c = (int)((i / ((long long)S * S)) % 3);
+    const int b = (int)(i / ((long long)3 * S * S));
+    float acc = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 4; ++kh) {
+      const int ty = y + 1 - kh;
+      if (ty < 0 || (ty & 1)) continue;
+      const int oy = ty >> 1;
+      if (oy >= So) continue;
+#pragma unroll
+      for (int kw = 0; kw < 4; ++kw) {
+        const int tx = x + 1 - kw;
+        if (tx < 0 || (tx & 1)) continue;
+        const int ox = tx >> 1;
+        if (ox >= So) continue;
+        acc += __bfloat162float(dcol[(((long long)b * So + oy) * So + ox) * 64 + (kh * 4 + kw) * 3 + c]);
+      }
+    }
+    dimg[i] = acc;
+  }
+}
+
+// NHWC bf16 [B][HW][C] <-> NCHW fp32 [B][C][HW]   (x_immediate = x_code.reshape(B,-1), model.py:427-428)
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int B,
+                                             int HW, int C) {
+  const long long total = (long long)B * HW * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int p = (int)((i / C) % HW);
+    const int b = (int)(i / ((long long)C * HW));
+    out[((long long)b * C + c) * HW + p] = __bfloat162float(in[i]);
+  }
+}
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B,
+                                             int HW, int C) {
+  const long long total = (long long)B * HW * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int p = (int)((i / C) % HW);
+    const int b = (int)(i / ((long long)C * HW));
+    out[i] = __float2bfloat16_rn(in[((long long)b * C + c) * HW + p]);
+  }
+}
+
+static inline unsigned grid1d(long long n, int threads = 256) {
+  long long g = (n + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace sg2
+
+using namespace sg2;
+
+extern "C" {
+
+int sg2_pack_weights(int kind, const float* w, void* wpk, void* wpkT, int Cout, int Cin, int CoP, int CiP,
+                     void* stream) {
+  if (kind < 0 || kind > 4 || CoP < Cout || CiP < Cin) EW_FAIL(SG2_EINVAL, "pack_weights: bad arguments");
+  if (kind == SG2_STEM4x4 && Cin != 48) EW_FAIL(SG2_EINVAL, "pack_weights: stem expects Cin == 48 (3 x 4 x 4)");
+  const int slots = (kind == SG2_CONV3x3) ? 9 : ((kind == SG2_GEMM || kind == SG2_STEM4x4) ? 1 : 16);
+  const long long total = (long long)CoP * slots * CiP;
+  pack_weights_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(
+      kind, w, (__nv_bfloat16*)wpk, (__nv_bfloat16*)wpkT, Cout, Cin, CoP, CiP);
+  return launch_ok("pack_weights");
+}
+
+int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad, int Cout, int Cin, int CoP, int CiP, int accumulate,
+                     void* stream) {
+  if (kind < 0 || kind > 4) EW_FAIL(SG2_EINVAL, "unpack_wgrad: bad kind");
+  const int kk = (kind == SG2_CONV3x3 || kind == SG2_UPCONV3x3) ? 9 : ((kind == SG2_GEMM || kind == SG2_STEM4x4) ? 1 : 16);
+  unpack_wgrad_kernel<<<grid1d((long long)Cout * Cin * kk), 256, 0, (cudaStream_t)stream>>>(
+      kind, dwpk, grad, Cout, Cin, CoP, CiP, accumulate);
+  return launch_ok("unpack_wgrad");
+}
+
+int sg2_bn_stats(const void* x, long long P, int C, double* sums, void* stream) {
+  if (C % 8) EW_FAIL(SG2_EINVAL, "bn_stats: C %% 8");
+  Geo g = make_geo(P, C, 148 * 8);
+  bn_stats_kernel<<<g.grid, g.block, 0, (cudaStream_t)stream>>>((const uint4*)x, P, g.vc, g.cpb, g.rpb, sums, C);
+  return launch_ok("bn_stats");
+}
+
+int sg2_bn_finalize(double* sums, long long P, int C, float eps, float momentum, float* mean, float* rstd,
+                    float* running_mean, float* running_var, long long* num_batches_tracked, void* stream) {
+  bn_finalize_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, P, C, eps, momentum, mean, rstd,
+                                                                        running_mean, running_var,
+                                                                        num_batches_tracked);
+  return launch_ok("bn_finalize");
+}
+
+int sg2_bn_eval_prepare(const float* running_mean, const float* running_var, float eps, float* mean, float* rstd,
+                        int C, void* stream) {
+  bn_eval_prepare_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(running_mean, running_var, eps, mean,
+                                                                            rstd, C);
+  return launch_ok("bn_eval_prepare");
+}
+
+int sg2_bn_act_fwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                   const void* residual, void* out, long long P, int C, int act, void* stream) {
+  const int Cout = act == ACT_GLU ? C / 2 : C;
+  if (Cout % 8) EW_FAIL(SG2_EINVAL, "bn_act_fwd: channels %% 8");
+  Geo g = make_geo(P, Cout, 148 * 8);
+  const int has_bn = mean != nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+#define ARGS (const uint4*)x, mean, rstd, gamma, beta, (const uint4*)residual, (uint4*)out, P, C / 8, Cout / 8, g.cpb, g.rpb, has_bn
+  if (act == ACT_GLU) bn_act_fwd_kernel<ACT_GLU><<<g.grid, g.block, 0, st>>>(ARGS);
+  else if (act == ACT_LRELU) bn_act_fwd_kernel<ACT_LRELU><<<g.grid, g.block, 0, st>>>(ARGS);
+  else bn_act_fwd_kernel<ACT_NONE><<<g.grid, g.block, 0, st>>>(ARGS);
+#undef ARGS
+  return launch_ok("bn_act_fwd");
+}
+
+int sg2_bn_act_bwd(const void* x, const void* dout, const float* mean, const float* rstd, const float* gamma,
+                   const float* beta, double* sums, void* dx, float* dgamma, float* dbeta, int accumulate,
+                   long long P, int C, int act, void* stream) {
+  const int Cout = act == ACT_GLU ? C / 2 : C;
+  if (Cout % 8) EW_FAIL(SG2_EINVAL, "bn_act_bwd: channels %% 8");
+  Geo g = make_geo(P, Cout, 148 * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+#define RARGS (const uint4*)x, (const uint4*)dout, mean, rstd, gamma, beta, P, C / 8, Cout / 8, g.cpb, g.rpb, sums, C
+#define AARGS (const uint4*)x, (const uint4*)dout, mean, rstd, gamma, beta, sums, P, C / 8, Cout / 8, g.cpb, g.rpb, (uint4*)dx, C
+  if (act == ACT_GLU) {
+    bn_act_bwd_reduce_kernel<ACT_GLU><<<g.grid, g.block, 0, st>>>(RARGS);
+    bn_act_bwd_apply_kernel<ACT_GLU><<<g.grid, g.block, 0, st>>>(AARGS);
+  } else if (act == ACT_LRELU) {
+    bn_act_bwd_reduce_kernel<ACT_LRELU><<<g.grid, g.block, 0, st>>>(RARGS);
+    bn_act_bwd_apply_kernel<ACT_LRELU><<<g.grid, g.block, 0, st>>>(AARGS);
+  } else {
+    bn_act_bwd_reduce_kernel<ACT_NONE><<<g.grid, g.block, 0, st>>>(RARGS);
+    bn_act_bwd_apply_kernel<ACT_NONE><<<g.grid, g.block, 0, st>>>(AARGS);
+  }
+#undef RARGS
+#undef AARGS
+  bn_bwd_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, C, dgamma, dbeta, accumulate);
+  return launch_ok("bn_act_bwd");
+}
+
+int sg2_lrelu_bwd(const void* x, const void* dout, void* dx, long long n, void* stream) {
+  if (n % 8) EW_FAIL(SG2_EINVAL, "lrelu_bwd: n %% 8");
+  lrelu_bwd_kernel<<<grid1d(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)dout, (uint4*)dx,
+                                                                    n / 8);
+  return launch_ok("lrelu_bwd");
+}
+
+int sg2_add_bf16(const void* a, const void* b, void* out, long long n, void* stream) {
+  if (n % 8) EW_FAIL(SG2_EINVAL, "add_bf16: n %% 8");
+  add_bf16_kernel<<<grid1d(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (uint4*)out,
+                                                                   n / 8);
+  return launch_ok("add_bf16");
+}
+
+int sg2_f32_to_bf16(const float* in, void* out, long long n, void* stream) {
+  if (n % 4) EW_FAIL(SG2_EINVAL, "f32_to_bf16: n %% 4");
+  f32_to_bf16_kernel<<<grid1d(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)in, (uint2*)out, n / 4);
+  return launch_ok("f32_to_bf16");
+}
+
+int sg2_concat_c(const float* c, const void* h, void* out, int B, int HW, int E, int Ch, void* stream) {
+  if (E % 8 || Ch % 8) EW_FAIL(SG2_EINVAL, "concat_c: channels %% 8");
+  const long long total = (long long)B * HW * ((E + Ch) / 8);
+  concat_c_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(c, (const uint4*)h, (uint4*)out, B, HW, E, Ch);
+  return launch_ok("concat_c");
+}
+
+int sg2_concat_c_bwd(const void* dcat, void* dh, float* dc, int B, int HW, int E, int Ch, void* stream) {
+  if (E % 8 || Ch % 8) EW_FAIL(SG2_EINVAL, "concat_c_bwd: channels %% 8");
+  const long long per = (long long)HW * ((E + Ch) / 8);
+  unsigned gx = (unsigned)((per + 256 * 8 - 1) / (256 * 8));
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  concat_c_bwd_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>((const uint4*)dcat, (uint4*)dh, dc, B, HW, E, Ch);
+  return launch_ok("concat_c_bwd");
+}
+
+int sg2_head_tanh_fwd(const void* y, float* img, int B, int HW, int CP, void* stream) {
+  head_tanh_fwd_kernel<<<grid1d((long long)B * HW), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, img, B,
+                                                                                   HW, CP);
+  return launch_ok("head_tanh_fwd");
+}
+
+int sg2_head_tanh_bwd(const float* dimg, const float* img, void* dy, int B, int HW, int CP, void* stream) {
+  if (CP % 8) EW_FAIL(SG2_EINVAL, "head_tanh_bwd: CP %% 8");
+  head_tanh_bwd_kernel<<<grid1d((long long)B * HW * (CP / 8)), 256, 0, (cudaStream_t)stream>>>(
+      dimg, img, (__nv_bfloat16*)dy, B, HW, CP);
+  return launch_ok("head_tanh_bwd");
+}
+
+int sg2_stem_im2col(const float* img, void* col, int B, int S, void* stream) {
+  if (S % 2) EW_FAIL(SG2_EINVAL, "stem_im2col: odd image size");
+  stem_im2col_kernel<<<grid1d((long long)B * (S / 2) * (S / 2) * 8), 256, 0, (cudaStream_t)stream>>>(
+      img, (uint4*)col, B, S);
+  return launch_ok("stem_im2col");
+}
+
+int sg2_stem_col2im(const void* dcol, float* dimg, int B, int S, void* stream) {
+  stem_col2im_kernel<<<grid1d((long long)B * 3 * S * S), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dcol,
+                                                                                        dimg, B, S);
+  return launch_ok("stem_col2im");
+}
+
+int sg2_nhwc_to_nchw_f32(const void* in, float* out, int B, int HW, int C, void* stream) {
+  nhwc_bf16_to_nchw_f32_kernel<<<grid1d((long long)B * HW * C), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in, out, B, HW, C);
+  return launch_ok("nhwc_to_nchw_f32");
+}
+
+int sg2_nchw_f32_to_nhwc(const float* in, void* out, int B, int HW, int C, void* stream) {
+  nchw_f32_to_nhwc_bf16_kernel<<<grid1d((long long)B * HW * C), 256, 0, (cudaStream_t)stream>>>(
+      in, (__nv_bfloat16*)out, B, HW, C);
+  return launch_ok("nchw_f32_to_nhwc");
+}
+
+}  // extern "C"

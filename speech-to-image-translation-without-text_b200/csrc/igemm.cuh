@@ -1,0 +1,351 @@
+// Implicit-GEMM convolution kernels on tcgen05 / TMEM, operands staged by TMA (sm_100a only).
+//
+// fprop/dgrad kernel ("gather" form):
+//   out[pixel, n] = sum_{tap, c} act[pixel + shift(tap), c] * wpk[n, tap, c]
+//   A (activations) : NHWC bf16, 4-D TMA boxes {BK channels, tw, th, nb} = 128 pixels x BK, K-major, swizzled;
+//                     zero padding = TMA out-of-bounds fill; stride-2 / nearest-2x convs use parity-plane
+//                     tensor maps (strided views of the same NHWC tensor), so nothing is materialised.
+//   B (weights)     : packed [group][N][taps*Cin] bf16, 2-D TMA boxes {BK, BN}, K-major, swizzled.
+//   D (accumulator) : 128 lanes x BN fp32 columns in TMEM; epilogue warps read it with tcgen05.ld.
+//
+// wgrad kernel ("outer product over pixels" form):
+//   dw[m, job, n] += sum_{pixel} dy[pixel, m] * act[pixel + shift(job), n]
+//   Both operands are MN-major (channels contiguous, pixels = K), loaded as {CW channels, 64 pixels} boxes.
+#pragma once
+#include "ptx.cuh"
+
+namespace sg2 {
+
+constexpr int kBlockM = 128;
+constexpr int kNumThreads = 192;  // warp0: TMA producer, warp1: MMA issuer + TMEM owner, warps2-5: epilogue
+
+struct TapF {
+  int8_t map, dy, dx, pad;
+};
+
+enum OutMode : int { OUT_BF16 = 0, OUT_F32_ATOMIC = 1, OUT_F32_STORE = 2 };
+
+struct FpropParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  TapF taps[4][16];  // [group][tap]
+  int ntaps, kchunks;
+  int ngroups, splitk;
+  int tw, th, nb;
+  int tiles_x, tiles_y, tiles_b;
+  int Wo, Ho, B;
+  int N;
+  long long out_off[4];
+  long long sb, sy, sx;
+  void* out;
+  int out_mode;
+  int stages;
+};
+
+template <int BN, int BK>
+struct FpropCfg {
+  static constexpr int kSw = BK * 2;  // swizzle span in bytes (128/64/32)
+  static constexpr int kABytes = kBlockM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static size_t smem_bytes(int stages) { return size_t(stages) * kStageBytes + 1024 + 256; }
+};
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_constant__ FpropParams p) {
+  using Cfg = FpropCfg<BN, BK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(S) * Cfg::kStageBytes);
+  uint64_t* empty = full + S;
+  uint64_t* tmem_full = empty + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x;
+  t /= p.tiles_x;
+  const int ty = t % p.tiles_y;
+  const int tb = t / p.tiles_y;
+  const int x0 = tx * p.tw, y0 = ty * p.th, b0 = tb * p.nb;
+  const int n0 = blockIdx.y * BN;
+  const int g = blockIdx.z / p.splitk;
+  const int split = blockIdx.z % p.splitk;
+  const int KB = p.ntaps * p.kchunks;
+  const int kb_begin = (int)((long long)KB * split / p.splitk);
+  const int kb_end = (int)((long long)KB * (split + 1) / p.splitk);
+  const int nkb = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmA[0]);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], Cfg::kStageBytes);
+        const int kb = kb_begin + it;
+        const int tap = kb / p.kchunks;
+        const int ch = kb - tap * p.kchunks;
+        const TapF tp = p.taps[g][tap];
+        uint8_t* sa = smem + size_t(s) * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        tma_load_4d(&p.tmA[tp.map], &full[s], sa, ch * BK, x0 + tp.dx, y0 + tp.dy, b0);
+        tma_load_2d(&p.tmB, &full[s], sb, kb * BK, n0 + g * p.N);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 0, 0);
+      constexpr uint32_t swc = swizzle_code(Cfg::kSw);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + size_t(s) * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABytes;
+        const uint64_t adesc = make_smem_desc(sa, 16, 8 * Cfg::kSw, swc);
+        const uint64_t bdesc = make_smem_desc(sb, 16, 8 * Cfg::kSw, swc);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          umma_f16(tmem_base, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int xi = row % p.tw;
+    const int yi = (row / p.tw) % p.th;
+    const int bi = row / (p.tw * p.th);
+    const int x = x0 + xi, y = y0 + yi, b = b0 + bi;
+    const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
+    const long long off = p.out_off[g] + (long long)b * p.sb + (long long)y * p.sy + (long long)x * p.sx + n0;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c0, v);
+      tmem_ld_wait();
+      if (valid) {
+        if (p.out_mode == OUT_BF16) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + c0);
+#pragma unroll
+          for (int j = 0; j < (BN < 32 ? BN / 8 : 4); ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+            dst[j] = o;
+          }
+        } else if (p.out_mode == OUT_F32_ATOMIC) {
+          float* dst = reinterpret_cast<float*>(p.out) + off + c0;
+#pragma unroll
+          for (int j = 0; j < (BN < 32 ? BN : 32); ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+        } else {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + c0);
+#pragma unroll
+          for (int j = 0; j < (BN < 32 ? BN / 4 : 8); ++j)
+            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+struct JobW {
+  int8_t amap, bmap, dy, dx;
+};
+
+struct WgradParams {
+  CUtensorMap tmA[4];  // dy maps: {CWA channels, tw, th, nb} boxes
+  CUtensorMap tmB[4];  // activation maps: {CWB channels, tw, th, nb} boxes
+  JobW jobs[16];
+  int njobs;
+  int tw, th, nb;  // tw*th*nb == 64 pixels per K block
+  int tiles_x, tiles_y, tiles_b;
+  int splitk;
+  int Cout, Cin;
+  float* dw;  // [Cout][njobs][Cin]
+  int stages;
+};
+
+constexpr int kWgradBKP = 64;  // pixels per K block
+
+template <int BN, int CWA, int CWB>
+struct WgradCfg {
+  static constexpr int kAChunkBytes = kWgradBKP * CWA * 2;
+  static constexpr int kBChunkBytes = kWgradBKP * CWB * 2;
+  static constexpr int kAChunks = kBlockM / CWA;
+  static constexpr int kBChunks = BN / CWB;
+  static constexpr int kABytes = kAChunks * kAChunkBytes;  // 16 KB
+  static constexpr int kBBytes = kBChunks * kBChunkBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static size_t smem_bytes(int stages) { return size_t(stages) * kStageBytes + 1024 + 256; }
+};
+
+template <int BN, int CWA, int CWB>
+__global__ void __launch_bounds__(kNumThreads) igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using Cfg = WgradCfg<BN, CWA, CWB>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(S) * Cfg::kStageBytes);
+  uint64_t* empty = full + S;
+  uint64_t* tmem_full = empty + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int n_tiles = (p.Cin + BN - 1) / BN;
+  const int m0 = (blockIdx.x / n_tiles) * kBlockM;
+  const int n0 = (blockIdx.x % n_tiles) * BN;
+  const int job = blockIdx.y;
+  const int split = blockIdx.z;
+  const int PT = p.tiles_x * p.tiles_y * p.tiles_b;  // pixel tiles = K blocks
+  const int kb_begin = (int)((long long)PT * split / p.splitk);
+  const int kb_end = (int)((long long)PT * (split + 1) / p.splitk);
+  const int nkb = kb_end - kb_begin;
+  const int a_chunks = min(Cfg::kAChunks, (p.Cout - m0 + CWA - 1) / CWA);
+  const int b_chunks = min(Cfg::kBChunks, (p.Cin - n0 + CWB - 1) / CWB);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const JobW jb = p.jobs[job];
+      const uint32_t tx_bytes = a_chunks * Cfg::kAChunkBytes + b_chunks * Cfg::kBChunkBytes;
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], tx_bytes);
+        int t = kb_begin + it;
+        const int tx = t % p.tiles_x;
+        t /= p.tiles_x;
+        const int ty = t % p.tiles_y;
+        const int tb = t / p.tiles_y;
+        const int x0 = tx * p.tw, y0 = ty * p.th, b0 = tb * p.nb;
+        uint8_t* sa = smem + size_t(s) * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        for (int c = 0; c < a_chunks; ++c)
+          tma_load_4d(&p.tmA[jb.amap], &full[s], sa + c * Cfg::kAChunkBytes, m0 + c * CWA, x0, y0, b0);
+        for (int c = 0; c < b_chunks; ++c)
+          tma_load_4d(&p.tmB[jb.bmap], &full[s], sb + c * Cfg::kBChunkBytes, n0 + c * CWB, x0 + jb.dx, y0 + jb.dy,
+                      b0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 1, 1);
+      constexpr uint32_t swa = swizzle_code(CWA * 2), swb = swizzle_code(CWB * 2);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + size_t(s) * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABytes;
+        // MN-major: LBO = bytes between consecutive channel chunks, SBO = bytes between 8-pixel groups.
+        const uint64_t adesc = make_smem_desc(sa, Cfg::kAChunkBytes, 8 * CWA * 2, swa);
+        const uint64_t bdesc = make_smem_desc(sb, Cfg::kBChunkBytes, 8 * CWB * 2, swb);
+#pragma unroll
+        for (int k = 0; k < kWgradBKP / 16; ++k) {
+          const uint64_t ka = uint64_t((k * 16 * CWA * 2) >> 4);
+          const uint64_t kbo = uint64_t((k * 16 * CWB * 2) >> 4);
+          umma_f16(tmem_base, adesc + ka, bdesc + kbo, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    const bool valid = m < p.Cout;
+    float* rowp = p.dw + ((long long)m * p.njobs + job) * p.Cin + n0;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c0, v);
+      tmem_ld_wait();
+      if (valid && nkb > 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (n0 + c0 + j < p.Cin) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rowp + c0 + j),
+                         "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
+                         "f"(__uint_as_float(v[j + 3]))
+                         : "memory");
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace sg2

@@ -1,0 +1,329 @@
+// Small fp32 operators of the path whose cost is launch latency or weight bandwidth, not FLOPs:
+//   CA_NET fc + GLU + reparameterisation   (model.py:172-200)
+//   INIT_STAGE_G fc 228 -> 32768           (model.py:216-219)    [M = batch <= 64 rows]
+//   D logits: conv k4 s4 512 -> 1 + bias + sigmoid == one 8192-long dot product per sample (model.py:414-422)
+//   fused Adam(beta1=.5) + EMA             (trainer.py:236-252, 571-572)
+// Warp-shuffle reductions, coalesced weight reads; fp32 master weights are read directly (no bf16 copy).
+#include "../../include/sg2b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sg2 {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------------ linear (tiny M)
+// out[m][n] = sum_k x(m,k) * w[n][k] (+ bias[n]);  x(m,k) = k < K1 ? x1[m][k] : x2[m][k-K1]  (cat(c_code, z))
+// One warp per output feature n; lanes stride K (coalesced weight row); M rows in chunks of 8.
+template <bool OUT_BF16>
+__global__ void linear_fwd_kernel(const float* __restrict__ x1, int K1, const float* __restrict__ x2, int K2,
+                                  const float* __restrict__ w, const float* __restrict__ bias, void* __restrict__ out,
+                                  int M, int N) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const int K = K1 + K2;
+  const float* wr = w + (long long)n * K;
+  for (int m0 = 0; m0 < M; m0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float wv = wr[k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int m = m0 + j;
+        if (m < M) acc[j] += wv * (k < K1 ? x1[(long long)m * K1 + k] : x2[(long long)m * K2 + (k - K1)]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = warp_sum(acc[j]);
+      const int m = m0 + j;
+      if (lane == 0 && m < M) {
+        const float v = s + (bias ? bias[n] : 0.f);
+        if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[(long long)m * N + n] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float*>(out)[(long long)m * N + n] = v;
+      }
+    }
+  }
+}
+
+// dw[n][k] (+)= sum_m dy[m][n] * x(m,k);  dbias[n] (+)= sum_m dy[m][n].   thread per (n, k) pair, k fastest.
+template <bool DY_BF16>
+__global__ void linear_bwd_w_kernel(const void* __restrict__ dy, const float* __restrict__ x1, int K1,
+                                    const float* __restrict__ x2, int K2, float* __restrict__ dw,
+                                    float* __restrict__ dbias, int M, int N, int accumulate) {
+  const int K = K1 + K2;
+  const long long total = (long long)N * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int n = (int)(i / K);
+    float acc = 0.f, accb = 0.f;
+    for (int m = 0; m < M; ++m) {
+      const float d = DY_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy)[(long long)m * N + n])
+                              : reinterpret_cast<const float*>(dy)[(long long)m * N + n];
+      acc += d * (k < K1 ? x1[(long long)m * K1 + k] : x2[(long long)m * K2 + (k - K1)]);
+      accb += d;
+    }
+    if (accumulate) dw[i] += acc; else dw[i] = acc;
+    if (dbias && k == 0) { if (accumulate) dbias[n] += accb; else dbias[n] = accb; }
+  }
+}
+
+// dx[m][k] = sum_n dy[m][n] * w[n][k] for k < Kout (only the leading Kout inputs need a gradient).
+// grid.x = n-slabs; thread = k; atomics into a zeroed dx.
+template <bool DY_BF16>
+__global__ void linear_bwd_x_kernel(const void* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
+                                    int M, int N, int K, int Kout, int slab) {
+  const int k = threadIdx.x;
+  const int nb = blockIdx.x * slab;
+  const int ne = min(N, nb + slab);
+  for (int m0 = 0; m0 < M; m0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (k < Kout) {
+      for (int n = nb; n < ne; ++n) {
+        const float wv = w[(long long)n * K + k];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int m = m0 + j;
+          if (m < M) {
+            const float d = DY_BF16
+                                ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy)[(long long)m * N + n])
+                                : reinterpret_cast<const float*>(dy)[(long long)m * N + n];
+            acc[j] += d * wv;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (m0 + j < M) atomicAdd(&dx[(long long)(m0 + j) * Kout + k], acc[j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ CA_NET tail
+// fc [B][4E] -> GLU -> [B][2E] = (mu | logvar);  c = eps * exp(0.5 * logvar) + mu
+__global__ void ca_glu_reparam_fwd_kernel(const float* __restrict__ fc, const float* __restrict__ eps,
+                                          float* __restrict__ mu, float* __restrict__ logvar, float* __restrict__ c,
+                                          int B, int E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * E) return;
+  const int b = i / E, e = i % E;
+  const float* r = fc + (long long)b * 4 * E;
+  const float m = r[e] * sigm(r[2 * E + e]);
+  const float lv = r[E + e] * sigm(r[3 * E + e]);
+  mu[i] = m;
+  logvar[i] = lv;
+  c[i] = eps[i] * __expf(0.5f * lv) + m;
+}
+// dfc from (dmu, dlogvar, dc): dmu_t = dmu + dc ; dlv_t = dlogvar + dc * eps * 0.5 * exp(0.5 logvar); then GLU'.
+__global__ void ca_glu_reparam_bwd_kernel(const float* __restrict__ fc, const float* __restrict__ eps,
+                                          const float* __restrict__ dmu, const float* __restrict__ dlogvar,
+                                          const float* __restrict__ dc, float* __restrict__ dfc, int B, int E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * E) return;
+  const int b = i / E, e = i % E;
+  const float* r = fc + (long long)b * 4 * E;
+  float* o = dfc + (long long)b * 4 * E;
+  const float s_m = sigm(r[2 * E + e]), s_l = sigm(r[3 * E + e]);
+  const float lv = r[E + e] * s_l;
+  const float g_c = dc ? dc[i] : 0.f;
+  const float g_m = (dmu ? dmu[i] : 0.f) + g_c;
+  const float g_l = (dlogvar ? dlogvar[i] : 0.f) + g_c * eps[i] * 0.5f * __expf(0.5f * lv);
+  o[e] = g_m * s_m;
+  o[2 * E + e] = g_m * r[e] * s_m * (1.f - s_m);
+  o[E + e] = g_l * s_l;
+  o[3 * E + e] = g_l * r[E + e] * s_l * (1.f - s_l);
+}
+
+// ------------------------------------------------------------------------------------------ fc feature permute
+// INIT_STAGE_G: GLU output [B][C*HW] in NCHW feature order (f = c*HW + p) <-> NHWC bf16 [B][HW][C]
+__global__ void chw_to_hwc_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B,
+                                       int C, int HW, int to_hwc) {
+  const long long total = (long long)B * C * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // i indexes the HWC side (coalesced on c)
+    const int c = (int)(i % C);
+    const int p = (int)((i / C) % HW);
+    const long long b = i / ((long long)C * HW);
+    const long long j = (b * C + c) * HW + p;
+    if (to_hwc) out[i] = in[j]; else out[j] = in[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ D logits
+// prob[b] = sigmoid(bias + sum_{p,c} x[b][p][c] * w[c][p]),  x NHWC bf16 [B][HW=16][C], w fp32 OIHW [1][C][4][4]
+__global__ void logits_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                  const float* __restrict__ bias, float* __restrict__ prob, int HW, int C) {
+  const int b = blockIdx.x;
+  const int n = HW * C;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i % C, p = i / C;
+    acc += __bfloat162float(x[(long long)b * n + i]) * w[c * HW + p];
+  }
+  __shared__ float sh[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) prob[b] = sigm(v + bias[0]);
+  }
+}
+// dpre[b] = dprob[b] * p (1-p);  dx[b][p][c] (=|+=) dpre[b] * w[c][p];  dw[c][p] += sum_b dpre[b] x[b][p][c];  dbias += sum dpre
+__global__ void logits_bwd_kernel(const float* __restrict__ dprob, const float* __restrict__ prob,
+                                  const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                  __nv_bfloat16* __restrict__ dx, int dx_accumulate, float* __restrict__ dw,
+                                  float* __restrict__ dbias, int B, int HW, int C) {
+  const int n = HW * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = i % C, p = i / C;
+    const float wv = w[c * HW + p];
+    float gw = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float pr = prob[b];
+      const float dpre = dprob[b] * pr * (1.f - pr);
+      const long long o = (long long)b * n + i;
+      gw += dpre * __bfloat162float(x[o]);
+      if (dx) {
+        float v = dpre * wv;
+        if (dx_accumulate) v += __bfloat162float(dx[o]);
+        dx[o] = __float2bfloat16_rn(v);
+      }
+    }
+    if (dw) dw[c * HW + p] += gw;
+  }
+  if (dbias && blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) { const float pr = prob[b]; s += dprob[b] * pr * (1.f - pr); }
+    dbias[0] += s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ Adam (+ EMA)
+// torch.optim.Adam semantics (no amsgrad, no weight decay): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+// p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).  Optional EMA: avg = 0.999 avg + 0.001 p  (trainer.py:571-572).
+__global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, float* __restrict__ avg, long long n, float lr, float b1,
+                                float b2, float eps, float bc1, float bc2_sqrt, float ema_decay) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    const float pi = p[i] - (lr / bc1) * (mi / denom);
+    p[i] = pi;
+    if (avg) avg[i] = ema_decay * avg[i] + (1.f - ema_decay) * pi;
+  }
+}
+
+static inline unsigned grid1d(long long n, int threads = 256) {
+  long long g = (n + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace sg2
+
+using namespace sg2;
+
+extern "C" {
+
+int sg2_linear_fwd(const float* x1, int K1, const float* x2, int K2, const float* w, const float* bias, void* out,
+                   int out_bf16, int M, int N, void* stream) {
+  if (M < 1 || M > 4096) SG2_FAIL(SG2_EINVAL, "linear_fwd: M=%d", M);
+  const int wpb = 8;
+  dim3 grid((N + wpb - 1) / wpb), block(wpb * 32);
+  if (out_bf16)
+    linear_fwd_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(x1, K1, x2, K2, w, bias, out, M, N);
+  else
+    linear_fwd_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(x1, K1, x2, K2, w, bias, out, M, N);
+  SG2_LAUNCH_OK("linear_fwd");
+}
+
+int sg2_linear_bwd_w(const void* dy, int dy_bf16, const float* x1, int K1, const float* x2, int K2, float* dw,
+                     float* dbias, int M, int N, int accumulate, void* stream) {
+  const long long total = (long long)N * (K1 + K2);
+  if (dy_bf16)
+    linear_bwd_w_kernel<true><<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(dy, x1, K1, x2, K2, dw, dbias, M, N,
+                                                                               accumulate);
+  else
+    linear_bwd_w_kernel<false><<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(dy, x1, K1, x2, K2, dw, dbias, M, N,
+                                                                                accumulate);
+  SG2_LAUNCH_OK("linear_bwd_w");
+}
+
+int sg2_linear_bwd_x(const void* dy, int dy_bf16, const float* w, float* dx, int M, int N, int K, int Kout,
+                     void* stream) {
+  if (Kout > 1024 || Kout > K) SG2_FAIL(SG2_EINVAL, "linear_bwd_x: Kout=%d", Kout);
+  cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)M * Kout, (cudaStream_t)stream);
+  if (e != cudaSuccess) SG2_FAIL((int)e, "linear_bwd_x memset: %s", cudaGetErrorString(e));
+  const int slab = 64;
+  const int threads = ((Kout + 31) / 32) * 32;
+  if (dy_bf16)
+    linear_bwd_x_kernel<true><<<(N + slab - 1) / slab, threads, 0, (cudaStream_t)stream>>>(dy, w, dx, M, N, K, Kout,
+                                                                                          slab);
+  else
+    linear_bwd_x_kernel<false><<<(N + slab - 1) / slab, threads, 0, (cudaStream_t)stream>>>(dy, w, dx, M, N, K, Kout,
+                                                                                           slab);
+  SG2_LAUNCH_OK("linear_bwd_x");
+}
+
+int sg2_ca_glu_reparam_fwd(const float* fc, const float* eps, float* mu, float* logvar, float* c, int B, int E,
+                           void* stream) {
+  ca_glu_reparam_fwd_kernel<<<(B * E + 255) / 256, 256, 0, (cudaStream_t)stream>>>(fc, eps, mu, logvar, c, B, E);
+  SG2_LAUNCH_OK("ca_glu_reparam_fwd");
+}
+
+int sg2_ca_glu_reparam_bwd(const float* fc, const float* eps, const float* dmu, const float* dlogvar, const float* dc,
+                           float* dfc, int B, int E, void* stream) {
+  ca_glu_reparam_bwd_kernel<<<(B * E + 255) / 256, 256, 0, (cudaStream_t)stream>>>(fc, eps, dmu, dlogvar, dc, dfc, B,
+                                                                                  E);
+  SG2_LAUNCH_OK("ca_glu_reparam_bwd");
+}
+
+int sg2_chw_hwc_bf16(const void* in, void* out, int B, int C, int HW, int to_hwc, void* stream) {
+  chw_to_hwc_bf16_kernel<<<grid1d((long long)B * C * HW), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, C, HW, to_hwc);
+  SG2_LAUNCH_OK("chw_hwc_bf16");
+}
+
+int sg2_logits_fwd(const void* x, const float* w, const float* bias, float* prob, int B, int HW, int C,
+                   void* stream) {
+  logits_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w, bias, prob, HW, C);
+  SG2_LAUNCH_OK("logits_fwd");
+}
+
+int sg2_logits_bwd(const float* dprob, const float* prob, const void* x, const float* w, void* dx, int dx_accumulate,
+                   float* dw, float* dbias, int B, int HW, int C, void* stream) {
+  const int n = HW * C;
+  logits_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      dprob, prob, (const __nv_bfloat16*)x, w, (__nv_bfloat16*)dx, dx_accumulate, dw, dbias, B, HW, C);
+  SG2_LAUNCH_OK("logits_bwd");
+}
+
+int sg2_adam_ema(float* p, const float* g, float* m, float* v, float* avg, long long n, float lr, float beta1,
+                 float beta2, float eps, int step, float ema_decay, void* stream) {
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  adam_ema_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, avg, n, lr, beta1, beta2, eps, bc1,
+                                                              sqrtf(bc2), ema_decay);
+  SG2_LAUNCH_OK("adam_ema");
+}
+
+}  // extern "C"
