@@ -113,9 +113,19 @@ int sg2_chw_hwc_bf16(const void* in, void* out, int B, int C, int HW, int to_hwc
 int sg2_logits_fwd(const void* x, const float* w, const float* bias, float* prob, int B, int HW, int C, void* stream);
 int sg2_logits_bwd(const float* dprob, const float* prob, const void* x, const float* w, void* dx, int dx_accumulate,
                    float* dw /* += */, float* dbias /* += */, int B, int HW, int C, void* stream);
-/* Adam (betas from trainer.py:236-252) fused with the generator EMA (trainer.py:571-572; avg may be NULL) */
+/* ---- losses (trainer.py:54-58, 298-311, 394-409, 439-446, 499) ---------------------------------------------
+ * loss is a device scalar that the kernels ADD to (zero it first). probs/dprobs are contiguous [nvec][B]. */
+int sg2_gan_bce(const float* probs, const float* targets, const float* weights, int nvec, int B, float* loss,
+                float* dprobs, void* stream);
+int sg2_kl_loss(const float* mu, const float* logvar, int n, float coeff, float* loss, float* dmu, float* dlogvar,
+                void* stream);
+int sg2_cal_loss(const float* x, const int* labels, int B, int F, float* ws, float* loss, float* dx, void* stream);
+/* Adam (torch.optim.Adam semantics, betas from trainer.py:236-252) over a flat fp32 parameter bucket, fused with the
+ * generator EMA (trainer.py:571-572; avg may be NULL). sg2_adam_tick increments the device-side step counter and
+ * writes bc = {1 - beta1^t, sqrt(1 - beta2^t)} (device-resident so CUDA-graph replays stay correct). */
+int sg2_adam_tick(int* step, float* bc, float beta1, float beta2, void* stream);
 int sg2_adam_ema(float* p, const float* g, float* m, float* v, float* avg, long long n, float lr, float beta1,
-                 float beta2, float eps, int step, float ema_decay, void* stream);
+                 float beta2, float eps, const float* bc, float ema_decay, void* stream);
 
 #ifdef __cplusplus
 }

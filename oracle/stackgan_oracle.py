@@ -36,12 +36,41 @@ class Cfg:
 
 BN_EPS, BN_MOM = 1e-5, 0.1
 
+# bf16 emulation: when EMULATE_BF16 is set, every tensor the CUDA path stores in bf16 (conv operands, conv outputs,
+# activation outputs) is rounded to bf16 here too, with a straight-through gradient. The arithmetic in between stays
+# fp32 (the tensor cores accumulate in fp32). Used by the GPU parity tests to separate "kernel computes the same
+# function" (tight tolerance vs the emulating oracle) from "bf16 storage vs the fp32 reference" (quantisation gap).
+EMULATE_BF16 = False
+
+
+class emulate_bf16:
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        global EMULATE_BF16
+        self.prev, EMULATE_BF16 = EMULATE_BF16, self.on
+
+    def __exit__(self, *a):
+        global EMULATE_BF16
+        EMULATE_BF16 = self.prev
+
+
+def _q(t):
+    if not EMULATE_BF16:
+        return t
+    return t + (t.detach().bfloat16().float() - t.detach())
+
+
+def _conv(x, w, **kw):
+    return _q(F.conv2d(_q(x), _q(w), **kw))
+
 
 # --------------------------------------------------------------------------------------------- building blocks
 def glu(x):
     """model.py:112-122"""
     nc = x.size(1) // 2
-    return x[:, :nc] * torch.sigmoid(x[:, nc:])
+    return _q(x[:, :nc] * torch.sigmoid(x[:, nc:]))
 
 
 def _bn(x, sd, prefix, training):
@@ -55,23 +84,23 @@ def _bn(x, sd, prefix, training):
 def _up_block(x, sd, prefix, training):
     """upBlock, model.py:133-140: nearest 2x, conv3x3, BN, GLU"""
     x = F.interpolate(x, scale_factor=2, mode="nearest")
-    x = F.conv2d(x, sd[prefix + ".1.weight"], padding=1)
+    x = _conv(x, sd[prefix + ".1.weight"], padding=1)
     return glu(_bn(x, sd, prefix + ".2", training))
 
 
 def _block3x3_glu(x, sd, prefix, training):
     """Block3x3_relu, model.py:144-150"""
-    x = F.conv2d(x, sd[prefix + ".0.weight"], padding=1)
+    x = _conv(x, sd[prefix + ".0.weight"], padding=1)
     return glu(_bn(x, sd, prefix + ".1", training))
 
 
 def _res_block(x, sd, prefix, training):
     """ResBlock, model.py:153-169"""
-    h = F.conv2d(x, sd[prefix + ".block.0.weight"], padding=1)
+    h = _conv(x, sd[prefix + ".block.0.weight"], padding=1)
     h = glu(_bn(h, sd, prefix + ".block.1", training))
-    h = F.conv2d(h, sd[prefix + ".block.3.weight"], padding=1)
+    h = _conv(h, sd[prefix + ".block.3.weight"], padding=1)
     h = _bn(h, sd, prefix + ".block.4", training)
-    return h + x
+    return _q(h + x)
 
 
 def ca_net(sd, emb, eps, cfg):
@@ -86,34 +115,34 @@ def g_forward(sd, z, emb, eps, cfg, training=True):
     """G_NET.forward, model.py:327-354 -> ([img64, img128, img256][:BRANCH_NUM], mu, logvar)."""
     c, mu, logvar = ca_net(sd, emb, eps, cfg)
     ngf = cfg.GF_DIM * 16
-    h = F.linear(torch.cat((c, z), 1), sd["h_net1.fc.0.weight"])          # model.py:227-233
+    h = _q(F.linear(torch.cat((c, z), 1), sd["h_net1.fc.0.weight"]))      # model.py:227-233
     h = glu(_bn(h, sd, "h_net1.fc.1", training)).view(-1, ngf, 4, 4)
     for i in (1, 2, 3, 4):
         h = _up_block(h, sd, f"h_net1.upsample{i}", training)
-    imgs = [torch.tanh(F.conv2d(h, sd["img_net1.img.0.weight"], padding=1))]
+    imgs = [torch.tanh(_conv(h, sd["img_net1.img.0.weight"], padding=1))]
     for stage in range(2, cfg.BRANCH_NUM + 1):
         p = f"h_net{stage}"
         s = h.size(2)
         cc = c.view(-1, cfg.EMBEDDING_DIM, 1, 1).repeat(1, 1, s, s)        # model.py:272-277
-        h = _block3x3_glu(torch.cat((cc, h), 1), sd, p + ".jointConv", training)
+        h = _block3x3_glu(torch.cat((_q(cc), h), 1), sd, p + ".jointConv", training)
         for r in range(cfg.R_NUM):
             h = _res_block(h, sd, f"{p}.residual.{r}", training)
         h = _up_block(h, sd, p + ".upsample", training)
-        imgs.append(torch.tanh(F.conv2d(h, sd[f"img_net{stage}.img.0.weight"], padding=1)))
+        imgs.append(torch.tanh(_conv(h, sd[f"img_net{stage}.img.0.weight"], padding=1)))
     return imgs, mu, logvar
 
 
 def _down(x, sd, conv, bn, training):
-    x = F.conv2d(x, sd[conv + ".weight"], stride=2, padding=1)
+    x = _conv(x, sd[conv + ".weight"], stride=2, padding=1)
     if bn is not None:
         x = _bn(x, sd, bn, training)
-    return F.leaky_relu(x, 0.2)
+    return _q(F.leaky_relu(x, 0.2))
 
 
 def _block3x3_lrelu(x, sd, prefix, training):
     """Block3x3_leakRelu, model.py:358-365"""
-    x = F.conv2d(x, sd[prefix + ".0.weight"], padding=1)
-    return F.leaky_relu(_bn(x, sd, prefix + ".1", training), 0.2)
+    x = _conv(x, sd[prefix + ".0.weight"], padding=1)
+    return _q(F.leaky_relu(_bn(x, sd, prefix + ".1", training), 0.2))
 
 
 def d_forward(sd, img, c, which, cfg, training=True):
@@ -133,7 +162,7 @@ def d_forward(sd, img, c, which, cfg, training=True):
         x = _block3x3_lrelu(x, sd, "img_code_s64_2", training)
     x_immediate = x.reshape(x.shape[0], -1)
     cc = c.view(-1, cfg.EMBEDDING_DIM, 1, 1).repeat(1, 1, 4, 4)
-    h = _block3x3_lrelu(torch.cat((cc, x), 1), sd, "jointConv", training)
+    h = _block3x3_lrelu(torch.cat((_q(cc), x), 1), sd, "jointConv", training)
     cond = torch.sigmoid(F.conv2d(h, sd["logits.0.weight"], sd["logits.0.bias"], stride=4))
     uncond = torch.sigmoid(F.conv2d(x, sd["uncond_logits.0.weight"], sd["uncond_logits.0.bias"], stride=4))
     return [cond.view(-1), uncond.view(-1)], x_immediate

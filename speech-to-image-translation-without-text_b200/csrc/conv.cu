@@ -100,7 +100,9 @@ static int max_stages(int stage_bytes) {
     int v = e ? atoi(e) : 100;
     return v < 16 ? 16 : (v > 220 ? 220 : v);
   }();
-  int s = budget_kb * 1024 / stage_bytes;
+  // small tiles are latency-bound: prefer four co-resident CTAs per SM over a deep pipeline
+  const int kb = stage_bytes < 24 * 1024 ? (budget_kb < 48 ? budget_kb : 48) : budget_kb;
+  int s = kb * 1024 / stage_bytes;
   return s > 8 ? 8 : (s < 2 ? 2 : s);
 }
 
@@ -186,13 +188,17 @@ static int launch_fprop(const GatherDesc& d, cudaStream_t st) {
   if (d.Cin % 16) SG2_FAIL(SG2_EINVAL, "K per tap (%d) must be a multiple of 16", d.Cin);
   if (d.N % 16) SG2_FAIL(SG2_EINVAL, "N (%d) must be a multiple of 16", d.N);
   const int bk = (d.Cin % 64 == 0) ? 64 : ((d.Cin % 32 == 0) ? 32 : 16);
-  const int bn = (d.N % 256 == 0) ? 256 : ((d.N % 128 == 0) ? 128 : ((d.N % 64 == 0) ? 64 : ((d.N % 32 == 0) ? 32 : 16)));
+  const int bn = (d.N == 160 || d.N == 192)
+                     ? d.N
+                     : ((d.N % 256 == 0) ? 256
+                                         : ((d.N % 128 == 0) ? 128 : ((d.N % 64 == 0) ? 64 : ((d.N % 32 == 0) ? 32 : 16))));
 #define SG2_CASE(BN_, BK_) \
   if (bn == BN_ && bk == BK_) return launch_fprop_t<BN_, BK_>(d, st);
   SG2_CASE(256, 64) SG2_CASE(128, 64) SG2_CASE(64, 64) SG2_CASE(32, 64)
   SG2_CASE(256, 32) SG2_CASE(128, 32) SG2_CASE(64, 32) SG2_CASE(32, 32)
   SG2_CASE(256, 16) SG2_CASE(128, 16) SG2_CASE(64, 16) SG2_CASE(32, 16)
   SG2_CASE(16, 64) SG2_CASE(16, 32) SG2_CASE(16, 16)
+  SG2_CASE(160, 64) SG2_CASE(160, 32) SG2_CASE(192, 64) SG2_CASE(192, 32)
 #undef SG2_CASE
   SG2_FAIL(SG2_EINVAL, "no fprop instance for BN=%d BK=%d", bn, bk);
 }

@@ -41,10 +41,13 @@ static Geo make_geo(long long P, int C, int max_row_blocks) {
   while (g.vc % g.cpb) --g.cpb;
   g.rpb = 256 / g.cpb;
   if (g.rpb < 1) g.rpb = 1;
-  long long rb = (P + g.rpb - 1) / g.rpb;
-  if (rb > max_row_blocks) rb = max_row_blocks;
+  const int col_blocks = g.vc / g.cpb;
+  long long rb = (P + (long long)g.rpb * 8 - 1) / ((long long)g.rpb * 8);   // >= 8 row iterations per block
+  long long cap = max_row_blocks / col_blocks;
+  if (cap < 1) cap = 1;
+  if (rb > cap) rb = cap;
   if (rb < 1) rb = 1;
-  g.grid = dim3(g.vc / g.cpb, (unsigned)rb);
+  g.grid = dim3(col_blocks, (unsigned)rb);
   g.block = dim3(g.cpb * g.rpb);
   return g;
 }
@@ -105,39 +108,54 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_
   }
 }
 
+// dwpk [CoP][jobs][CiP] -> grad OIHW [Cout][Cin][kk].  One block = one output channel x 32 input channels:
+// reads run along ci (contiguous in dwpk), writes along (ci, tap) (contiguous in OIHW); the transpose goes
+// through shared memory so both sides are coalesced.
 __global__ void unpack_wgrad_kernel(int kind, const float* __restrict__ dwpk, float* __restrict__ grad, int Cout,
                                     int Cin, int CoP, int CiP, int accumulate) {
+  __shared__ float tile[16][33];
   const int kk = (kind == SG2_CONV3x3 || kind == SG2_UPCONV3x3) ? 9 : ((kind == SG2_GEMM) ? 1 : 16);
   const int jobs = (kind == SG2_CONV3x3) ? 9 : ((kind == SG2_GEMM || kind == SG2_STEM4x4) ? 1 : 16);
-  const long long total = (kind == SG2_STEM4x4) ? (long long)Cout * 48 : (long long)Cout * Cin * kk;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    if (kind == SG2_STEM4x4) {  // grad[co][c][t] <- dwpk[co][0][t*3 + c]
-      const int t = (int)(i % 16), c = (int)((i / 16) % 3), co = (int)(i / 48);
+  if (kind == SG2_STEM4x4) {  // grad[co][c][t] <- dwpk[co][0][t*3 + c]   (tiny: 64 x 48)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Cout * 48; i += gridDim.x * blockDim.x) {
+      const int t = i % 16, c = (i / 16) % 3, co = i / 48;
       const float v = dwpk[(long long)co * CiP + t * 3 + c];
       if (accumulate) grad[i] += v; else grad[i] = v;
-      continue;
     }
-    const int t = (int)(i % kk);
-    const int ci = (int)((i / kk) % Cin);
-    const int co = (int)(i / ((long long)kk * Cin));
-    const float* row = dwpk + (long long)co * jobs * CiP + ci;
-    float v = 0.f;
-    if (kind == SG2_UPCONV3x3) {
-      const int kh = t / 3, kw = t % 3;
-      for (int py = 0; py < 2; ++py)
-        for (int a = 0; a < 2; ++a) {
-          if (kh < up_lo(py, a) || kh > up_hi(py, a)) continue;
-          for (int px = 0; px < 2; ++px)
-            for (int b = 0; b < 2; ++b) {
-              if (kw < up_lo(px, b) || kw > up_hi(px, b)) continue;
-              v += row[(long long)((py * 2 + px) * 4 + a * 2 + b) * CiP];
-            }
-        }
-    } else {
-      v = row[(long long)t * CiP];
+    return;
+  }
+  const int ci_blocks = (Cin + 31) / 32;
+  for (int blk = blockIdx.x; blk < Cout * ci_blocks; blk += gridDim.x) {
+    const int co = blk / ci_blocks, ci0 = (blk % ci_blocks) * 32;
+    const float* row = dwpk + (long long)co * jobs * CiP;
+    // load: thread (j = tid / 32, lane) reads job j, channel ci0 + lane
+    for (int j = threadIdx.x >> 5; j < jobs; j += blockDim.x >> 5) {
+      const int ci = ci0 + (threadIdx.x & 31);
+      tile[j][threadIdx.x & 31] = ci < Cin ? row[(long long)j * CiP + ci] : 0.f;
     }
-    if (accumulate) grad[i] += v; else grad[i] = v;
+    __syncthreads();
+    const int nci = min(32, Cin - ci0);
+    for (int e = threadIdx.x; e < nci * kk; e += blockDim.x) {
+      const int l = e / kk, t = e % kk;
+      float v = 0.f;
+      if (kind == SG2_UPCONV3x3) {
+        const int kh = t / 3, kw = t % 3;
+        for (int py = 0; py < 2; ++py)
+          for (int a = 0; a < 2; ++a) {
+            if (kh < up_lo(py, a) || kh > up_hi(py, a)) continue;
+            for (int px = 0; px < 2; ++px)
+              for (int b = 0; b < 2; ++b) {
+                if (kw < up_lo(px, b) || kw > up_hi(px, b)) continue;
+                v += tile[(py * 2 + px) * 4 + a * 2 + b][l];
+              }
+          }
+      } else {
+        v = tile[t][l];
+      }
+      const long long o = ((long long)co * Cin + ci0) * kk + e;
+      if (accumulate) grad[o] += v; else grad[o] = v;
+    }
+    __syncthreads();
   }
 }
 
@@ -149,7 +167,21 @@ __global__ void bn_stats_kernel(const uint4* __restrict__ x, long long P, int vc
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-  for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += (long long)gridDim.y * rpb) {
+  const long long stride = (long long)gridDim.y * rpb;
+  long long r = (long long)blockIdx.y * rpb + rl;
+  for (; r + 3 * stride < P; r += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = x[(r + u * stride) * vc + col];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+    }
+  }
+  for (; r < P; r += stride) {
     float f[8];
     unpack8(x[r * vc + col], f);
 #pragma unroll
@@ -446,40 +478,48 @@ __global__ void concat_c_kernel(const float* __restrict__ c, const uint4* __rest
   }
 }
 // dh = dcat[..., E:] ; dc[b, e] += sum_{pixels} dcat[b, pixel, e]
+// grid (chunks, B). Each block sweeps a chunk of one sample's pixels: thread (pl, v) owns vector column v of the
+// c part (ve = E/8 columns) for pixel lanes pl; block-reduce over pixel lanes in smem, one atomic per channel.
 __global__ void concat_c_bwd_kernel(const uint4* __restrict__ dcat, uint4* __restrict__ dh, float* __restrict__ dc,
                                     int B, int HW, int E, int Ch) {
   const int ve = E / 8, vh = Ch / 8, vo = ve + vh;
-  // blockIdx.y = batch sample; threads sweep that sample's pixels
   const int b = blockIdx.y;
-  const long long base = (long long)b * HW * vo;
+  const int per = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  const long long base = (long long)b * HW;
+  // ---- dc reduction
+  const int lanes = blockDim.x / ve;           // pixel lanes (blockDim.x is a multiple of ve)
+  const int v = threadIdx.x % ve, pl = threadIdx.x / ve;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  // thread's fixed vector column: (threadIdx.x % vo) requires blockDim.x % vo == 0 -> handled by generic loop below
-  const long long total = (long long)HW * vo;
-  int my_v = -1;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % vo);
-    const long long pix = i / vo;
-    const uint4 val = dcat[base + i];
-    if (v < ve) {
+  if (pl < lanes) {
+    for (int p = p0 + pl; p < p1; p += lanes) {
       float f[8];
-      unpack8(val, f);
-      if (my_v != v && my_v >= 0) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { atomicAdd(&dc[(long long)b * E + my_v * 8 + j], acc[j]); acc[j] = 0.f; }
-      }
-      my_v = v;
+      unpack8(dcat[(base + p) * vo + v], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += f[j];
-    } else if (dh) {
-      dh[((long long)b * HW + pix) * vh + (v - ve)] = val;
     }
   }
-  if (my_v >= 0) {
+  __shared__ float sh[256][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&dc[(long long)b * E + my_v * 8 + j], acc[j]);
+  for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (pl == 0) {
+    for (int k = 1; k < lanes; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += sh[threadIdx.x + k * ve][j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&dc[(long long)b * E + v * 8 + j], acc[j]);
+  }
+  // ---- dh copy
+  if (dh) {
+    const long long n = (long long)(p1 - p0) * vh;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const long long p = p0 + i / vh;
+      const int c = (int)(i % vh);
+      dh[(base + p) * vh + c] = dcat[(base + p) * vo + ve + c];
+    }
   }
 }
 
@@ -631,14 +671,17 @@ int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad, int Cout, int Cin
                      void* stream) {
   if (kind < 0 || kind > 4) EW_FAIL(SG2_EINVAL, "unpack_wgrad: bad kind");
   const int kk = (kind == SG2_CONV3x3 || kind == SG2_UPCONV3x3) ? 9 : ((kind == SG2_GEMM || kind == SG2_STEM4x4) ? 1 : 16);
-  unpack_wgrad_kernel<<<grid1d((long long)Cout * Cin * kk), 256, 0, (cudaStream_t)stream>>>(
+  (void)kk;
+  long long nblk = (long long)Cout * ((Cin + 31) / 32);
+  if (nblk > 148 * 32) nblk = 148 * 32;
+  unpack_wgrad_kernel<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(
       kind, dwpk, grad, Cout, Cin, CoP, CiP, accumulate);
   return launch_ok("unpack_wgrad");
 }
 
 int sg2_bn_stats(const void* x, long long P, int C, double* sums, void* stream) {
   if (C % 8) EW_FAIL(SG2_EINVAL, "bn_stats: C %% 8");
-  Geo g = make_geo(P, C, 148 * 8);
+  Geo g = make_geo(P, C, 148 * 4);
   bn_stats_kernel<<<g.grid, g.block, 0, (cudaStream_t)stream>>>((const uint4*)x, P, g.vc, g.cpb, g.rpb, sums, C);
   return launch_ok("bn_stats");
 }
@@ -662,7 +705,7 @@ int sg2_bn_act_fwd(const void* x, const float* mean, const float* rstd, const fl
                    const void* residual, void* out, long long P, int C, int act, void* stream) {
   const int Cout = act == ACT_GLU ? C / 2 : C;
   if (Cout % 8) EW_FAIL(SG2_EINVAL, "bn_act_fwd: channels %% 8");
-  Geo g = make_geo(P, Cout, 148 * 8);
+  Geo g = make_geo(P, Cout, 148 * 4);
   const int has_bn = mean != nullptr;
   cudaStream_t st = (cudaStream_t)stream;
 #define ARGS (const uint4*)x, mean, rstd, gamma, beta, (const uint4*)residual, (uint4*)out, P, C / 8, Cout / 8, g.cpb, g.rpb, has_bn
@@ -678,7 +721,7 @@ int sg2_bn_act_bwd(const void* x, const void* dout, const float* mean, const flo
                    long long P, int C, int act, void* stream) {
   const int Cout = act == ACT_GLU ? C / 2 : C;
   if (Cout % 8) EW_FAIL(SG2_EINVAL, "bn_act_bwd: channels %% 8");
-  Geo g = make_geo(P, Cout, 148 * 8);
+  Geo g = make_geo(P, Cout, 148 * 4);
   cudaStream_t st = (cudaStream_t)stream;
 #define RARGS (const uint4*)x, (const uint4*)dout, mean, rstd, gamma, beta, P, C / 8, Cout / 8, g.cpb, g.rpb, sums, C
 #define AARGS (const uint4*)x, (const uint4*)dout, mean, rstd, gamma, beta, sums, P, C / 8, Cout / 8, g.cpb, g.rpb, (uint4*)dx, C
@@ -727,11 +770,13 @@ int sg2_concat_c(const float* c, const void* h, void* out, int B, int HW, int E,
 
 int sg2_concat_c_bwd(const void* dcat, void* dh, float* dc, int B, int HW, int E, int Ch, void* stream) {
   if (E % 8 || Ch % 8) EW_FAIL(SG2_EINVAL, "concat_c_bwd: channels %% 8");
-  const long long per = (long long)HW * ((E + Ch) / 8);
-  unsigned gx = (unsigned)((per + 256 * 8 - 1) / (256 * 8));
+  const int ve = E / 8;
+  if (ve > 256) EW_FAIL(SG2_EINVAL, "concat_c_bwd: E too large");
+  unsigned gx = (unsigned)((HW + 255) / 256);   // >= 256 pixels per block
   if (gx < 1) gx = 1;
   if (gx > 64) gx = 64;
-  concat_c_bwd_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>((const uint4*)dcat, (uint4*)dh, dc, B, HW, E, Ch);
+  const int threads = (256 / ve) * ve;
+  concat_c_bwd_kernel<<<dim3(gx, B), threads, 0, (cudaStream_t)stream>>>((const uint4*)dcat, (uint4*)dh, dc, B, HW, E, Ch);
   return launch_ok("concat_c_bwd");
 }
 

@@ -48,7 +48,7 @@ struct FpropCfg {
   static constexpr int kABytes = kBlockM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   static size_t smem_bytes(int stages) { return size_t(stages) * kStageBytes + 1024 + 256; }
 };
 
@@ -171,7 +171,10 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
         } else if (p.out_mode == OUT_F32_ATOMIC) {
           float* dst = reinterpret_cast<float*>(p.out) + off + c0;
 #pragma unroll
-          for (int j = 0; j < (BN < 32 ? BN : 32); ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+          for (int j = 0; j < (BN < 32 ? BN : 32); j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                         "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                         : "memory");
         } else {
           float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + c0);
 #pragma unroll

@@ -215,9 +215,16 @@ __global__ void logits_bwd_kernel(const float* __restrict__ dprob, const float* 
 // ------------------------------------------------------------------------------------------ Adam (+ EMA)
 // torch.optim.Adam semantics (no amsgrad, no weight decay): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
 // p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).  Optional EMA: avg = 0.999 avg + 0.001 p  (trainer.py:571-572).
+// step counter lives on the device so that a captured CUDA graph replays the right bias corrections
+__global__ void adam_tick_kernel(int* __restrict__ step, float* __restrict__ bc, float b1, float b2) {
+  const int t = ++(*step);
+  bc[0] = 1.f - powf(b1, (float)t);
+  bc[1] = sqrtf(1.f - powf(b2, (float)t));
+}
 __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, float* __restrict__ avg, long long n, float lr, float b1,
-                                float b2, float eps, float bc1, float bc2_sqrt, float ema_decay) {
+                                float b2, float eps, const float* __restrict__ bc, float ema_decay) {
+  const float bc1 = bc[0], bc2_sqrt = bc[1];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i];
@@ -229,6 +236,114 @@ __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__
     const float pi = p[i] - (lr / bc1) * (mi / denom);
     p[i] = pi;
     if (avg) avg[i] = ema_decay * avg[i] + (1.f - ema_decay) * pi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ losses
+// nn.BCELoss (trainer.py:499; mean reduction, log clamped at -100) over `nvec` probability vectors of length B.
+// probs / dprobs are contiguous [nvec][B].
+// loss[0] += sum_v weight[v] * BCE(prob[v], target[v]);  dprob[v][b] = weight[v] * (p - t) / max(p (1-p), 1e-12) / B.
+__global__ void gan_bce_kernel(const float* __restrict__ probs, const float* __restrict__ targets,
+                               const float* __restrict__ weights, int nvec, int B, float* __restrict__ loss,
+                               float* __restrict__ dprobs) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nvec * B; i += blockDim.x) {
+    const int v = i / B;
+    const float p = probs[i], t = targets[v], w = weights[v];
+    const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(log1pf(-p), -100.f);
+    acc += -w * (t * lp + (1.f - t) * l1p) / (float)B;
+    if (dprobs) dprobs[i] = w * (p - t) / fmaxf(p * (1.f - p), 1e-12f) / (float)B;
+  }
+  __shared__ float sh[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) loss[0] += v;
+  }
+}
+
+// KL_loss (trainer.py:54-58) * coeff: loss[0] += coeff * -0.5 * mean(1 + lv - mu^2 - exp(lv)); grads (=).
+__global__ void kl_loss_kernel(const float* __restrict__ mu, const float* __restrict__ lv, int n, float coeff,
+                               float* __restrict__ loss, float* __restrict__ dmu, float* __restrict__ dlv) {
+  float acc = 0.f;
+  const float inv = 1.f / (float)n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float m = mu[i], l = lv[i], e = __expf(l);
+    acc += 1.f + l - m * m - e;
+    if (dmu) dmu[i] = coeff * m * inv;
+    if (dlv) dlv[i] = coeff * (-0.5f) * (1.f - e) * inv;
+  }
+  __shared__ float sh[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) loss[0] += coeff * (-0.5f) * v * inv;
+  }
+}
+
+// class_aware_loss (trainer.py:298-311): S = X X^T; loss = max(0, mean(S) - mean(S[same class, off-diagonal])) / F.
+__global__ void cal_scores_kernel(const float* __restrict__ x, int B, int F, float* __restrict__ S) {
+  const int i = blockIdx.x / B, j = blockIdx.x % B;
+  float acc = 0.f;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) acc += x[(long long)i * F + f] * x[(long long)j * F + f];
+  __shared__ float sh[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) S[blockIdx.x] = v;
+  }
+}
+// one block: loss and the symmetric coefficient matrix G = dL/dS + (dL/dS)^T   (B <= 128)
+__global__ void cal_coeff_kernel(const float* __restrict__ S, const int* __restrict__ labels, int B, int F,
+                                 float* __restrict__ loss, float* __restrict__ G) {
+  __shared__ float s_all, s_pair;
+  __shared__ int n_pair;
+  if (threadIdx.x == 0) { s_all = 0.f; s_pair = 0.f; n_pair = 0; }
+  __syncthreads();
+  float a = 0.f, pr = 0.f;
+  int np = 0;
+  for (int i = threadIdx.x; i < B * B; i += blockDim.x) {
+    const int r = i / B, c = i % B;
+    const float v = S[i];
+    a += v;
+    if (r != c && labels[r] == labels[c]) { pr += v; ++np; }
+  }
+  atomicAdd(&s_all, a);
+  atomicAdd(&s_pair, pr);
+  atomicAdd(&n_pair, np);
+  __syncthreads();
+  const float l = (n_pair > 0) ? (s_all / (float)(B * B) - s_pair / (float)n_pair) : 0.f;
+  const bool active = (n_pair > 0) && (l > 0.f);
+  if (threadIdx.x == 0 && active) loss[0] += l / (float)F;
+  for (int i = threadIdx.x; i < B * B; i += blockDim.x) {
+    const int r = i / B, c = i % B;
+    float d = 0.f;
+    if (active) {
+      d = 1.f / (float)(B * B);
+      if (r != c && labels[r] == labels[c]) d -= 1.f / (float)n_pair;
+      d *= 2.f / (float)F;   // the pair mask is symmetric, so dL/dS + its transpose = 2 dL/dS
+    }
+    G[i] = d;
+  }
+}
+__global__ void cal_dx_kernel(const float* __restrict__ x, const float* __restrict__ G, int B, int F,
+                              float* __restrict__ dx) {
+  const long long total = (long long)B * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F), r = (int)(i / F);
+    float acc = 0.f;
+    for (int j = 0; j < B; ++j) acc += G[r * B + j] * x[(long long)j * F + f];
+    dx[i] = acc;
   }
 }
 
@@ -317,12 +432,37 @@ int sg2_logits_bwd(const float* dprob, const float* prob, const void* x, const f
   SG2_LAUNCH_OK("logits_bwd");
 }
 
+int sg2_gan_bce(const float* probs, const float* targets, const float* weights, int nvec, int B, float* loss,
+                float* dprobs, void* stream) {
+  gan_bce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(probs, targets, weights, nvec, B, loss, dprobs);
+  SG2_LAUNCH_OK("gan_bce");
+}
+
+int sg2_kl_loss(const float* mu, const float* logvar, int n, float coeff, float* loss, float* dmu, float* dlogvar,
+                void* stream) {
+  kl_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(mu, logvar, n, coeff, loss, dmu, dlogvar);
+  SG2_LAUNCH_OK("kl_loss");
+}
+
+int sg2_cal_loss(const float* x, const int* labels, int B, int F, float* ws /* 2*B*B floats */, float* loss,
+                 float* dx, void* stream) {
+  if (B > 1024) SG2_FAIL(SG2_EINVAL, "cal_loss: B=%d", B);
+  cudaStream_t st = (cudaStream_t)stream;
+  cal_scores_kernel<<<B * B, 128, 0, st>>>(x, B, F, ws);
+  cal_coeff_kernel<<<1, 256, 0, st>>>(ws, labels, B, F, loss, ws + (size_t)B * B);
+  if (dx) cal_dx_kernel<<<grid1d((long long)B * F), 256, 0, st>>>(x, ws + (size_t)B * B, B, F, dx);
+  SG2_LAUNCH_OK("cal_loss");
+}
+
+int sg2_adam_tick(int* step, float* bc, float beta1, float beta2, void* stream) {
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step, bc, beta1, beta2);
+  SG2_LAUNCH_OK("adam_tick");
+}
+
 int sg2_adam_ema(float* p, const float* g, float* m, float* v, float* avg, long long n, float lr, float beta1,
-                 float beta2, float eps, int step, float ema_decay, void* stream) {
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2 = 1.f - powf(beta2, (float)step);
-  adam_ema_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, avg, n, lr, beta1, beta2, eps, bc1,
-                                                              sqrtf(bc2), ema_decay);
+                 float beta2, float eps, const float* bc, float ema_decay, void* stream) {
+  adam_ema_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, avg, n, lr, beta1, beta2, eps, bc,
+                                                              ema_decay);
   SG2_LAUNCH_OK("adam_ema");
 }
 

@@ -1,0 +1,397 @@
+"""Execution engines for G_NET and D_NET64/128/256: hand-scheduled forward and backward over the sg2b200 kernels.
+
+The nn.Module classes in model.py only hold parameters/buffers (reference names and order); these engines read
+them, run NHWC-bf16 pipelines on the CUDA kernels and hand gradients back to autograd. Reference behaviour
+mirrored: StackGAN_v2/model.py:112-354 (G side), 358-551 (D side).
+"""
+import torch
+
+from . import ops
+from .ops import ACT_GLU, ACT_LRELU, ACT_NONE, CONV3, CONV4S2, GEMM, STEM, UPCONV
+
+
+def _pad_to(n, m):
+    return -(-n // m) * m
+
+
+class ConvOperand:
+    """bf16 operand packs (fprop + dgrad) and the fp32 wgrad accumulator of one conv weight."""
+
+    def __init__(self, kind, weight, cout_pad=None, cin_pad=None):
+        self.kind = kind
+        self.weight = weight
+        self.Cout = weight.shape[0]
+        self.Cin = 48 if kind == STEM else weight.shape[1]
+        self.CoP = cout_pad or self.Cout
+        self.CiP = cin_pad or self.Cin
+        self._key = None
+        self.wpk = self.wpkT = self.dwpk = None
+        # algorithmic / executed FLOP ratio of the padded operand (image heads pad 3 -> 32, stems pad 48 -> 64)
+        self.flop_scale = (self.Cout * self.Cin) / float(self.CoP * self.CiP)
+
+    def packs(self):
+        w = self.weight
+        # _sg2_version: bumped by FlatBucket.adam(), whose kernel updates the weights behind torch's back
+        key = (w.data_ptr(), w._version, getattr(w, "_sg2_version", 0), w.device)
+        if key != self._key:
+            s1, s2 = ops.pack_shapes(GEMM if self.kind == STEM else self.kind, self.CoP, self.CiP)
+            if self.wpk is None or self.wpk.device != w.device:
+                self.wpk = torch.empty(s1, device=w.device, dtype=torch.bfloat16)
+                self.wpkT = torch.empty(s2, device=w.device, dtype=torch.bfloat16)
+            ops.pack_weights(self.kind, w.detach(), self.wpk, self.wpkT, self.Cout, self.Cin, self.CoP, self.CiP)
+            self._key = key
+        return self.wpk, self.wpkT
+
+    def wgrad_begin(self, device):
+        k = GEMM if self.kind == STEM else self.kind
+        shape = (self.CoP, ops.JOBS[k], self.CiP)
+        if self.dwpk is None or self.dwpk.device != device:
+            self.dwpk = torch.empty(shape, device=device, dtype=torch.float32)
+        self.dwpk.zero_()
+
+    def wgrad_add(self, x, dy):
+        """dwpk += dy^T im2col(x) (tcgen05 wgrad kernel, fp32 red.global.add)."""
+        ops.conv_wgrad(GEMM if self.kind == STEM else self.kind, x, dy, self.dwpk, flop_scale=self.flop_scale)
+
+    def wgrad_finish(self, out=None):
+        """packed fp32 accumulator -> OIHW fp32 gradient (written into `out` if given)."""
+        g = torch.empty_like(self.weight) if out is None else out
+        ops.unpack_wgrad(self.kind, self.dwpk, g, self.Cout, self.Cin, self.CoP, self.CiP, False)
+        return g
+
+
+class GradSink:
+    """Collects parameter gradients of one or several backward passes (e.g. D's real/wrong/fake passes).
+
+    Conv weight gradients accumulate in the packed fp32 buffers and are unpacked once in finish(); the small
+    BN / linear / logit gradients accumulate in place. `views` optionally maps parameter -> preallocated
+    fp32 tensor (a slice of a flat gradient bucket) that receives the result."""
+
+    def __init__(self, views=None):
+        self.g = {}
+        self.views = views or {}
+        self.pending = []
+
+    def slot(self, p):
+        """(tensor, accumulate_flag) for a small gradient written by a kernel."""
+        if p in self.g:
+            return self.g[p], True
+        t = self.views.get(p)
+        if t is None:
+            t = torch.empty_like(p, dtype=torch.float32)
+        self.g[p] = t
+        return t, False
+
+    def zero_slot(self, p):
+        """Tensor for `+=` kernels: zeroed on first use."""
+        t, acc = self.slot(p)
+        if not acc:
+            t.zero_()
+        return t
+
+    def conv(self, op, x, dy):
+        if op not in self.pending:
+            op.wgrad_begin(x.device)
+            self.pending.append(op)
+        op.wgrad_add(x, dy)
+
+    def finish(self):
+        for op in self.pending:
+            self.g[op.weight] = op.wgrad_finish(self.views.get(op.weight))
+        self.pending = []
+        return self.g
+
+
+class ConvBlock:
+    """conv (3x3 | fused-upsample 3x3 | 4x4 s2) -> [BatchNorm] -> GLU | LeakyReLU | (+residual)."""
+
+    def __init__(self, kind, conv, bn, act):
+        self.kind, self.conv, self.bn, self.act = kind, conv, bn, act
+        self.op = ConvOperand(kind, conv.weight)
+
+    def fwd(self, x, training, residual=None):
+        wpk, _ = self.op.packs()
+        y = ops.conv_fprop(self.kind, x, wpk, self.op.Cout)
+        if self.bn is not None:
+            y2 = y.view(-1, y.shape[-1])
+            if training:
+                mean, rstd = ops.bn_batch_stats(y2, self.bn.running_mean, self.bn.running_var,
+                                                self.bn.num_batches_tracked)
+            else:
+                mean, rstd = ops.bn_eval_stats(self.bn.running_mean, self.bn.running_var)
+            out = ops.bn_act_fwd(y, mean, rstd, self.bn.weight.detach(), self.bn.bias.detach(), self.act, residual)
+        else:
+            mean = rstd = None
+            out = ops.bn_act_fwd(y, None, None, None, None, self.act, residual)
+        return out, (x, y, mean, rstd)
+
+    def bwd(self, saved, dout, sink, need_dx=True, need_w=True):
+        x, y, mean, rstd = saved
+        if self.bn is not None:
+            if need_w:
+                (dg, acc), (db, _) = sink.slot(self.bn.weight), sink.slot(self.bn.bias)
+            else:
+                dg = db = None
+                acc = False
+            dy = ops.bn_act_bwd(y, dout, mean, rstd, self.bn.weight.detach(), self.bn.bias.detach(), self.act,
+                                dg, db, acc)
+        elif self.act == ACT_LRELU:
+            dy = ops.lrelu_bwd(y, dout)
+        else:
+            dy = dout
+        if need_w:
+            sink.conv(self.op, x, dy)
+        if not need_dx:
+            return None
+        _, wpkT = self.op.packs()
+        B, H, W, Cin = x.shape
+        return ops.conv_dgrad(self.kind, dy, wpkT, B, H, W, Cin)
+
+
+class HeadBlock:
+    """GET_IMAGE_G (model.py:287-298): conv3x3 C->3 + tanh; output NCHW fp32 image."""
+    CP = 32
+
+    def __init__(self, conv):
+        self.conv = conv
+        self.op = ConvOperand(CONV3, conv.weight, cout_pad=self.CP)
+
+    def fwd(self, h):
+        wpk, _ = self.op.packs()
+        y = ops.conv_fprop(CONV3, h, wpk, self.CP, flop_scale=self.op.flop_scale)
+        B, H, W, _ = h.shape
+        return ops.head_tanh_fwd(y, B, H, W), h
+
+    def bwd(self, h, img, dimg, sink):
+        dy = ops.head_tanh_bwd(dimg, img, self.CP)
+        sink.conv(self.op, h, dy)
+        _, wpkT = self.op.packs()
+        B, H, W, C = h.shape
+        return ops.conv_dgrad(CONV3, dy, wpkT, B, H, W, C, flop_scale=self.op.flop_scale)
+
+
+def _acc(a, b):
+    if a is None:
+        return b
+    if b is None:
+        return a
+    return ops.add_bf16(a, b)
+
+
+# =============================================================================================== generator
+class GEngine:
+    def __init__(self, net, cfg):
+        self.net = net
+        self.E = cfg.GAN.EMBEDDING_DIM
+        self.Z = cfg.GAN.Z_DIM
+        self.branches = cfg.TREE.BRANCH_NUM
+        self.ngf = cfg.GAN.GF_DIM * 16
+        h1 = net.h_net1
+        self.ups1 = [ConvBlock(UPCONV, getattr(h1, f"upsample{i}")[1], getattr(h1, f"upsample{i}")[2], ACT_GLU)
+                     for i in (1, 2, 3, 4)]
+        self.heads = [HeadBlock(net.img_net1.img[0])]
+        self.stages = []
+        for s in range(2, self.branches + 1):
+            hn = getattr(net, f"h_net{s}")
+            joint = ConvBlock(CONV3, hn.jointConv[0], hn.jointConv[1], ACT_GLU)
+            res = [(ConvBlock(CONV3, r.block[0], r.block[1], ACT_GLU), ConvBlock(CONV3, r.block[3], r.block[4], ACT_NONE))
+                   for r in hn.residual]
+            up = ConvBlock(UPCONV, hn.upsample[1], hn.upsample[2], ACT_GLU)
+            self.stages.append((joint, res, up))
+            self.heads.append(HeadBlock(getattr(net, f"img_net{s}").img[0]))
+
+    def params(self):
+        return [p for p in self.net.parameters()]
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, z, emb, eps, training):
+        net = self.net
+        B = z.shape[0]
+        T = {}
+        ca = net.ca_net.fc
+        T["emb"], T["z"], T["eps"] = emb, z, eps
+        T["fc_ca"] = ops.linear_fwd(emb, None, ca.weight.detach(), ca.bias.detach(), False)
+        mu, logvar, c = ops.ca_glu_reparam_fwd(T["fc_ca"], eps)
+        T["c"] = c
+        fc, bn = net.h_net1.fc[0], net.h_net1.fc[1]
+        h = ops.linear_fwd(c, z, fc.weight.detach(), None, True)                       # (B, ngf*32) bf16
+        if training:
+            mean, rstd = ops.bn_batch_stats(h, bn.running_mean, bn.running_var, bn.num_batches_tracked)
+        else:
+            mean, rstd = ops.bn_eval_stats(bn.running_mean, bn.running_var)
+        g = ops.bn_act_fwd(h, mean, rstd, bn.weight.detach(), bn.bias.detach(), ACT_GLU)  # (B, ngf*16) CHW order
+        T["fc"] = (h, mean, rstd)
+        x = ops.chw_hwc(g, B, self.ngf, 16, True).view(B, 4, 4, self.ngf)
+        T["ups1"] = []
+        for blk in self.ups1:
+            x, sv = blk.fwd(x, training)
+            T["ups1"].append(sv)
+        imgs = []
+        img, hsv = self.heads[0].fwd(x)
+        imgs.append(img)
+        T["heads"] = [hsv]
+        T["stages"] = []
+        for si, (joint, res, up) in enumerate(self.stages):
+            cat = ops.concat_c(c, x)
+            x, sj = joint.fwd(cat, training)
+            sres = []
+            for (b0, b1) in res:
+                mid, s0 = b0.fwd(x, training)
+                x, s1 = b1.fwd(mid, training, residual=x)
+                sres.append((s0, s1))
+            x, su = up.fwd(x, training)
+            T["stages"].append((sj, sres, su))
+            img, hsv = self.heads[si + 1].fwd(x)
+            imgs.append(img)
+            T["heads"].append(hsv)
+        T["imgs"] = imgs
+        return imgs, mu, logvar, T
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, T, dimgs, dmu, dlogvar, sink=None):
+        """-> dict {parameter: fp32 grad}. dimgs[i] may be None."""
+        net = self.net
+        own = sink is None
+        grads = sink = GradSink() if own else sink
+        c = T["c"]
+        B = c.shape[0]
+        dc = torch.zeros_like(c)
+        dx = None   # gradient flowing into the h_code of the current stage (NHWC bf16)
+        for si in range(len(self.stages), -1, -1):
+            head = self.heads[si]
+            if dimgs[si] is not None:
+                dx = _acc(dx, head.bwd(T["heads"][si], T["imgs"][si], dimgs[si].contiguous(), grads))
+            else:
+                sink.zero_slot(head.conv.weight)
+            if si == 0:
+                break
+            joint, res, up = self.stages[si - 1]
+            sj, sres, su = T["stages"][si - 1]
+            if dx is None:
+                raise RuntimeError("sg2b200: no gradient reached generator stage %d" % (si + 1))
+            dx = up.bwd(su, dx, grads)
+            for (b0, b1), (s0, s1) in zip(reversed(res), reversed(sres)):
+                dmid = b1.bwd(s1, dx, grads)
+                dblk = b0.bwd(s0, dmid, grads)
+                dx = ops.add_bf16(dblk, dx)
+            dcat = joint.bwd(sj, dx, grads)
+            dx = ops.concat_c_bwd(dcat, self.E, dc)
+        for blk, sv in zip(reversed(self.ups1), reversed(T["ups1"])):
+            dx = blk.bwd(sv, dx, grads)
+        # INIT_STAGE_G fc: NHWC -> CHW feature order -> BN1d+GLU backward -> linear
+        fc, bn = net.h_net1.fc[0], net.h_net1.fc[1]
+        h, mean, rstd = T["fc"]
+        dg = ops.chw_hwc(dx.reshape(B, -1), B, self.ngf, 16, False)
+        (dgam, acc), (dbet, _) = sink.slot(bn.weight), sink.slot(bn.bias)
+        dh = ops.bn_act_bwd(h, dg, mean, rstd, bn.weight.detach(), bn.bias.detach(), ACT_GLU, dgam, dbet, acc)
+        dw, acc = sink.slot(fc.weight)
+        ops.linear_bwd_w(dh, c, T["z"], dw, None, acc)
+        dc.add_(ops.linear_bwd_x(dh, fc.weight.detach(), self.E))     # (B, E) fp32: plumbing-sized
+        ca = net.ca_net.fc
+        dfc = ops.ca_glu_reparam_bwd(T["fc_ca"], T["eps"], dmu, dlogvar, dc)
+        (dw, acc), (db, _) = sink.slot(ca.weight), sink.slot(ca.bias)
+        ops.linear_bwd_w(dfc, T["emb"], None, dw, db, acc)
+        return sink.finish() if own else None
+
+
+# =============================================================================================== discriminators
+class StemBlock:
+    """encode_image_by_16times[0:2] (model.py:383-384): conv4x4 s2 3->ndf (no BN) + LeakyReLU, as im2col + GEMM."""
+
+    def __init__(self, conv):
+        self.conv = conv
+        self.op = ConvOperand(STEM, conv.weight, cin_pad=64)
+
+    def fwd(self, img):
+        B, _, S, _ = img.shape
+        col = ops.stem_im2col(img)
+        wpk, _ = self.op.packs()
+        y = ops.conv_fprop(GEMM, col, wpk, self.op.Cout, flop_scale=self.op.flop_scale).view(B, S // 2, S // 2, self.op.Cout)
+        out = ops.bn_act_fwd(y, None, None, None, None, ACT_LRELU)
+        return out, (col, y, B, S)
+
+    def bwd(self, saved, dout, sink, need_dimg, need_w=True):
+        col, y, B, S = saved
+        dy = ops.lrelu_bwd(y, dout).view(1, 1, -1, self.op.Cout)
+        if need_w:
+            sink.conv(self.op, col, dy)
+        if not need_dimg:
+            return None
+        _, wpkT = self.op.packs()
+        dcol = ops.conv_dgrad(GEMM, dy, wpkT, 1, 1, col.shape[2], 64, flop_scale=self.op.flop_scale)
+        return ops.stem_col2im(dcol, B, S)
+
+
+class DEngine:
+    def __init__(self, net, cfg):
+        self.net = net
+        self.E = cfg.GAN.EMBEDDING_DIM
+        s16 = net.img_code_s16
+        self.stem = StemBlock(s16[0])
+        self.trunk = [ConvBlock(CONV4S2, s16[2], s16[3], ACT_LRELU), ConvBlock(CONV4S2, s16[5], s16[6], ACT_LRELU),
+                      ConvBlock(CONV4S2, s16[8], s16[9], ACT_LRELU)]
+        for name, kind in (("img_code_s32", CONV4S2), ("img_code_s64", CONV4S2), ("img_code_s32_1", CONV3),
+                           ("img_code_s64_1", CONV3), ("img_code_s64_2", CONV3)):
+            if hasattr(net, name):
+                m = getattr(net, name)
+                self.trunk.append(ConvBlock(kind, m[0], m[1], ACT_LRELU))
+        self.joint = ConvBlock(CONV3, net.jointConv[0], net.jointConv[1], ACT_LRELU)
+
+    def params(self):
+        return [p for p in self.net.parameters()]
+
+    def forward(self, img, c, training, out_cond=None, out_uncond=None):
+        T = {}
+        x, T["stem"] = self.stem.fwd(img)
+        T["trunk"] = []
+        for blk in self.trunk:
+            x, sv = blk.fwd(x, training)
+            T["trunk"].append(sv)
+        T["x_code"] = x
+        x_imm = ops.nhwc_to_nchw_f32(x)
+        cat = ops.concat_c(c, x)
+        h, T["joint"] = self.joint.fwd(cat, training)
+        T["h"] = h
+        lg, ul = self.net.logits[0], self.net.uncond_logits[0]
+        cond = ops.logits_fwd(h, lg.weight.detach(), lg.bias.detach(), out_cond)
+        uncond = ops.logits_fwd(x, ul.weight.detach(), ul.bias.detach(), out_uncond)
+        T["cond"], T["uncond"], T["c"] = cond, uncond, c
+        return cond, uncond, x_imm, T
+
+    def backward(self, T, dcond, duncond, dx_imm, need_dimg, need_dc, need_w=True, sink=None):
+        """-> (grads dict or None when an external sink is used, dimg or None, dc or None)"""
+        own = sink is None
+        sink = GradSink() if own else sink
+        lg, ul = self.net.logits[0], self.net.uncond_logits[0]
+        x, h = T["x_code"], T["h"]
+        B = x.shape[0]
+        dc = torch.zeros_like(T["c"])
+        dx = None
+        if need_w:   # `+=` kernels and never-reached branches need zeroed slots
+            for p in (lg.weight, lg.bias, ul.weight, ul.bias):
+                sink.zero_slot(p)
+        if dcond is not None:
+            dh = torch.empty_like(h)
+            ops.logits_bwd(dcond, T["cond"], h, lg.weight.detach(), dh, False,
+                           sink.g[lg.weight] if need_w else None, sink.g[lg.bias] if need_w else None)
+            dcat = self.joint.bwd(T["joint"], dh, sink, need_w=need_w)
+            dx = ops.concat_c_bwd(dcat, self.E, dc)
+        elif need_w:
+            for p in (self.joint.conv.weight, self.joint.bn.weight, self.joint.bn.bias):
+                sink.zero_slot(p)
+        if duncond is not None:
+            first = dx is None
+            if first:
+                dx = torch.empty_like(x)
+            ops.logits_bwd(duncond, T["uncond"], x, ul.weight.detach(), dx, not first,
+                           sink.g[ul.weight] if need_w else None, sink.g[ul.bias] if need_w else None)
+        if dx_imm is not None:
+            _, H, W, C = x.shape
+            dxi = ops.nchw_f32_to_nhwc(dx_imm, B, H, W, C)
+            dx = dxi if dx is None else ops.add_bf16(dx, dxi)
+        if dx is None:
+            raise RuntimeError("sg2b200: D backward without any output gradient")
+        for blk, sv in zip(reversed(self.trunk), reversed(T["trunk"])):
+            dx = blk.bwd(sv, dx, sink, need_w=need_w)
+        dimg = self.stem.bwd(T["stem"], dx, sink, need_dimg, need_w=need_w)
+        return (sink.finish() if own else None), dimg, (dc if need_dc else None)

@@ -1,0 +1,362 @@
+"""Tensor-level wrappers over the C ABI (include/sg2b200.h). Torch is plumbing only: it owns the memory and the
+stream; every kernel launched here is one of ours. No CPU path: CPU tensors are rejected.
+
+Layout convention: activations are NHWC bf16 torch tensors of shape (B, H, W, C) (or (P, C)).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+CONV3, UPCONV, CONV4S2, GEMM, STEM = 0, 1, 2, 3, 4
+ACT_NONE, ACT_GLU, ACT_LRELU = 0, 1, 2
+OUT_BF16, OUT_F32_ATOMIC, OUT_F32_STORE = 0, 1, 2
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+N_SM = 148
+
+_launches = 0   # kernels of ours launched through this module (bench.py reports it as gpu_launches)
+
+
+def launches():
+    return _launches
+
+
+def _st():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("sg2b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("sg2b200: non-contiguous tensor passed to a kernel")
+    return t.data_ptr()
+
+
+def _call(name, n_launch, *args):
+    global _launches
+    _launches += n_launch
+    _lib.call(name, *args)
+
+
+# ---- optional live profiling of the convolution kernels (bench.py's roofline): CUDA events around each launch
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = {"events": [], "flops": 0.0}
+
+
+def profile_end():
+    global _prof
+    torch.cuda.synchronize()
+    p, _prof = _prof, None
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in p["events"])
+    return {"conv": {"ms": ms, "flops": p["flops"], "n": len(p["events"])}}
+
+
+_TAPS_EFF = {0: 9, 1: 16, 2: 16, 3: 1}
+
+
+def _conv_flops(kind, B, H, W, Cin, Cout):
+    """MMA FLOPs one launch executes (fprop, dgrad and wgrad of a layer all contract the same index set)."""
+    pix = B * (H // 2) * (W // 2) if kind == CONV4S2 else B * H * W
+    return 2.0 * _TAPS_EFF[kind] * Cin * Cout * pix
+
+
+def _conv_call(name, n_launch, flops, *args):
+    if _prof is None:
+        return _call(name, n_launch, *args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _call(name, n_launch, *args)
+    e1.record()
+    _prof["events"].append((e0, e1))
+    _prof["flops"] += flops
+
+
+# ------------------------------------------------------------------------------------------ weights
+JOBS = {CONV3: 9, UPCONV: 16, CONV4S2: 16, GEMM: 1, STEM: 1}
+
+
+def pack_shapes(kind, CoP, CiP):
+    if kind == CONV3:
+        return (CoP, 9, CiP), (CiP, 9, CoP)
+    if kind == UPCONV:
+        return (4, CoP, 4, CiP), (CiP, 16, CoP)
+    if kind == CONV4S2:
+        return (CoP, 16, CiP), (4, CiP, 4, CoP)
+    return (CoP, CiP), (CiP, CoP)
+
+
+def pack_weights(kind, w, wpk, wpkT, Cout, Cin, CoP, CiP):
+    _call("sg2_pack_weights", 1, kind, _p(w), _p(wpk), _p(wpkT), Cout, Cin, CoP, CiP, _st())
+
+
+def unpack_wgrad(kind, dwpk, grad, Cout, Cin, CoP, CiP, accumulate):
+    _call("sg2_unpack_wgrad", 1, kind, _p(dwpk), _p(grad), Cout, Cin, CoP, CiP, int(accumulate), _st())
+
+
+# ------------------------------------------------------------------------------------------ convolutions
+def _out_hw(kind, H, W):
+    if kind == UPCONV:
+        return 2 * H, 2 * W
+    if kind == CONV4S2:
+        return H // 2, W // 2
+    return H, W
+
+
+def _auto_split(m_rows, n_cols, k_blocks):
+    """Split-K factor for GEMMs whose 128 x BN output tiles cannot fill the 148 SMs."""
+    bn = n_cols if n_cols in (160, 192) else (
+        256 if n_cols % 256 == 0 else (128 if n_cols % 128 == 0 else (64 if n_cols % 64 == 0 else 32)))
+    tiles = -(-m_rows // 128) * max(1, n_cols // bn)
+    if tiles >= 96 or k_blocks < 8:
+        return 1
+    s = min(k_blocks // 8, -(-N_SM // tiles))      # >= 8 K blocks per CTA: fewer fp32 atomics per output
+    return max(1, s)
+
+
+def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0):
+    """x (B,H,W,Cin) bf16 -> y bf16 (B,Ho,Wo,Cout)."""
+    B, H, W, Cin = x.shape
+    fl = flop_scale * _conv_flops(kind, B, H, W, Cin, Cout)
+    Ho, Wo = _out_hw(kind, H, W)
+    taps = {CONV3: 9, UPCONV: 4, CONV4S2: 16, GEMM: 1}[kind]
+    groups = 4 if kind == UPCONV else 1
+    if splitk is None:
+        splitk = _auto_split(B * Ho * Wo // groups, Cout, taps * max(1, Cin // 64))
+    if splitk > 1:
+        y32 = torch.zeros((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
+        _conv_call("sg2_conv_fprop", 2, fl, kind, _p(x), _p(wpk), _p(y32), OUT_F32_ATOMIC, B, H, W, Cin, Cout, splitk, _st())
+        return f32_to_bf16(y32)
+    y = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
+    _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, 1, _st())
+    return y
+
+
+def conv_dgrad(kind, dy, wpkT, B, H, W, Cin, splitk=None, flop_scale=1.0):
+    """dy (B,Ho,Wo,Cout) bf16 -> dx bf16 (B,H,W,Cin)."""
+    Cout = dy.shape[-1]
+    fl = flop_scale * _conv_flops(kind, B, H, W, Cin, Cout)
+    taps = {CONV3: 9, UPCONV: 16, CONV4S2: 4, GEMM: 1}[kind]
+    groups = 4 if kind == CONV4S2 else 1
+    if splitk is None:
+        splitk = _auto_split(B * H * W // groups, Cin, taps * max(1, Cout // 64))
+    if splitk > 1:
+        dx32 = torch.zeros((B, H, W, Cin), device=dy.device, dtype=torch.float32)
+        _conv_call("sg2_conv_dgrad", 2, fl, kind, _p(dy), _p(wpkT), _p(dx32), OUT_F32_ATOMIC, B, H, W, Cin, Cout, splitk, _st())
+        return f32_to_bf16(dx32)
+    dx = torch.empty((B, H, W, Cin), device=dy.device, dtype=torch.bfloat16)
+    _conv_call("sg2_conv_dgrad", 1, fl, kind, _p(dy), _p(wpkT), _p(dx), OUT_BF16, B, H, W, Cin, Cout, 1, _st())
+    return dx
+
+
+def conv_wgrad(kind, x, dy, dwpk, splitk=None, flop_scale=1.0):
+    """dwpk (Cout, jobs, Cin) fp32 += dy^T im2col(x)."""
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    fl = flop_scale * _conv_flops(kind, B, H, W, Cin, Cout)
+    if splitk is None:
+        pix = dy.shape[0] * dy.shape[1] * dy.shape[2] // (4 if kind == UPCONV else 1)
+        ktiles = max(1, pix // 64)
+        bn = 16 if Cin <= 16 else (32 if Cin <= 32 else (64 if Cin <= 64 else (128 if Cin <= 128 else 256)))
+        ctas = -(-Cout // 128) * -(-Cin // bn) * JOBS[kind]
+        splitk = max(1, min(ktiles // 2 if ktiles >= 2 else 1, -(-2 * N_SM // ctas)))
+    _conv_call("sg2_conv_wgrad", 1, fl, kind, _p(x), _p(dy), _p(dwpk), B, H, W, Cin, Cout, splitk, _st())
+
+
+# ------------------------------------------------------------------------------------------ BN / activations
+_sums_cache = {}
+
+
+def bn_sums(C, device):
+    """Zero-initialised fp64 [2][C] workspace; the kernels leave it zeroed."""
+    key = (C, device.index, torch.cuda.current_stream().cuda_stream)
+    t = _sums_cache.get(key)
+    if t is None:
+        t = torch.zeros(2 * C, device=device, dtype=torch.float64)
+        _sums_cache[key] = t
+    return t
+
+
+def bn_batch_stats(x2d, rmean, rvar, nbt, update_running=True):
+    """x2d (P, C) bf16 -> mean, rstd (fp32); updates running stats like nn.BatchNorm in train mode."""
+    P, C = x2d.shape
+    sums = bn_sums(C, x2d.device)
+    mean = torch.empty(C, device=x2d.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    _call("sg2_bn_stats", 1, _p(x2d), P, C, _p(sums), _st())
+    _call("sg2_bn_finalize", 1, _p(sums), P, C, BN_EPS, BN_MOMENTUM, _p(mean), _p(rstd),
+          _p(rmean) if update_running else None, _p(rvar) if update_running else None,
+          _p(nbt) if update_running else None, _st())
+    return mean, rstd
+
+
+def bn_eval_stats(rmean, rvar):
+    C = rmean.numel()
+    mean = torch.empty(C, device=rmean.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    _call("sg2_bn_eval_prepare", 1, _p(rmean), _p(rvar), BN_EPS, _p(mean), _p(rstd), C, _st())
+    return mean, rstd
+
+
+def bn_act_fwd(x, mean, rstd, gamma, beta, act, residual=None):
+    C = x.shape[-1]
+    P = x.numel() // C
+    out = torch.empty(x.shape[:-1] + ((C // 2) if act == ACT_GLU else C,), device=x.device, dtype=torch.bfloat16)
+    _call("sg2_bn_act_fwd", 1, _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(out), P, C, act, _st())
+    return out
+
+
+def bn_act_bwd(x, dout, mean, rstd, gamma, beta, act, dgamma=None, dbeta=None, accumulate=False):
+    """-> dx (shape of x, bf16); dgamma/dbeta (fp32, = or +=) are written into the given tensors."""
+    C = x.shape[-1]
+    P = x.numel() // C
+    dx = torch.empty_like(x)
+    if dgamma is None:
+        dgamma = torch.empty(C, device=x.device, dtype=torch.float32)
+        dbeta = torch.empty_like(dgamma)
+        accumulate = False
+    sums = bn_sums(C, x.device)
+    _call("sg2_bn_act_bwd", 3, _p(x), _p(dout), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(sums), _p(dx),
+          _p(dgamma), _p(dbeta), int(accumulate), P, C, act, _st())
+    return dx
+
+
+def lrelu_bwd(x, dout):
+    dx = torch.empty_like(x)
+    _call("sg2_lrelu_bwd", 1, _p(x), _p(dout), _p(dx), x.numel(), _st())
+    return dx
+
+
+def add_bf16(a, b, out=None):
+    out = torch.empty_like(a) if out is None else out
+    _call("sg2_add_bf16", 1, _p(a), _p(b), _p(out), a.numel(), _st())
+    return out
+
+
+def f32_to_bf16(x):
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _call("sg2_f32_to_bf16", 1, _p(x), _p(out), x.numel(), _st())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ concat / heads / stems
+def concat_c(c, h):
+    B, H, W, Ch = h.shape
+    E = c.shape[1]
+    out = torch.empty((B, H, W, E + Ch), device=h.device, dtype=torch.bfloat16)
+    _call("sg2_concat_c", 1, _p(c), _p(h), _p(out), B, H * W, E, Ch, _st())
+    return out
+
+
+def concat_c_bwd(dcat, E, dc, want_dh=True):
+    B, H, W, Ct = dcat.shape
+    Ch = Ct - E
+    dh = torch.empty((B, H, W, Ch), device=dcat.device, dtype=torch.bfloat16) if want_dh else None
+    _call("sg2_concat_c_bwd", 1, _p(dcat), _p(dh), _p(dc), B, H * W, E, Ch, _st())
+    return dh
+
+
+def head_tanh_fwd(y, B, H, W):
+    img = torch.empty((B, 3, H, W), device=y.device, dtype=torch.float32)
+    _call("sg2_head_tanh_fwd", 1, _p(y), _p(img), B, H * W, y.shape[-1], _st())
+    return img
+
+
+def head_tanh_bwd(dimg, img, CP):
+    B, _, H, W = img.shape
+    dy = torch.empty((B, H, W, CP), device=img.device, dtype=torch.bfloat16)
+    _call("sg2_head_tanh_bwd", 1, _p(dimg), _p(img), _p(dy), B, H * W, CP, _st())
+    return dy
+
+
+def stem_im2col(img):
+    B, _, S, _ = img.shape
+    col = torch.empty((1, 1, B * (S // 2) * (S // 2), 64), device=img.device, dtype=torch.bfloat16)
+    _call("sg2_stem_im2col", 1, _p(img), _p(col), B, S, _st())
+    return col
+
+
+def stem_col2im(dcol, B, S):
+    dimg = torch.empty((B, 3, S, S), device=dcol.device, dtype=torch.float32)
+    _call("sg2_stem_col2im", 1, _p(dcol), _p(dimg), B, S, _st())
+    return dimg
+
+
+def nhwc_to_nchw_f32(x):
+    B, H, W, C = x.shape
+    out = torch.empty((B, C * H * W), device=x.device, dtype=torch.float32)
+    _call("sg2_nhwc_to_nchw_f32", 1, _p(x), _p(out), B, H * W, C, _st())
+    return out
+
+
+def nchw_f32_to_nhwc(x, B, H, W, C):
+    out = torch.empty((B, H, W, C), device=x.device, dtype=torch.bfloat16)
+    _call("sg2_nchw_f32_to_nhwc", 1, _p(x), _p(out), B, H * W, C, _st())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ small fp32 ops
+def linear_fwd(x1, x2, w, bias, out_bf16):
+    M, K1 = x1.shape
+    K2 = 0 if x2 is None else x2.shape[1]
+    N = w.shape[0]
+    out = torch.empty((M, N), device=w.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    _call("sg2_linear_fwd", 1, _p(x1), K1, _p(x2), K2, _p(w), _p(bias), _p(out), int(out_bf16), M, N, _st())
+    return out
+
+
+def linear_bwd_w(dy, x1, x2, dw, db, accumulate=False):
+    M, K1 = x1.shape
+    K2 = 0 if x2 is None else x2.shape[1]
+    N = dy.shape[1]
+    _call("sg2_linear_bwd_w", 1, _p(dy), int(dy.dtype == torch.bfloat16), _p(x1), K1, _p(x2), K2, _p(dw), _p(db),
+          M, N, int(accumulate), _st())
+
+
+def linear_bwd_x(dy, w, Kout):
+    M, N = dy.shape
+    dx = torch.empty((M, Kout), device=dy.device, dtype=torch.float32)
+    _call("sg2_linear_bwd_x", 2, _p(dy), int(dy.dtype == torch.bfloat16), _p(w), _p(dx), M, N, w.shape[1], Kout, _st())
+    return dx
+
+
+def ca_glu_reparam_fwd(fc, eps):
+    B, E4 = fc.shape
+    E = E4 // 4
+    mu = torch.empty((B, E), device=fc.device, dtype=torch.float32)
+    logvar, c = torch.empty_like(mu), torch.empty_like(mu)
+    _call("sg2_ca_glu_reparam_fwd", 1, _p(fc), _p(eps), _p(mu), _p(logvar), _p(c), B, E, _st())
+    return mu, logvar, c
+
+
+def ca_glu_reparam_bwd(fc, eps, dmu, dlogvar, dc):
+    B, E4 = fc.shape
+    dfc = torch.empty_like(fc)
+    _call("sg2_ca_glu_reparam_bwd", 1, _p(fc), _p(eps), _p(dmu), _p(dlogvar), _p(dc), _p(dfc), B, E4 // 4, _st())
+    return dfc
+
+
+def chw_hwc(x, B, C, HW, to_hwc):
+    out = torch.empty_like(x)
+    _call("sg2_chw_hwc_bf16", 1, _p(x), _p(out), B, C, HW, int(to_hwc), _st())
+    return out
+
+
+def logits_fwd(x, w, bias, out=None):
+    B, H, W, C = x.shape
+    prob = torch.empty(B, device=x.device, dtype=torch.float32) if out is None else out
+    _call("sg2_logits_fwd", 1, _p(x), _p(w), _p(bias), _p(prob), B, H * W, C, _st())
+    return prob
+
+
+def logits_bwd(dprob, prob, x, w, dx, dx_accumulate, dw, dbias):
+    B, H, W, C = x.shape
+    _call("sg2_logits_bwd", 1, _p(dprob), _p(prob), _p(x), _p(w), _p(dx), int(dx_accumulate), _p(dw), _p(dbias),
+          B, H * W, C, _st())

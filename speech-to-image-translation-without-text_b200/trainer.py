@@ -1,0 +1,164 @@
+"""Fused train step: the inner loop of the reference's condGANTrainer.train (StackGAN_v2/trainer.py:529-572, minus
+the out-of-scope Inception scoring) scheduled by hand over the sg2b200 engines — no autograd graph, no Python-side
+loss arithmetic.
+
+    step = G forward -> for each D: train_Dnet (real / wrong / fake passes, 6 BCE terms, backward, Adam)
+           -> train_Gnet (D forwards on the live fakes, BCE + class-aware + KL losses, backward through the Ds
+              and G, Adam) -> EMA of the generator weights
+
+Differences from the reference that do not change any result ("wasted reference work"):
+no dgrad into real/wrong images, no D weight gradients in the G step (the reference zeroes them before use,
+trainer.py:385), the three D passes accumulate their weight gradients in one packed fp32 buffer.
+
+Parameters, Adam moments, EMA shadow and gradients of each network live in flat fp32 buckets (one Adam launch per
+network; the gradient bucket is what NCCL all-reduces in the data-parallel run).
+"""
+import ctypes
+
+import torch
+
+from . import ops
+from .nets import GradSink
+
+_st = ops._st
+_p = ops._p
+
+
+class FlatBucket:
+    """All parameters of one network as views of a single flat fp32 buffer (+ grad / Adam m, v / optional EMA)."""
+
+    def __init__(self, net, with_ema=False):
+        self.params = [p for p in net.parameters()]
+        dev = self.params[0].device
+        sizes = [p.numel() for p in self.params]
+        pad = lambda n: -(-n // 4) * 4           # keep every view 16-byte aligned
+        offs, total = [], 0
+        for n in sizes:
+            offs.append(total)
+            total += pad(n)
+        self.n = total
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros_like(self.flat)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.views = {}
+        with torch.no_grad():
+            for p, o, n in zip(self.params, offs, sizes):
+                self.flat[o:o + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat[o:o + n].view(p.shape)
+                self.views[p] = self.grad[o:o + n].view(p.shape)
+        self.avg = self.flat.clone() if with_ema else None     # trainer.py:494 copy_G_params
+        self.step = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.bc = torch.zeros(2, device=dev, dtype=torch.float32)
+
+    def adam(self, lr, beta1=0.5, beta2=0.999, eps=1e-8, ema_decay=0.999):
+        ops._call("sg2_adam_tick", 1, _p(self.step), _p(self.bc), beta1, beta2, _st())
+        ops._call("sg2_adam_ema", 1, _p(self.flat), _p(self.grad), _p(self.m), _p(self.v), _p(self.avg), self.n,
+                  lr, beta1, beta2, eps, _p(self.bc), ema_decay, _st())
+        self.dirty()
+
+    def dirty(self):
+        """The Adam kernel wrote the weights behind torch's back: invalidate the cached bf16 operand packs."""
+        for p in self.params:
+            p._sg2_version = getattr(p, "_sg2_version", 0) + 1
+
+    def ema_params(self):
+        """EMA weights as a list shaped like net.parameters() (what trainer.py:256 load_params() copies in)."""
+        out, o = [], 0
+        for p in self.params:
+            n = p.numel()
+            out.append(self.avg[o:o + n].view(p.shape))
+            o += -(-n // 4) * 4
+        return out
+
+
+class FusedTrainer:
+    def __init__(self, netG, netsD, cfg, lr_g=None, lr_d=None, all_reduce=None):
+        self.netG, self.netsD = netG, list(netsD)
+        self.cfg = cfg
+        c = cfg.TRAIN.COEFF
+        self.uncond, self.cal, self.kl = float(c.UNCOND_LOSS), float(c.CAL_LOSS), float(c.KL)
+        if self.uncond <= 0:
+            raise NotImplementedError("UNCOND_LOSS == 0 is not used by any reference cfg")
+        self.lr_g = float(cfg.TRAIN.GENERATOR_LR if lr_g is None else lr_g)
+        self.lr_d = float(cfg.TRAIN.DISCRIMINATOR_LR if lr_d is None else lr_d)
+        self.G = netG.engine()
+        self.Ds = [d.engine() for d in self.netsD]
+        self.bG = FlatBucket(netG, with_ema=True)
+        self.bD = [FlatBucket(d) for d in self.netsD]
+        self.all_reduce = all_reduce          # callable(flat_grad_tensor) or None (single GPU)
+        dev = self.bG.flat.device
+        self.dev = dev
+        # loss scalars: errD[i], errG_total, kl, cal
+        self.losses = torch.zeros(len(self.Ds) + 3, device=dev, dtype=torch.float32)
+        self._tables = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _bce(self, probs, targets, weights, loss_slot):
+        """probs (nvec, B) -> dprobs (nvec, B); adds sum_v w_v * BCE(probs[v], t_v) to loss_slot."""
+        nvec, B = probs.shape
+        dprobs = torch.empty_like(probs)
+        key = (tuple(targets), tuple(weights))
+        tw = self._tables.get(key)
+        if tw is None:
+            tw = (torch.tensor(targets, dtype=torch.float32, device=self.dev),
+                  torch.tensor(weights, dtype=torch.float32, device=self.dev))
+            self._tables[key] = tw
+        ops._call("sg2_gan_bce", 1, _p(probs), _p(tw[0]), _p(tw[1]), nvec, B, _p(loss_slot), _p(dprobs), _st())
+        return dprobs
+
+    # ------------------------------------------------------------------ the step
+    def step(self, z, emb, real, wrong, labels, eps=None):
+        """z (B,Z) f32, emb (B,T) f32, real/wrong: lists of (B,3,S,S) f32 NCHW, labels (B,) int32 — all on the GPU.
+        Returns the device tensor [errD_0.., errG_total, kl, cal] (no host sync)."""
+        nD = len(self.Ds)
+        B = z.shape[0]
+        self.losses.zero_()
+        if eps is None:
+            eps = torch.empty(B, self.G.E, device=self.dev, dtype=torch.float32).normal_()   # model.py:190-193
+        fake, mu, logvar, Tg = self.G.forward(z, emb, eps, True)                             # trainer.py:544
+        # ---------------- (2) update the D networks, trainer.py:375-427
+        for i, D in enumerate(self.Ds):
+            bucket = self.bD[i]
+            sink = GradSink(bucket.views)
+            tapes = []
+            probs = torch.empty(6, B, device=self.dev, dtype=torch.float32)
+            for k, img in enumerate((real[i], wrong[i], fake[i])):
+                _, _, _, T = D.forward(img, mu, True, probs[2 * k], probs[2 * k + 1])
+                tapes.append(T)
+            # targets: real -> 1,1 ; wrong -> cond 0, uncond 1 (trainer.py:400-401) ; fake -> 0,0
+            u = self.uncond
+            dprobs = self._bce(probs, (1, 1, 0, 1, 0, 0), (1, u, 1, u, 1, u), self.losses[i:i + 1])
+            for k, T in enumerate(tapes):
+                D.backward(T, dprobs[2 * k], dprobs[2 * k + 1], None, False, False, True, sink)
+            sink.finish()
+            if self.all_reduce is not None:
+                self.all_reduce(bucket.grad)
+            bucket.adam(self.lr_d)
+        # ---------------- (3) update the G network, trainer.py:429-489
+        sinkG = GradSink(self.bG.views)
+        dimgs = []
+        dmu = torch.empty_like(mu)
+        dlogvar = torch.empty_like(logvar)
+        eG, kl, cal = self.losses[nD:nD + 1], self.losses[nD + 1:nD + 2], self.losses[nD + 2:nD + 3]
+        ops._call("sg2_kl_loss", 1, _p(mu), _p(logvar), mu.numel(), self.kl, _p(kl), _p(dmu), _p(dlogvar), _st())
+        for i, D in enumerate(self.Ds):
+            probs = torch.empty(2, B, device=self.dev, dtype=torch.float32)
+            _, _, x_imm, T = D.forward(fake[i], mu, True, probs[0], probs[1])
+            dprobs = self._bce(probs, (1, 1), (1, self.uncond), eG)
+            dx_imm = None
+            if self.cal > 0:
+                ws = torch.empty(2 * B * B, device=self.dev, dtype=torch.float32)
+                dx_imm = torch.empty_like(x_imm)
+                ops._call("sg2_cal_loss", 3, _p(x_imm), _p(labels), B, x_imm.shape[1], _p(ws), _p(cal), _p(dx_imm), _st())
+            _, dimg, dc = D.backward(T, dprobs[0], dprobs[1], dx_imm, True, True, False, None)
+            dimgs.append(dimg)
+            dmu.add_(dc)                         # mu is not detached in train_Gnet (trainer.py:438)
+        self.G.backward(Tg, dimgs, dmu, dlogvar, sinkG)
+        sinkG.finish()
+        if self.all_reduce is not None:
+            self.all_reduce(self.bG.grad)
+        self.bG.adam(self.lr_g)                  # + EMA avg = 0.999 avg + 0.001 p (trainer.py:571-572)
+        # errG_total = sum errG_i + kl + cal (trainer.py:486): fold on device
+        eG.add_(kl).add_(cal)
+        return self.losses
