@@ -54,9 +54,11 @@ int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad_oihw, int Cout, in
  *   fprop : x [B][H][W][Cin] -> y  (CONV3x3: [B][H][W][Cout]; UPCONV3x3: [B][2H][2W][Cout]; CONV4x4S2: [B][H/2][W/2][Cout])
  *   dgrad : dy (shape of y) -> dx [B][H][W][Cin]
  *   wgrad : dwpk[Cout][jobs][Cin] += dy^T (x) im2col(x)   (fp32, red.global.add)
- * out_mode: SG2_OUT_BF16 store, SG2_OUT_F32_ATOMIC (split-K accumulate into a zeroed fp32 buffer), SG2_OUT_F32_STORE. */
+ * out_mode: SG2_OUT_BF16 store, SG2_OUT_F32_ATOMIC (split-K accumulate into a zeroed fp32 buffer), SG2_OUT_F32_STORE.
+ * stats (fprop, optional): fp32 [2][Cout], += per-channel sum and sum of squares of the bf16 outputs, computed in the
+ * epilogue from the TMEM accumulators (the BatchNorm batch statistics, consumed by sg2_bn_act_fwd). */
 int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mode, int B, int H, int W, int Cin,
-                   int Cout, int splitk, void* stream);
+                   int Cout, int splitk, float* stats, void* stream);
 int sg2_conv_dgrad(int kind, const void* dy, const void* wpkT, void* dx, int out_mode, int B, int H, int W, int Cin,
                    int Cout, int splitk, void* stream);
 int sg2_conv_wgrad(int kind, const void* x, const void* dy, float* dwpk, int B, int H, int W, int Cin, int Cout,
@@ -65,16 +67,19 @@ int sg2_conv_wgrad(int kind, const void* x, const void* dy, float* dwpk, int B, 
 /* ---- BatchNorm (+ GLU / LeakyReLU(0.2) / residual) on [P pixels][C channels] bf16 ---------------------
  * nn.BatchNorm2d/1d train mode (model.py:137,147,158,161,218,361,372,387-394): batch mean, biased variance,
  * eps, momentum; running_var gets the unbiased variance; num_batches_tracked += 1.
- * sums: fp64 workspace [2][C], must be zero on entry, is left zero on exit of finalize / bwd. */
-int sg2_bn_stats(const void* x, long long P, int C, double* sums, void* stream);
-int sg2_bn_finalize(double* sums, long long P, int C, float eps, float momentum, float* mean, float* rstd,
-                    float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
+ * stats: fp32 [2][C] per-channel sum / sum of squares, accumulated (+=) into a ZEROED workspace either by the conv
+ * epilogue (sg2_conv_fprop), by sg2_f32_to_bf16_stats (split-K accumulators, fc outputs) or by sg2_bn_stats. */
+int sg2_bn_stats(const void* x, long long P, int C, float* stats, void* stream);
+int sg2_f32_to_bf16_stats(const float* x, void* y, long long P, int C, float* stats, void* stream);
 int sg2_bn_eval_prepare(const float* running_mean, const float* running_var, float eps, float* mean, float* rstd,
                         int C, void* stream);
-/* out = act(bn(x)) (+ residual, ACT_NONE only). GLU (model.py:112-122) halves the channel count. mean==NULL: no BN. */
-int sg2_bn_act_fwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                   const void* residual, void* out, long long P, int C, int act, void* stream);
-/* dx (shape of x) from dout (shape of out); dgamma/dbeta (=|+=). Two passes + a finalize. */
+/* out = act(bn(x)) (+ residual, ACT_NONE only). GLU (model.py:112-122) halves the channel count.
+ * train: stats != NULL -> mean/rstd are derived in-kernel, written to mean/rstd (saved for backward) and the running
+ * statistics are updated.  eval: stats == NULL, mean/rstd are inputs.  mean == NULL: no BatchNorm (D stem). */
+int sg2_bn_act_fwd(const void* x, const float* stats, float* mean, float* rstd, const float* gamma, const float* beta,
+                   const void* residual, void* out, long long P, int C, int act, float eps, float momentum,
+                   float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
+/* dx (shape of x) from dout (shape of out); dgamma/dbeta (=|+=). sums: fp64 [2][C] ZEROED workspace. Two launches. */
 int sg2_bn_act_bwd(const void* x, const void* dout, const float* mean, const float* rstd, const float* gamma,
                    const float* beta, double* sums, void* dx, float* dgamma, float* dbeta, int accumulate,
                    long long P, int C, int act, void* stream);

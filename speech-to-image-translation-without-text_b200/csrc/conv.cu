@@ -131,6 +131,7 @@ struct GatherDesc {
   void* out;
   long long out_off[4], osx, osy, osb;
   int out_mode, splitk;
+  float* stats;
 };
 
 template <int BN, int BK>
@@ -164,6 +165,7 @@ static int launch_fprop_t(const GatherDesc& d, cudaStream_t st) {
   p.sx = d.osx;
   p.out = d.out;
   p.out_mode = d.out_mode;
+  p.stats = d.stats;
   const int smax = max_stages(Cfg::kStageBytes);
   int stages = smax;
   if (stages > KB / p.splitk + 1) stages = KB / p.splitk + 1;
@@ -288,9 +290,12 @@ int sg2_version(void) { return 1; }
 const char* sg2_last_error(void) { return g_err; }
 
 int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mode, int B, int H, int W, int Cin,
-                   int Cout, int splitk, void* stream) {
+                   int Cout, int splitk, float* stats, void* stream) {
   GatherDesc d;
   memset(&d, 0, sizeof(d));
+  d.stats = stats;
+  if (stats && (out_mode != SG2_OUT_BF16 || splitk > 1))
+    SG2_FAIL(SG2_EINVAL, "fused BN statistics need SG2_OUT_BF16 without split-K");
   d.Cin = Cin;
   d.w = wpk;
   d.N = Cout;

@@ -58,53 +58,83 @@ __device__ __forceinline__ int up_lo(int p, int a) { return (p == 0) ? (a == 0 ?
 __device__ __forceinline__ int up_hi(int p, int a) { return (p == 0) ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2); }
 __device__ __forceinline__ int s2_kh(int p, int a) { return (p == 0) ? (a == 0 ? 1 : 3) : (a == 0 ? 2 : 0); }
 
+// Offsets of (co, slot, ci) in the fprop pack / dgrad pack of each kind.
+__device__ __forceinline__ void pack_offsets(int kind, int co, int slot, int ci, int CoP, int CiP, long long& fo,
+                                             long long& to) {
+  if (kind == SG2_CONV3x3) {
+    fo = ((long long)co * 9 + slot) * CiP + ci;
+    to = ((long long)ci * 9 + slot) * CoP + co;
+  } else if (kind == SG2_GEMM) {
+    fo = (long long)co * CiP + ci;
+    to = (long long)ci * CoP + co;
+  } else if (kind == SG2_CONV4x4S2) {
+    const int kh = slot >> 2, kw = slot & 3;
+    fo = ((long long)co * 16 + slot) * CiP + ci;
+    // dgrad pack [g=(py,px)][ci][a*2+b][co] with kh = s2_kh(py,a)
+    const int py = (kh == 1 || kh == 3) ? 0 : 1, a = (kh == 1 || kh == 2) ? 0 : 1;
+    const int px = (kw == 1 || kw == 3) ? 0 : 1, b = (kw == 1 || kw == 2) ? 0 : 1;
+    to = ((((long long)(py * 2 + px) * CiP + ci) * 4) + a * 2 + b) * CoP + co;
+  } else {  // SG2_UPCONV3x3: slot = (py*2+px)*4 + a*2+b
+    const int g = slot >> 2;
+    fo = ((((long long)g * CoP + co) * 4) + (slot & 3)) * CiP + ci;
+    to = ((long long)ci * 16 + slot) * CoP + co;
+  }
+}
+
+// fp32 OIHW -> bf16 packs. One block = 16 output channels x 32 input channels x all taps, staged in shared memory:
+// the OIHW read is a contiguous run per output channel, the two packs are written in 64-byte / 32-byte runs.
+constexpr int kPackCo = 16, kPackCi = 32;
 __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk,
                                     __nv_bfloat16* __restrict__ wpkT, int Cout, int Cin, int CoP, int CiP) {
-  // one thread per (co, slot, ci) of the padded fprop pack; writes both packs
-  const int slots = (kind == SG2_CONV3x3) ? 9 : ((kind == SG2_GEMM || kind == SG2_STEM4x4) ? 1 : 16);
-  const long long total = (long long)CoP * slots * CiP;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int ci = (int)(i % CiP);
-    const int slot = (int)((i / CiP) % slots);
-    const int co = (int)(i / ((long long)CiP * slots));
-    const bool in = (co < Cout) && (ci < Cin);
-    float v = 0.f;
-    long long fo, to;  // offsets in wpk / wpkT
-    if (kind == SG2_STEM4x4) {
-      // GEMM over im2col rows: k = (kh*4+kw)*3 + c  (Cin == 48 == 3*16 here, CiP == 64)
-      if (in) { const int c = ci % 3, t = ci / 3; v = w[((long long)co * 3 + c) * 16 + t]; }
-      fo = (long long)co * CiP + ci;
-      to = (long long)ci * CoP + co;
-    } else if (kind == SG2_CONV3x3) {
-      if (in) v = w[((long long)co * Cin + ci) * 9 + slot];
-      fo = ((long long)co * 9 + slot) * CiP + ci;
-      to = ((long long)ci * 9 + slot) * CoP + co;
-    } else if (kind == SG2_GEMM) {
-      if (in) v = w[(long long)co * Cin + ci];
-      fo = (long long)co * CiP + ci;
-      to = (long long)ci * CoP + co;
-    } else if (kind == SG2_CONV4x4S2) {
-      const int kh = slot >> 2, kw = slot & 3;
-      if (in) v = w[((long long)co * Cin + ci) * 16 + slot];
-      fo = ((long long)co * 16 + slot) * CiP + ci;
-      // dgrad pack [g=(py,px)][ci][a*2+b][co] with kh = s2_kh(py,a)
-      const int py = (kh == 1 || kh == 3) ? 0 : 1, a = (kh == 1 || kh == 2) ? 0 : 1;
-      const int px = (kw == 1 || kw == 3) ? 0 : 1, b = (kw == 1 || kw == 2) ? 0 : 1;
-      to = ((((long long)(py * 2 + px) * CiP + ci) * 4) + a * 2 + b) * CoP + co;
-    } else {  // SG2_UPCONV3x3: slot = (py*2+px)*4 + a*2+b
-      const int g = slot >> 2, a = (slot >> 1) & 1, b = slot & 1, py = g >> 1, px = g & 1;
-      if (in) {
-        const float* wp = w + ((long long)co * Cin + ci) * 9;
-        for (int kh = up_lo(py, a); kh <= up_hi(py, a); ++kh)
-          for (int kw = up_lo(px, b); kw <= up_hi(px, b); ++kw) v += wp[kh * 3 + kw];
-      }
-      fo = ((((long long)g * CoP + co) * 4) + (a * 2 + b)) * CiP + ci;
-      to = ((long long)ci * 16 + slot) * CoP + co;
+  __shared__ float tile[kPackCo][kPackCi][17];
+  const int kk = (kind == SG2_CONV3x3 || kind == SG2_UPCONV3x3) ? 9 : ((kind == SG2_GEMM) ? 1 : 16);   // source taps
+  const int slots = (kind == SG2_CONV3x3) ? 9 : ((kind == SG2_GEMM) ? 1 : 16);                         // packed slots
+  const int ci_tiles = (CiP + kPackCi - 1) / kPackCi, co_tiles = (CoP + kPackCo - 1) / kPackCo;
+  for (int blk = blockIdx.x; blk < ci_tiles * co_tiles; blk += gridDim.x) {
+    const int co0 = (blk / ci_tiles) * kPackCo, ci0 = (blk % ci_tiles) * kPackCi;
+    for (int e = threadIdx.x; e < kPackCo * kPackCi * kk; e += blockDim.x) {
+      const int t = e % kk, cl = (e / kk) % kPackCi, ol = e / (kk * kPackCi);
+      const int co = co0 + ol, ci = ci0 + cl;
+      tile[ol][cl][t] = (co < Cout && ci < Cin) ? w[((long long)co * Cin + ci) * kk + t] : 0.f;
     }
+    __syncthreads();
+    for (int pass = 0; pass < 2; ++pass) {
+      __nv_bfloat16* dst = pass == 0 ? wpk : wpkT;
+      if (!dst) continue;
+      for (int e = threadIdx.x; e < kPackCo * kPackCi * slots; e += blockDim.x) {
+        int ol, cl, slot;
+        if (pass == 0) { cl = e % kPackCi; slot = (e / kPackCi) % slots; ol = e / (kPackCi * slots); }   // ci fastest
+        else { ol = e % kPackCo; slot = (e / kPackCo) % slots; cl = e / (kPackCo * slots); }            // co fastest
+        const int co = co0 + ol, ci = ci0 + cl;
+        if (co >= CoP || ci >= CiP) continue;
+        float v;
+        if (kind == SG2_UPCONV3x3) {
+          const int g = slot >> 2, a = (slot >> 1) & 1, b = slot & 1, py = g >> 1, px = g & 1;
+          v = 0.f;
+          for (int kh = up_lo(py, a); kh <= up_hi(py, a); ++kh)
+            for (int kw = up_lo(px, b); kw <= up_hi(px, b); ++kw) v += tile[ol][cl][kh * 3 + kw];
+        } else {
+          v = tile[ol][cl][slot];
+        }
+        long long fo, to;
+        pack_offsets(kind, co, slot, ci, CoP, CiP, fo, to);
+        dst[pass == 0 ? fo : to] = __float2bfloat16_rn(v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// 3-channel stem (tiny): GEMM over im2col rows, k = (kh*4+kw)*3 + c, padded to CiP.
+__global__ void pack_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk,
+                                 __nv_bfloat16* __restrict__ wpkT, int Cout, int CoP, int CiP) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < CoP * CiP; i += gridDim.x * blockDim.x) {
+    const int ci = i % CiP, co = i / CiP;
+    float v = 0.f;
+    if (co < Cout && ci < 48) { const int c = ci % 3, t = ci / 3; v = w[((long long)co * 3 + c) * 16 + t]; }
     const __nv_bfloat16 bv = __float2bfloat16_rn(v);
-    if (wpk) wpk[fo] = bv;
-    if (wpkT) wpkT[to] = bv;
+    if (wpk) wpk[(long long)co * CiP + ci] = bv;
+    if (wpkT) wpkT[(long long)ci * CoP + co] = bv;
   }
 }
 
@@ -160,30 +190,30 @@ __global__ void unpack_wgrad_kernel(int kind, const float* __restrict__ dwpk, fl
 }
 
 // ============================================================================================ BN statistics
-__global__ void bn_stats_kernel(const uint4* __restrict__ x, long long P, int vc, int cpb, int rpb,
-                                double* __restrict__ sums, int C) {
+// Per-channel sum / sum of squares of a [P][C] tensor into a ZEROED fp32 workspace stats[2][C] (fp32 atomics).
+// IN_F32: the input is a split-K fp32 accumulator; it is rounded to bf16 on the way (written to `y`) and the
+// statistics are those of the rounded values (what BatchNorm-apply reads back).
+template <bool IN_F32>
+__global__ void bn_stats_kernel(const void* __restrict__ xin, uint4* __restrict__ y, long long P, int vc, int cpb,
+                                int rpb, float* __restrict__ stats, int C) {
   const int col = blockIdx.x * cpb + threadIdx.x % cpb;
   const int rl = threadIdx.x / cpb;
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   const long long stride = (long long)gridDim.y * rpb;
-  long long r = (long long)blockIdx.y * rpb + rl;
-  for (; r + 3 * stride < P; r += 4 * stride) {
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = x[(r + u * stride) * vc + col];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float f[8];
-      unpack8(v[u], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
-    }
-  }
-  for (; r < P; r += stride) {
+  for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += stride) {
     float f[8];
-    unpack8(x[r * vc + col], f);
+    if (IN_F32) {
+      const float4* x4 = reinterpret_cast<const float4*>(xin) + (r * vc + col) * 2;
+      const float4 lo = x4[0], hi = x4[1];
+      const float t[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      const uint4 pk = pack8(t);
+      y[r * vc + col] = pk;
+      unpack8(pk, f);
+    } else {
+      unpack8(reinterpret_cast<const uint4*>(xin)[r * vc + col], f);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
   }
@@ -197,32 +227,21 @@ __global__ void bn_stats_kernel(const uint4* __restrict__ x, long long P, int vc
       for (int j = 0; j < 8; ++j) { s[j] += sh[0][threadIdx.x + k * cpb][j]; q[j] += sh[1][threadIdx.x + k * cpb][j]; }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sums[col * 8 + j], (double)s[j]);
-      atomicAdd(&sums[C + col * 8 + j], (double)q[j]);
+      atomicAdd(&stats[col * 8 + j], s[j]);
+      atomicAdd(&stats[C + col * 8 + j], q[j]);
     }
   }
 }
 
-// mean / rstd from the fp64 sums; updates running stats the way nn.BatchNorm does (momentum, unbiased var);
-// zeroes the sums for the next user.
-__global__ void bn_finalize_kernel(double* __restrict__ sums, long long P, int C, float eps, float momentum,
-                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ rmean,
-                                   float* __restrict__ rvar, long long* __restrict__ nbt) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && nbt) *nbt += 1;
-  if (c >= C) return;
-  const double m = sums[c] / (double)P;
-  double var = sums[C + c] / (double)P - m * m;
+// batch mean / rstd of channel c from the accumulated sums (biased variance, like nn.BatchNorm in train mode)
+__device__ __forceinline__ void stat_mean_rstd(const float* __restrict__ stats, int C, int c, double invP, float eps,
+                                               float& m, float& r, float& var_out) {
+  const double mm = (double)stats[c] * invP;
+  double var = (double)stats[C + c] * invP - mm * mm;
   if (var < 0) var = 0;
-  mean[c] = (float)m;
-  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (rmean) {
-    const double unb = P > 1 ? var * (double)P / (double)(P - 1) : var;
-    rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)m;
-    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
-  }
-  sums[c] = 0.0;
-  sums[C + c] = 0.0;
+  m = (float)mm;
+  r = (float)(1.0 / sqrt(var + (double)eps));
+  var_out = (float)var;
 }
 
 __global__ void bn_eval_prepare_kernel(const float* rmean, const float* rvar, float eps, float* mean, float* rstd,
@@ -240,23 +259,51 @@ __global__ void bn_act_fwd_kernel(const uint4* __restrict__ x, const float* __re
                                   const float* __restrict__ rstd, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, const uint4* __restrict__ residual,
                                   uint4* __restrict__ out, long long P, int vc_in, int vc_out, int cpb, int rpb,
-                                  int has_bn) {
+                                  int has_bn, const float* __restrict__ stats, float eps, float momentum,
+                                  float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                  float* __restrict__ rmean, float* __restrict__ rvar, long long* __restrict__ nbt) {
+  // stats != NULL: train mode — mean/rstd are derived here from the sums the conv epilogue accumulated; the first
+  // row-block also saves them for backward and updates the running statistics (momentum, unbiased variance).
   const int col = blockIdx.x * cpb + threadIdx.x % cpb;  // output vector column
   const int rl = threadIdx.x / cpb;
+  const int C = vc_in * 8;
+  const bool writer = stats && blockIdx.y == 0 && rl == 0;
+  const double invP = 1.0 / (double)P;
+  if (writer && nbt && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;
   float sc0[8], sh0[8], sc1[8], sh1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = col * 8 + j;
     if (has_bn) {
-      sc0[j] = gamma[c] * rstd[c];
-      sh0[j] = beta[c] - mean[c] * sc0[j];
+      float m, r, var = 0.f;
+      if (stats) stat_mean_rstd(stats, C, c, invP, eps, m, r, var); else { m = mean[c]; r = rstd[c]; }
+      if (writer) {
+        mean_out[c] = m; rstd_out[c] = r;
+        if (rmean) {
+          const float unb = P > 1 ? var * (float)((double)P / (double)(P - 1)) : var;
+          rmean[c] = (1.f - momentum) * rmean[c] + momentum * m;
+          rvar[c] = (1.f - momentum) * rvar[c] + momentum * unb;
+        }
+      }
+      sc0[j] = gamma[c] * r;
+      sh0[j] = beta[c] - m * sc0[j];
     } else {
       sc0[j] = 1.f; sh0[j] = 0.f;
     }
     if (ACT == ACT_GLU) {
       const int c2 = c + vc_out * 8;
-      sc1[j] = gamma[c2] * rstd[c2];
-      sh1[j] = beta[c2] - mean[c2] * sc1[j];
+      float m, r, var = 0.f;
+      if (stats) stat_mean_rstd(stats, C, c2, invP, eps, m, r, var); else { m = mean[c2]; r = rstd[c2]; }
+      if (writer) {
+        mean_out[c2] = m; rstd_out[c2] = r;
+        if (rmean) {
+          const float unb = P > 1 ? var * (float)((double)P / (double)(P - 1)) : var;
+          rmean[c2] = (1.f - momentum) * rmean[c2] + momentum * m;
+          rvar[c2] = (1.f - momentum) * rvar[c2] + momentum * unb;
+        }
+      }
+      sc1[j] = gamma[c2] * r;
+      sh1[j] = beta[c2] - m * sc1[j];
     }
   }
   for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += (long long)gridDim.y * rpb) {
@@ -374,10 +421,24 @@ __global__ void bn_act_bwd_apply_kernel(const uint4* __restrict__ x, const uint4
                                         const float* __restrict__ mean, const float* __restrict__ rstd,
                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                         const double* __restrict__ sums, long long P, int vc_in, int vc_out, int cpb,
-                                        int rpb, uint4* __restrict__ dx, int C) {
+                                        int rpb, uint4* __restrict__ dx, int C, float* __restrict__ dgamma,
+                                        float* __restrict__ dbeta, int accumulate) {
   const int col = blockIdx.x * cpb + threadIdx.x % cpb;
   const int rl = threadIdx.x / cpb;
   const float invP = 1.f / (float)P;
+  if (dgamma && blockIdx.y == 0 && rl == 0) {   // dgamma = sum dz * xhat, dbeta = sum dz
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = col * 8 + j;
+      const float db = (float)sums[c], dg = (float)sums[C + c];
+      if (accumulate) { dgamma[c] += dg; dbeta[c] += db; } else { dgamma[c] = dg; dbeta[c] = db; }
+      if (ACT == ACT_GLU) {
+        const int c2 = c + vc_out * 8;
+        const float db2 = (float)sums[c2], dg2 = (float)sums[C + c2];
+        if (accumulate) { dgamma[c2] += dg2; dbeta[c2] += db2; } else { dgamma[c2] = dg2; dbeta[c2] = db2; }
+      }
+    }
+  }
   float sc0[8], sh0[8], sc1[8], sh1[8], m0[8], r0[8], m1[8], r1[8], k0[8], k1[8], l0[8], l1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -407,17 +468,6 @@ __global__ void bn_act_bwd_apply_kernel(const uint4* __restrict__ x, const uint4
       dx[r * vc_in + col + vc_out] = pack8(o);
     }
   }
-}
-
-// dgamma = sum dz*xhat, dbeta = sum dz; zero the sums
-__global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, int C, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float db = (float)sums[c], dg = (float)sums[C + c];
-  if (accumulate) { dgamma[c] += dg; dbeta[c] += db; } else { dgamma[c] = dg; dbeta[c] = db; }
-  sums[c] = 0.0;
-  sums[C + c] = 0.0;
 }
 
 // LeakyReLU without BN (D stem): backward is dx = dout * (x > 0 ? 1 : 0.2)
@@ -660,9 +710,14 @@ int sg2_pack_weights(int kind, const float* w, void* wpk, void* wpkT, int Cout, 
                      void* stream) {
   if (kind < 0 || kind > 4 || CoP < Cout || CiP < Cin) EW_FAIL(SG2_EINVAL, "pack_weights: bad arguments");
   if (kind == SG2_STEM4x4 && Cin != 48) EW_FAIL(SG2_EINVAL, "pack_weights: stem expects Cin == 48 (3 x 4 x 4)");
-  const int slots = (kind == SG2_CONV3x3) ? 9 : ((kind == SG2_GEMM || kind == SG2_STEM4x4) ? 1 : 16);
-  const long long total = (long long)CoP * slots * CiP;
-  pack_weights_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(
+  if (kind == SG2_STEM4x4) {
+    pack_stem_kernel<<<grid1d((long long)CoP * CiP), 256, 0, (cudaStream_t)stream>>>(
+        w, (__nv_bfloat16*)wpk, (__nv_bfloat16*)wpkT, Cout, CoP, CiP);
+    return launch_ok("pack_stem");
+  }
+  long long nblk = (long long)((CoP + kPackCo - 1) / kPackCo) * ((CiP + kPackCi - 1) / kPackCi);
+  if (nblk > 148 * 16) nblk = 148 * 16;
+  pack_weights_kernel<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(
       kind, w, (__nv_bfloat16*)wpk, (__nv_bfloat16*)wpkT, Cout, Cin, CoP, CiP);
   return launch_ok("pack_weights");
 }
@@ -679,19 +734,18 @@ int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad, int Cout, int Cin
   return launch_ok("unpack_wgrad");
 }
 
-int sg2_bn_stats(const void* x, long long P, int C, double* sums, void* stream) {
+int sg2_bn_stats(const void* x, long long P, int C, float* stats, void* stream) {
   if (C % 8) EW_FAIL(SG2_EINVAL, "bn_stats: C %% 8");
   Geo g = make_geo(P, C, 148 * 4);
-  bn_stats_kernel<<<g.grid, g.block, 0, (cudaStream_t)stream>>>((const uint4*)x, P, g.vc, g.cpb, g.rpb, sums, C);
+  bn_stats_kernel<false><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(x, nullptr, P, g.vc, g.cpb, g.rpb, stats, C);
   return launch_ok("bn_stats");
 }
 
-int sg2_bn_finalize(double* sums, long long P, int C, float eps, float momentum, float* mean, float* rstd,
-                    float* running_mean, float* running_var, long long* num_batches_tracked, void* stream) {
-  bn_finalize_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, P, C, eps, momentum, mean, rstd,
-                                                                        running_mean, running_var,
-                                                                        num_batches_tracked);
-  return launch_ok("bn_finalize");
+int sg2_f32_to_bf16_stats(const float* x, void* y, long long P, int C, float* stats, void* stream) {
+  if (C % 8) EW_FAIL(SG2_EINVAL, "f32_to_bf16_stats: C %% 8");
+  Geo g = make_geo(P, C, 148 * 4);
+  bn_stats_kernel<true><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(x, (uint4*)y, P, g.vc, g.cpb, g.rpb, stats, C);
+  return launch_ok("f32_to_bf16_stats");
 }
 
 int sg2_bn_eval_prepare(const float* running_mean, const float* running_var, float eps, float* mean, float* rstd,
@@ -701,14 +755,16 @@ int sg2_bn_eval_prepare(const float* running_mean, const float* running_var, flo
   return launch_ok("bn_eval_prepare");
 }
 
-int sg2_bn_act_fwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                   const void* residual, void* out, long long P, int C, int act, void* stream) {
+int sg2_bn_act_fwd(const void* x, const float* stats, float* mean, float* rstd, const float* gamma, const float* beta,
+                   const void* residual, void* out, long long P, int C, int act, float eps, float momentum,
+                   float* running_mean, float* running_var, long long* num_batches_tracked, void* stream) {
   const int Cout = act == ACT_GLU ? C / 2 : C;
   if (Cout % 8) EW_FAIL(SG2_EINVAL, "bn_act_fwd: channels %% 8");
   Geo g = make_geo(P, Cout, 148 * 4);
-  const int has_bn = mean != nullptr;
+  const int has_bn = (mean != nullptr);
+  if (stats && !mean) EW_FAIL(SG2_EINVAL, "bn_act_fwd: stats given without mean/rstd outputs");
   cudaStream_t st = (cudaStream_t)stream;
-#define ARGS (const uint4*)x, mean, rstd, gamma, beta, (const uint4*)residual, (uint4*)out, P, C / 8, Cout / 8, g.cpb, g.rpb, has_bn
+#define ARGS (const uint4*)x, mean, rstd, gamma, beta, (const uint4*)residual, (uint4*)out, P, C / 8, Cout / 8, g.cpb, g.rpb, has_bn, stats, eps, momentum, mean, rstd, running_mean, running_var, num_batches_tracked
   if (act == ACT_GLU) bn_act_fwd_kernel<ACT_GLU><<<g.grid, g.block, 0, st>>>(ARGS);
   else if (act == ACT_LRELU) bn_act_fwd_kernel<ACT_LRELU><<<g.grid, g.block, 0, st>>>(ARGS);
   else bn_act_fwd_kernel<ACT_NONE><<<g.grid, g.block, 0, st>>>(ARGS);
@@ -724,7 +780,7 @@ int sg2_bn_act_bwd(const void* x, const void* dout, const float* mean, const flo
   Geo g = make_geo(P, Cout, 148 * 4);
   cudaStream_t st = (cudaStream_t)stream;
 #define RARGS (const uint4*)x, (const uint4*)dout, mean, rstd, gamma, beta, P, C / 8, Cout / 8, g.cpb, g.rpb, sums, C
-#define AARGS (const uint4*)x, (const uint4*)dout, mean, rstd, gamma, beta, sums, P, C / 8, Cout / 8, g.cpb, g.rpb, (uint4*)dx, C
+#define AARGS (const uint4*)x, (const uint4*)dout, mean, rstd, gamma, beta, sums, P, C / 8, Cout / 8, g.cpb, g.rpb, (uint4*)dx, C, dgamma, dbeta, accumulate
   if (act == ACT_GLU) {
     bn_act_bwd_reduce_kernel<ACT_GLU><<<g.grid, g.block, 0, st>>>(RARGS);
     bn_act_bwd_apply_kernel<ACT_GLU><<<g.grid, g.block, 0, st>>>(AARGS);
@@ -737,7 +793,6 @@ int sg2_bn_act_bwd(const void* x, const void* dout, const float* mean, const flo
   }
 #undef RARGS
 #undef AARGS
-  bn_bwd_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, C, dgamma, dbeta, accumulate);
   return launch_ok("bn_act_bwd");
 }
 

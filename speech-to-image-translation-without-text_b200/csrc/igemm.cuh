@@ -40,7 +40,23 @@ struct FpropParams {
   void* out;
   int out_mode;
   int stages;
+  float* stats;  // optional [2][N] fp32: per-channel sum / sum of squares of the (bf16-rounded) outputs, += (BN statistics)
 };
+
+// Column sums over the 32 lanes of a warp for 32 per-lane values: after the butterfly, lane l holds the sum of v[l].
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = up ? v[j] : v[j + s];
+      const float keep = up ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
 
 template <int BN, int BK>
 struct FpropCfg {
@@ -62,6 +78,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
   uint64_t* empty = full + S;
   uint64_t* tmem_full = empty + S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  __shared__ float s_stats[2 * (BN < 32 ? 32 : BN)];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -148,6 +165,13 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
     const int x = x0 + xi, y = y0 + yi, b = b0 + bi;
     const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
     const long long off = p.out_off[g] + (long long)b * p.sb + (long long)y * p.sy + (long long)x * p.sx + n0;
+    const bool do_stats = (p.stats != nullptr) && (p.out_mode == OUT_BF16);
+    const int et = threadIdx.x - 64;  // 0..127 within the epilogue warps
+    constexpr int SN = BN < 32 ? 32 : BN;
+    if (do_stats) {
+      for (int i = et; i < 2 * SN; i += 128) s_stats[i] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
@@ -156,6 +180,22 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
       uint32_t v[32];
       tmem_ld_32x32(taddr + c0, v);
       tmem_ld_wait();
+      if (do_stats) {
+        // statistics of what BatchNorm will read back: the bf16-rounded outputs of the valid rows
+        float a[32], qq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float r = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j])));
+          a[j] = (valid && (c0 + j < BN)) ? r : 0.f;
+          qq[j] = a[j] * a[j];
+        }
+        const float cs = warp_transpose_sum(a, lane);
+        const float cq = warp_transpose_sum(qq, lane);
+        if (c0 + lane < BN) {
+          atomicAdd(&s_stats[c0 + lane], cs);
+          atomicAdd(&s_stats[SN + c0 + lane], cq);
+        }
+      }
       if (valid) {
         if (p.out_mode == OUT_BF16) {
           uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + c0);
@@ -182,6 +222,13 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
             dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         }
+      }
+    }
+    if (do_stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = et; i < BN; i += 128) {
+        atomicAdd(&p.stats[n0 + i], s_stats[i]);
+        atomicAdd(&p.stats[p.N + n0 + i], s_stats[SN + i]);
       }
     }
     tc_fence_before();

@@ -111,18 +111,21 @@ class ConvBlock:
 
     def fwd(self, x, training, residual=None):
         wpk, _ = self.op.packs()
-        y = ops.conv_fprop(self.kind, x, wpk, self.op.Cout)
-        if self.bn is not None:
-            y2 = y.view(-1, y.shape[-1])
-            if training:
-                mean, rstd = ops.bn_batch_stats(y2, self.bn.running_mean, self.bn.running_var,
-                                                self.bn.num_batches_tracked)
-            else:
-                mean, rstd = ops.bn_eval_stats(self.bn.running_mean, self.bn.running_var)
-            out = ops.bn_act_fwd(y, mean, rstd, self.bn.weight.detach(), self.bn.bias.detach(), self.act, residual)
+        bn = self.bn
+        if bn is None:
+            y = ops.conv_fprop(self.kind, x, wpk, self.op.Cout)
+            return ops.bn_act_fwd(y, None, None, self.act, residual), (x, y, None, None)
+        gamma, beta = bn.weight.detach(), bn.bias.detach()
+        if training:
+            # batch statistics come out of the conv epilogue (or the split-K fp32->bf16 pass): no pass over y
+            st = ops.bn_stats32(self.op.Cout, x.device)
+            y, _ = ops.conv_fprop(self.kind, x, wpk, self.op.Cout, stats=st)
+            out, mean, rstd = ops.bn_act_fwd(y, gamma, beta, self.act, residual, stats=st,
+                                             running=(bn.running_mean, bn.running_var, bn.num_batches_tracked))
         else:
-            mean = rstd = None
-            out = ops.bn_act_fwd(y, None, None, None, None, self.act, residual)
+            y = ops.conv_fprop(self.kind, x, wpk, self.op.Cout)
+            mean, rstd = ops.bn_eval_stats(bn.running_mean, bn.running_var)
+            out = ops.bn_act_fwd(y, gamma, beta, self.act, residual, mean=mean, rstd=rstd)
         return out, (x, y, mean, rstd)
 
     def bwd(self, saved, dout, sink, need_dx=True, need_w=True):
@@ -214,12 +217,16 @@ class GEngine:
         mu, logvar, c = ops.ca_glu_reparam_fwd(T["fc_ca"], eps)
         T["c"] = c
         fc, bn = net.h_net1.fc[0], net.h_net1.fc[1]
-        h = ops.linear_fwd(c, z, fc.weight.detach(), None, True)                       # (B, ngf*32) bf16
+        h32 = ops.linear_fwd(c, z, fc.weight.detach(), None, False)                    # (B, ngf*32) fp32
         if training:
-            mean, rstd = ops.bn_batch_stats(h, bn.running_mean, bn.running_var, bn.num_batches_tracked)
+            st = ops.bn_stats32(h32.shape[1], h32.device)
+            h = ops.f32_to_bf16_stats(h32, st)
+            g, mean, rstd = ops.bn_act_fwd(h, bn.weight.detach(), bn.bias.detach(), ACT_GLU, stats=st,
+                                           running=(bn.running_mean, bn.running_var, bn.num_batches_tracked))
         else:
+            h = ops.f32_to_bf16(h32)
             mean, rstd = ops.bn_eval_stats(bn.running_mean, bn.running_var)
-        g = ops.bn_act_fwd(h, mean, rstd, bn.weight.detach(), bn.bias.detach(), ACT_GLU)  # (B, ngf*16) CHW order
+            g = ops.bn_act_fwd(h, bn.weight.detach(), bn.bias.detach(), ACT_GLU, mean=mean, rstd=rstd)  # CHW order
         T["fc"] = (h, mean, rstd)
         x = ops.chw_hwc(g, B, self.ngf, 16, True).view(B, 4, 4, self.ngf)
         T["ups1"] = []
@@ -307,7 +314,7 @@ class StemBlock:
         col = ops.stem_im2col(img)
         wpk, _ = self.op.packs()
         y = ops.conv_fprop(GEMM, col, wpk, self.op.Cout, flop_scale=self.op.flop_scale).view(B, S // 2, S // 2, self.op.Cout)
-        out = ops.bn_act_fwd(y, None, None, None, None, ACT_LRELU)
+        out = ops.bn_act_fwd(y, None, None, ACT_LRELU)
         return out, (col, y, B, S)
 
     def bwd(self, saved, dout, sink, need_dimg, need_w=True):

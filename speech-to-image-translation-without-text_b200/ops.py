@@ -121,8 +121,9 @@ def _auto_split(m_rows, n_cols, k_blocks):
     return max(1, s)
 
 
-def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0):
-    """x (B,H,W,Cin) bf16 -> y bf16 (B,Ho,Wo,Cout)."""
+def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None):
+    """x (B,H,W,Cin) bf16 -> y bf16 (B,Ho,Wo,Cout). With `stats` (fp32 [2*Cout], zeroed) the epilogue also accumulates
+    the per-channel sum / sum of squares (in the epilogue, or in the fp32->bf16 pass of a split-K layer); returns (y, True)."""
     B, H, W, Cin = x.shape
     fl = flop_scale * _conv_flops(kind, B, H, W, Cin, Cout)
     Ho, Wo = _out_hw(kind, H, W)
@@ -132,11 +133,14 @@ def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0):
         splitk = _auto_split(B * Ho * Wo // groups, Cout, taps * max(1, Cin // 64))
     if splitk > 1:
         y32 = torch.zeros((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
-        _conv_call("sg2_conv_fprop", 2, fl, kind, _p(x), _p(wpk), _p(y32), OUT_F32_ATOMIC, B, H, W, Cin, Cout, splitk, _st())
-        return f32_to_bf16(y32)
+        _conv_call("sg2_conv_fprop", 2, fl, kind, _p(x), _p(wpk), _p(y32), OUT_F32_ATOMIC, B, H, W, Cin, Cout, splitk,
+                   None, _st())
+        if stats is None:
+            return f32_to_bf16(y32)
+        return f32_to_bf16_stats(y32, stats), True
     y = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
-    _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, 1, _st())
-    return y
+    _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, 1, _p(stats), _st())
+    return y if stats is None else (y, True)
 
 
 def conv_dgrad(kind, dy, wpkT, B, H, W, Cin, splitk=None, flop_scale=1.0):
@@ -171,30 +175,59 @@ def conv_wgrad(kind, x, dy, dwpk, splitk=None, flop_scale=1.0):
 
 
 # ------------------------------------------------------------------------------------------ BN / activations
-_sums_cache = {}
+class _ZeroArena:
+    """Ring of zero-initialised scratch for the per-layer BatchNorm sums (fp32 forward, fp64 backward).
+
+    A slot is handed out zeroed, accumulated into by one kernel and read by the next one on the same stream, then
+    never touched again, so instead of one clearing launch per layer the arena clears half of itself whenever the
+    bump pointer enters that half (everything that used it is already ordered before the clear on the stream)."""
+    SIZE = 16 << 20
+
+    def __init__(self, device):
+        self.buf = torch.zeros(self.SIZE, device=device, dtype=torch.uint8)
+        self.off = 0
+
+    def take(self, nbytes, dtype):
+        half = self.SIZE // 2
+        n = -(-nbytes // 256) * 256
+        if n > half:
+            raise RuntimeError("sg2b200: BatchNorm scratch request too large")
+        o = self.off % self.SIZE
+        if (o % half) + n > half:              # do not straddle a half: move to the start of the next one
+            o = (o // half + 1) * half % self.SIZE
+        if o % half == 0 and not (o == 0 and self.off == 0):
+            self.buf[o:o + half].zero_()       # entering a half: clear it (one fill per ~8 MB of slots)
+        self.off = o + n
+        return self.buf[o:o + nbytes].view(dtype)
 
 
-def bn_sums(C, device):
-    """Zero-initialised fp64 [2][C] workspace; the kernels leave it zeroed."""
-    key = (C, device.index, torch.cuda.current_stream().cuda_stream)
-    t = _sums_cache.get(key)
-    if t is None:
-        t = torch.zeros(2 * C, device=device, dtype=torch.float64)
-        _sums_cache[key] = t
-    return t
+_arenas = {}
 
 
-def bn_batch_stats(x2d, rmean, rvar, nbt, update_running=True):
-    """x2d (P, C) bf16 -> mean, rstd (fp32); updates running stats like nn.BatchNorm in train mode."""
+def _arena(device):
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    a = _arenas.get(key)
+    if a is None:
+        a = _arenas[key] = _ZeroArena(device)
+    return a
+
+
+def bn_stats32(C, device):
+    """Zeroed fp32 [2][C] slot for the per-channel sum / sum of squares (filled by a conv epilogue or bn_stats)."""
+    return _arena(device).take(2 * C * 4, torch.float32)
+
+
+def bn_stats(x2d, stats):
     P, C = x2d.shape
-    sums = bn_sums(C, x2d.device)
-    mean = torch.empty(C, device=x2d.device, dtype=torch.float32)
-    rstd = torch.empty_like(mean)
-    _call("sg2_bn_stats", 1, _p(x2d), P, C, _p(sums), _st())
-    _call("sg2_bn_finalize", 1, _p(sums), P, C, BN_EPS, BN_MOMENTUM, _p(mean), _p(rstd),
-          _p(rmean) if update_running else None, _p(rvar) if update_running else None,
-          _p(nbt) if update_running else None, _st())
-    return mean, rstd
+    _call("sg2_bn_stats", 1, _p(x2d), P, C, _p(stats), _st())
+
+
+def f32_to_bf16_stats(x32, stats):
+    """fp32 [..., C] -> bf16 copy, and += per-channel sums of the rounded values into `stats`."""
+    C = x32.shape[-1]
+    y = torch.empty(x32.shape, device=x32.device, dtype=torch.bfloat16)
+    _call("sg2_f32_to_bf16_stats", 1, _p(x32), _p(y), x32.numel() // C, C, _p(stats), _st())
+    return y
 
 
 def bn_eval_stats(rmean, rvar):
@@ -205,12 +238,25 @@ def bn_eval_stats(rmean, rvar):
     return mean, rstd
 
 
-def bn_act_fwd(x, mean, rstd, gamma, beta, act, residual=None):
+def bn_act_fwd(x, gamma, beta, act, residual=None, stats=None, mean=None, rstd=None, running=None):
+    """out = act(bn(x)) (+ residual).
+    train: stats (fp32 sums) given -> returns (out, mean, rstd) with mean/rstd derived in the kernel; `running` =
+           (running_mean, running_var, num_batches_tracked) is updated like nn.BatchNorm does.
+    eval : mean/rstd given.   no BN: gamma is None."""
     C = x.shape[-1]
     P = x.numel() // C
     out = torch.empty(x.shape[:-1] + ((C // 2) if act == ACT_GLU else C,), device=x.device, dtype=torch.bfloat16)
-    _call("sg2_bn_act_fwd", 1, _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(out), P, C, act, _st())
-    return out
+    if gamma is None:
+        _call("sg2_bn_act_fwd", 1, _p(x), None, None, None, None, None, _p(residual), _p(out), P, C, act, BN_EPS,
+              BN_MOMENTUM, None, None, None, _st())
+        return out
+    if stats is not None:
+        mr = torch.empty(2 * C, device=x.device, dtype=torch.float32)
+        mean, rstd = mr[:C], mr[C:]
+    rm, rv, nbt = running if (running is not None and stats is not None) else (None, None, None)
+    _call("sg2_bn_act_fwd", 1, _p(x), _p(stats), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(out), P, C,
+          act, BN_EPS, BN_MOMENTUM, _p(rm), _p(rv), _p(nbt), _st())
+    return (out, mean, rstd) if stats is not None else out
 
 
 def bn_act_bwd(x, dout, mean, rstd, gamma, beta, act, dgamma=None, dbeta=None, accumulate=False):
@@ -218,12 +264,8 @@ def bn_act_bwd(x, dout, mean, rstd, gamma, beta, act, dgamma=None, dbeta=None, a
     C = x.shape[-1]
     P = x.numel() // C
     dx = torch.empty_like(x)
-    if dgamma is None:
-        dgamma = torch.empty(C, device=x.device, dtype=torch.float32)
-        dbeta = torch.empty_like(dgamma)
-        accumulate = False
-    sums = bn_sums(C, x.device)
-    _call("sg2_bn_act_bwd", 3, _p(x), _p(dout), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(sums), _p(dx),
+    sums = _arena(x.device).take(2 * C * 8, torch.float64)
+    _call("sg2_bn_act_bwd", 2, _p(x), _p(dout), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(sums), _p(dx),
           _p(dgamma), _p(dbeta), int(accumulate), P, C, act, _st())
     return dx
 

@@ -53,6 +53,11 @@ def test_conv_fprop_dgrad_wgrad(kind, B, H, W, Ci, Co):
     dyn = dy.permute(0, 2, 3, 1).contiguous().bfloat16()
     y = ops.conv_fprop(kind, xn, wpk, Co, splitk=1)
     assert _rel(y.float().permute(0, 3, 1, 2), y_ref) < 5e-3
+    st = torch.zeros(2 * Co, device="cuda")                                            # BN statistics from the epilogue
+    y3, fused = ops.conv_fprop(kind, xn, wpk, Co, splitk=1, stats=st)
+    assert fused and torch.equal(y3, y)
+    yf = y.float().reshape(-1, Co)
+    assert _rel(st[:Co], yf.sum(0)) < 1e-4 and _rel(st[Co:], (yf * yf).sum(0)) < 1e-5
     y2 = ops.conv_fprop(kind, xn, wpk, Co, splitk=3)                                   # split-K, fp32 atomics
     assert _rel(y2.float().permute(0, 3, 1, 2), y_ref) < 5e-3
     dx = ops.conv_dgrad(kind, dyn, wpkT, B, H, W, Ci, splitk=1)
@@ -81,7 +86,10 @@ def test_bn_act_forward_backward(act, P, C):
     dout = _bf(torch.randn(P, Co, generator=g)).cuda()
     rm, rv, nbt = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"), torch.zeros((), dtype=torch.long, device="cuda")
     xb = x.bfloat16()
-    mean, rstd = ops.bn_batch_stats(xb, rm, rv, nbt)
+    st = ops.bn_stats32(C, xb.device)
+    ops.bn_stats(xb, st)
+    out, mean, rstd = ops.bn_act_fwd(xb, gamma, beta, act, None if res is None else res.bfloat16(), stats=st,
+                                     running=(rm, rv, nbt))
     xr = x.clone().requires_grad_(True)
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     rm2, rv2 = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
@@ -94,8 +102,10 @@ def test_bn_act_forward_backward(act, P, C):
         o_ref = F.leaky_relu(z, 0.2)
     else:
         o_ref = z + res
-    out = ops.bn_act_fwd(xb, mean, rstd, gamma, beta, act, None if res is None else res.bfloat16())
     assert _rel(out.float(), o_ref) < 4e-3
+    out_eval = ops.bn_act_fwd(xb, gamma, beta, act, None if res is None else res.bfloat16(), mean=mean.contiguous(),
+                              rstd=rstd.contiguous())
+    assert torch.equal(out_eval, out)          # eval-style call with given mean/rstd is the same arithmetic
     dx_ref, dg_ref, db_ref = torch.autograd.grad(o_ref, (xr, gr, br), dout)
     dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     dx = ops.bn_act_bwd(xb, dout.bfloat16(), mean, rstd, gamma, beta, act, dg, db, False)

@@ -23,7 +23,7 @@ def wrap(name, fn):
             LOG.append((f"{name} dc", a[2].detach().clone()))
         return out
     return w
-for n in ["conv_fprop", "conv_dgrad", "conv_wgrad", "bn_batch_stats", "bn_act_fwd", "bn_act_bwd", "lrelu_bwd", "add_bf16",
+for n in ["conv_fprop", "conv_dgrad", "conv_wgrad", "f32_to_bf16_stats", "bn_act_fwd", "bn_act_bwd", "lrelu_bwd", "add_bf16",
           "f32_to_bf16", "concat_c", "concat_c_bwd", "stem_im2col", "logits_fwd", "logits_bwd", "nhwc_to_nchw_f32"]:
     setattr(ops, n, wrap(n, getattr(ops, n)))
 

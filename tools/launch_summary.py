@@ -1,0 +1,37 @@
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel totals for the LAST step."""
+import csv, collections, re, sys
+path, nsteps = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 2
+lines = [l for l in open(path) if not l.startswith("==")]
+rows = []
+for row in csv.DictReader(lines):
+    if row.get("Metric Name") == "gpu__time_duration.sum":
+        v = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"]
+        v = v / 1000 if u == "ns" else (v * 1000 if u == "ms" else v)
+        rows.append((int(row["ID"]), re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", ""), v, row.get("Grid Size")))
+# step boundary = the G network's adam_ema launch (4 adam_ema launches per step, the last one closes the step)
+adam = [i for i, r in enumerate(rows) if "adam_ema_kernel" in r[1]]
+per_step = 4
+if len(adam) >= 2 * per_step:
+    it = rows[adam[-per_step - 1] + 1: adam[-1] + 1]
+else:
+    per = len(rows) // nsteps
+    it = rows[-per:]
+tot = sum(r[2] for r in it)
+print(f"{len(rows)} launches total; last step: {len(it)} launches, {tot/1000:.3f} ms of kernel time (cold-cache, serialised)")
+agg = collections.defaultdict(lambda: [0, 0.0])
+for _, k, v, g in it:
+    agg[k][0] += 1
+    agg[k][1] += v
+print(f"{'us':>10s} {'share':>6s} {'n':>5s}  kernel")
+for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:40]:
+    print(f"{t:10.1f} {100*t/tot:5.1f}% {n:5d}  {k[:100]}")
+fam = collections.defaultdict(float)
+for _, k, v, g in it:
+    f = "igemm (tcgen05 conv fprop/dgrad/wgrad)" if "igemm" in k else ("BN/act/elementwise (sg2)" if "sg2::" in k else "torch (fill/add/copy/rng)")
+    fam[f] += v
+for f, t in sorted(fam.items(), key=lambda x: -x[1]):
+    print(f"family {f:45s} {t/1000:8.3f} ms {100*t/tot:5.1f}%")
+if "--top" in sys.argv:
+    for r in sorted(it, key=lambda r: -r[2])[:40]:
+        print(f"{r[2]:9.1f} us id={r[0]} grid={r[3]} {r[1][:90]}")
