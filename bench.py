@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--branches", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -175,10 +176,23 @@ def run_ours(args):
                     for t in (v if isinstance(v, list) else [v]))
     noise = torch.empty(B, cfg.GAN.Z_DIM, device=dev)
 
-    def step_resident(i):
+    cap = None
+    if not args.no_graph:
+        cap = trainer.CapturedStep(tr, B)
+        cap.load(devb[0]["emb"], devb[0]["real"], devb[0]["wrong"], devb[0]["labels"])
+        cap.capture()
+
+    def step_eager(i):
         b = devb[i % n_host]
         noise.normal_(0, 1)                                       # trainer.py:542
         return tr.step(noise, b["emb"], b["real"], b["wrong"], b["labels"])
+
+    def step_resident(i):
+        if cap is None:
+            return step_eager(i)
+        b = devb[i % n_host]
+        cap.load(b["emb"], b["real"], b["wrong"], b["labels"])    # device -> static buffers (on-device copy)
+        return cap.replay()
 
     def barrier():
         if world > 1:
@@ -205,7 +219,7 @@ def run_ours(args):
         sampler.start()
     l0 = ops.launches()
     ms_total = timed(step_resident, args.steps)
-    launches = (ops.launches() - l0)
+    launches = (ops.launches() - l0) if cap is None else cap.launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * B / (ms_step / 1000.0)
@@ -238,9 +252,13 @@ def run_ours(args):
         s = i % 2
         cur = torch.cuda.current_stream()
         cur.wait_event(ready[s])
-        noise.normal_(0, 1)
         b = slots[s]
-        losses = tr.step(noise, b["emb"], b["real"], b["wrong"], b["labels"])
+        if cap is None:
+            noise.normal_(0, 1)
+            losses = tr.step(noise, b["emb"], b["real"], b["wrong"], b["labels"])
+        else:
+            cap.load(b["emb"], b["real"], b["wrong"], b["labels"])
+            losses = cap.replay()
         consumed[s].record(cur)
         loss_host[s].copy_(losses, non_blocking=True)
         loss_ev[s].record(cur)
@@ -261,7 +279,7 @@ def run_ours(args):
     if not args.no_roofline:
         ops.profile_begin()
         for i in range(3):
-            step_resident(i)
+            step_eager(i)                                          # eager: CUDA events bracket every conv launch
         torch.cuda.synchronize()
         prof = ops.profile_end()
         conv = prof["conv"]
@@ -289,6 +307,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": f"birds_3stages.yml {args.branches}-stage 256x256 train step (G + D64/D128/D256 fwd+bwd, Adam, EMA), batch {B}/GPU",
                    "global_batch": world * B, "parallelism": f"dp{world}",
+                   "launch": "eager" if cap is None else "CUDA graph replay (whole step)",
                    "l2": "inputs+activations per step (> 2 GB) exceed the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": tr.losses.numel() * 4},

@@ -212,6 +212,14 @@ def _arena(device):
     return a
 
 
+def arena_reset(device):
+    """Start of a train step: rewind and clear the scratch ring, so a CUDA-graph capture of the step contains every
+    clear its slots need (a replay reuses the same slots each time)."""
+    a = _arena(device)
+    a.off = 0
+    a.buf.zero_()
+
+
 def bn_stats32(C, device):
     """Zeroed fp32 [2][C] slot for the per-channel sum / sum of squares (filled by a conv epilogue or bn_stats)."""
     return _arena(device).take(2 * C * 4, torch.float32)

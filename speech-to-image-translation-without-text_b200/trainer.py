@@ -113,6 +113,7 @@ class FusedTrainer:
         Returns the device tensor [errD_0.., errG_total, kl, cal] (no host sync)."""
         nD = len(self.Ds)
         B = z.shape[0]
+        ops.arena_reset(self.dev)
         self.losses.zero_()
         if eps is None:
             eps = torch.empty(B, self.G.E, device=self.dev, dtype=torch.float32).normal_()   # model.py:190-193
@@ -161,4 +162,55 @@ class FusedTrainer:
         self.bG.adam(self.lr_g)                  # + EMA avg = 0.999 avg + 0.001 p (trainer.py:571-572)
         # errG_total = sum errG_i + kl + cal (trainer.py:486): fold on device
         eG.add_(kl).add_(cal)
+        return self.losses
+
+
+class CapturedStep:
+    """The whole train step (noise draw, G forward, 3 D updates, G update, Adam, EMA — ~1300 kernel launches) captured
+    once into a CUDA graph and replayed per step: the launch-bound inner loop costs one cudaGraphLaunch instead of
+    ~20 ms of Python/ctypes/driver work. Inputs live in static device buffers (`load()` copies a batch in)."""
+
+    def __init__(self, trainer, batch_size, warmup=3):
+        self.tr = trainer
+        cfg, dev = trainer.cfg, trainer.dev
+        B = batch_size
+        self.noise = torch.empty(B, cfg.GAN.Z_DIM, device=dev)
+        self.emb = torch.zeros(B, cfg.TEXT.DIMENSION, device=dev)
+        sizes = [64 * 2 ** i for i in range(len(trainer.Ds))]
+        self.real = [torch.zeros(B, 3, s, s, device=dev) for s in sizes]
+        self.wrong = [torch.zeros(B, 3, s, s, device=dev) for s in sizes]
+        self.labels = torch.zeros(B, device=dev, dtype=torch.int32)
+        self.graph = None
+        self.launches_per_step = 0
+        self._warmup = warmup
+
+    def load(self, emb, real, wrong, labels, non_blocking=True):
+        self.emb.copy_(emb, non_blocking=non_blocking)
+        for d, s in zip(self.real, real):
+            d.copy_(s, non_blocking=non_blocking)
+        for d, s in zip(self.wrong, wrong):
+            d.copy_(s, non_blocking=non_blocking)
+        self.labels.copy_(labels, non_blocking=non_blocking)
+
+    def _body(self):
+        self.noise.normal_(0, 1)                                           # trainer.py:542
+        return self.tr.step(self.noise, self.emb, self.real, self.wrong, self.labels)
+
+    def capture(self):
+        side = torch.cuda.Stream(device=self.tr.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(self._warmup):                                  # eager steps: allocations, packs, caches
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.launches()
+        with torch.cuda.graph(self.graph):
+            self.losses = self._body()
+        self.launches_per_step = ops.launches() - n0
+        return self
+
+    def replay(self):
+        self.graph.replay()
         return self.losses
