@@ -101,24 +101,31 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_
     for (int pass = 0; pass < 2; ++pass) {
       __nv_bfloat16* dst = pass == 0 ? wpk : wpkT;
       if (!dst) continue;
-      for (int e = threadIdx.x; e < kPackCo * kPackCi * slots; e += blockDim.x) {
-        int ol, cl, slot;
-        if (pass == 0) { cl = e % kPackCi; slot = (e / kPackCi) % slots; ol = e / (kPackCi * slots); }   // ci fastest
-        else { ol = e % kPackCo; slot = (e / kPackCo) % slots; cl = e / (kPackCo * slots); }            // co fastest
-        const int co = co0 + ol, ci = ci0 + cl;
+      // each thread produces 8 consecutive elements of the destination's contiguous axis -> one 128-bit store
+      const int inner8 = (pass == 0 ? kPackCi : kPackCo) / 8;
+      const int outer = pass == 0 ? kPackCo : kPackCi;
+      for (int e = threadIdx.x; e < outer * slots * inner8; e += blockDim.x) {
+        const int i8 = e % inner8, slot = (e / inner8) % slots, o = e / (inner8 * slots);
+        const int ol0 = pass == 0 ? o : i8 * 8, cl0 = pass == 0 ? i8 * 8 : o;
+        const int co = co0 + ol0, ci = ci0 + cl0;
         if (co >= CoP || ci >= CiP) continue;
-        float v;
-        if (kind == SG2_UPCONV3x3) {
-          const int g = slot >> 2, a = (slot >> 1) & 1, b = slot & 1, py = g >> 1, px = g & 1;
-          v = 0.f;
-          for (int kh = up_lo(py, a); kh <= up_hi(py, a); ++kh)
-            for (int kw = up_lo(px, b); kw <= up_hi(px, b); ++kw) v += tile[ol][cl][kh * 3 + kw];
-        } else {
-          v = tile[ol][cl][slot];
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int ol = pass == 0 ? ol0 : ol0 + j, cl = pass == 0 ? cl0 + j : cl0;
+          if (kind == SG2_UPCONV3x3) {
+            const int g = slot >> 2, a = (slot >> 1) & 1, b = slot & 1, py = g >> 1, px = g & 1;
+            float acc = 0.f;
+            for (int kh = up_lo(py, a); kh <= up_hi(py, a); ++kh)
+              for (int kw = up_lo(px, b); kw <= up_hi(px, b); ++kw) acc += tile[ol][cl][kh * 3 + kw];
+            v[j] = acc;
+          } else {
+            v[j] = tile[ol][cl][slot];
+          }
         }
         long long fo, to;
         pack_offsets(kind, co, slot, ci, CoP, CiP, fo, to);
-        dst[pass == 0 ? fo : to] = __float2bfloat16_rn(v);
+        *reinterpret_cast<uint4*>(dst + (pass == 0 ? fo : to)) = pack8(v);
       }
     }
     __syncthreads();

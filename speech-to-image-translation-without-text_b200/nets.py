@@ -67,10 +67,14 @@ class GradSink:
     BN / linear / logit gradients accumulate in place. `views` optionally maps parameter -> preallocated
     fp32 tensor (a slice of a flat gradient bucket) that receives the result."""
 
-    def __init__(self, views=None):
+    def __init__(self, views=None, side_stream=None):
         self.g = {}
         self.views = views or {}
         self.pending = []
+        # Weight gradients hang off the backward chain (only the optimiser consumes them), so they can run on a
+        # side stream next to the dgrad / BatchNorm-backward chain; finish() joins.
+        self.side = side_stream
+        self.keep = []
 
     def slot(self, p):
         """(tensor, accumulate_flag) for a small gradient written by a kernel."""
@@ -90,15 +94,35 @@ class GradSink:
         return t
 
     def conv(self, op, x, dy):
-        if op not in self.pending:
-            op.wgrad_begin(x.device)
-            self.pending.append(op)
-        op.wgrad_add(x, dy)
+        if self.side is None:
+            if op not in self.pending:
+                op.wgrad_begin(x.device)
+                self.pending.append(op)
+            op.wgrad_add(x, dy)
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.keep.append((x, dy))              # keep the operands alive until the side stream has consumed them
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            if op not in self.pending:
+                op.wgrad_begin(x.device)
+                self.pending.append(op)
+            op.wgrad_add(x, dy)
 
     def finish(self):
-        for op in self.pending:
-            self.g[op.weight] = op.wgrad_finish(self.views.get(op.weight))
+        if self.side is None:
+            for op in self.pending:
+                self.g[op.weight] = op.wgrad_finish(self.views.get(op.weight))
+        else:
+            with torch.cuda.stream(self.side):
+                for op in self.pending:
+                    self.g[op.weight] = op.wgrad_finish(self.views.get(op.weight))
+                ev = torch.cuda.Event()
+                ev.record(self.side)
+            torch.cuda.current_stream().wait_event(ev)
         self.pending = []
+        self.keep = []
         return self.g
 
 

@@ -14,6 +14,7 @@ Parameters, Adam moments, EMA shadow and gradients of each network live in flat 
 network; the gradient bucket is what NCCL all-reduces in the data-parallel run).
 """
 import ctypes
+import os
 
 import torch
 
@@ -87,6 +88,7 @@ class FusedTrainer:
         self.bG = FlatBucket(netG, with_ema=True)
         self.bD = [FlatBucket(d) for d in self.netsD]
         self.all_reduce = all_reduce          # callable(flat_grad_tensor) or None (single GPU)
+        self.concurrent = os.environ.get("SG2_CONCURRENT", "1") != "0"   # one stream per discriminator (see step())
         dev = self.bG.flat.device
         self.dev = dev
         # loss scalars: errD[i], errG_total, kl, cal
@@ -108,60 +110,91 @@ class FusedTrainer:
         return dprobs
 
     # ------------------------------------------------------------------ the step
+    def _streams(self):
+        if getattr(self, "_sD", None) is None:
+            self._sD = [torch.cuda.Stream(device=self.dev) for _ in self.Ds]
+            self._sW = [torch.cuda.Stream(device=self.dev) for _ in range(len(self.Ds) + 1)]   # wgrad side streams
+        return self._sD
+
     def step(self, z, emb, real, wrong, labels, eps=None):
         """z (B,Z) f32, emb (B,T) f32, real/wrong: lists of (B,3,S,S) f32 NCHW, labels (B,) int32 — all on the GPU.
-        Returns the device tensor [errD_0.., errG_total, kl, cal] (no host sync)."""
+        Returns the device tensor [errD_0.., errG_total, kl, cal] (no host sync).
+
+        Scheduling: the G forward runs on the current stream; the three discriminators are independent of one another
+        (own weights, own optimiser, own image scale), so each D's update AND its part of the G step (forward on the
+        live fake, backward to the image) run on their own stream; the current stream joins them before the G
+        backward. Captured into a CUDA graph these become parallel branches."""
         nD = len(self.Ds)
         B = z.shape[0]
+        main = torch.cuda.current_stream()
+        streams = self._streams() if self.concurrent else [main] * nD
         ops.arena_reset(self.dev)
         self.losses.zero_()
+        parts = torch.zeros(2 * nD, device=self.dev, dtype=torch.float32)    # per-D errG and cal (summed after the join)
         if eps is None:
             eps = torch.empty(B, self.G.E, device=self.dev, dtype=torch.float32).normal_()   # model.py:190-193
         fake, mu, logvar, Tg = self.G.forward(z, emb, eps, True)                             # trainer.py:544
-        # ---------------- (2) update the D networks, trainer.py:375-427
-        for i, D in enumerate(self.Ds):
-            bucket = self.bD[i]
-            sink = GradSink(bucket.views)
-            tapes = []
-            probs = torch.empty(6, B, device=self.dev, dtype=torch.float32)
-            for k, img in enumerate((real[i], wrong[i], fake[i])):
-                _, _, _, T = D.forward(img, mu, True, probs[2 * k], probs[2 * k + 1])
-                tapes.append(T)
-            # targets: real -> 1,1 ; wrong -> cond 0, uncond 1 (trainer.py:400-401) ; fake -> 0,0
-            u = self.uncond
-            dprobs = self._bce(probs, (1, 1, 0, 1, 0, 0), (1, u, 1, u, 1, u), self.losses[i:i + 1])
-            for k, T in enumerate(tapes):
-                D.backward(T, dprobs[2 * k], dprobs[2 * k + 1], None, False, False, True, sink)
-            sink.finish()
-            if self.all_reduce is not None:
-                self.all_reduce(bucket.grad)
-            bucket.adam(self.lr_d)
-        # ---------------- (3) update the G network, trainer.py:429-489
-        sinkG = GradSink(self.bG.views)
-        dimgs = []
         dmu = torch.empty_like(mu)
         dlogvar = torch.empty_like(logvar)
-        eG, kl, cal = self.losses[nD:nD + 1], self.losses[nD + 1:nD + 2], self.losses[nD + 2:nD + 3]
+        kl = self.losses[nD + 1:nD + 2]
         ops._call("sg2_kl_loss", 1, _p(mu), _p(logvar), mu.numel(), self.kl, _p(kl), _p(dmu), _p(dlogvar), _st())
+        fork = torch.cuda.Event()
+        fork.record(main)
+        dimgs, dcs, joins = [None] * nD, [None] * nD, []
+        u = self.uncond
         for i, D in enumerate(self.Ds):
-            probs = torch.empty(2, B, device=self.dev, dtype=torch.float32)
-            _, _, x_imm, T = D.forward(fake[i], mu, True, probs[0], probs[1])
-            dprobs = self._bce(probs, (1, 1), (1, self.uncond), eG)
-            dx_imm = None
-            if self.cal > 0:
-                ws = torch.empty(2 * B * B, device=self.dev, dtype=torch.float32)
-                dx_imm = torch.empty_like(x_imm)
-                ops._call("sg2_cal_loss", 3, _p(x_imm), _p(labels), B, x_imm.shape[1], _p(ws), _p(cal), _p(dx_imm), _st())
-            _, dimg, dc = D.backward(T, dprobs[0], dprobs[1], dx_imm, True, True, False, None)
-            dimgs.append(dimg)
+            st = streams[i]
+            with torch.cuda.stream(st):
+                if st is not main:
+                    st.wait_event(fork)
+                    ops.arena_reset(self.dev)
+                # ---------------- (2) update D_i, trainer.py:375-427
+                bucket = self.bD[i]
+                sink = GradSink(bucket.views, self._sW[i] if self.concurrent else None)
+                tapes = []
+                probs = torch.empty(6, B, device=self.dev, dtype=torch.float32)
+                for k, img in enumerate((real[i], wrong[i], fake[i])):
+                    _, _, _, T = D.forward(img, mu, True, probs[2 * k], probs[2 * k + 1])
+                    tapes.append(T)
+                # targets: real -> 1,1 ; wrong -> cond 0, uncond 1 (trainer.py:400-401) ; fake -> 0,0
+                dprobs = self._bce(probs, (1, 1, 0, 1, 0, 0), (1, u, 1, u, 1, u), self.losses[i:i + 1])
+                for k, T in enumerate(tapes):
+                    D.backward(T, dprobs[2 * k], dprobs[2 * k + 1], None, False, False, True, sink)
+                sink.finish()
+                del tapes
+                if self.all_reduce is not None:
+                    self.all_reduce(bucket.grad)
+                bucket.adam(self.lr_d)
+                # ---------------- (3a) D_i's share of the G step, trainer.py:436-446 (updated D weights, live fake, mu)
+                probs = torch.empty(2, B, device=self.dev, dtype=torch.float32)
+                _, _, x_imm, T = D.forward(fake[i], mu, True, probs[0], probs[1])
+                dprobs = self._bce(probs, (1, 1), (1, u), parts[i:i + 1])
+                dx_imm = None
+                if self.cal > 0:
+                    ws = torch.empty(2 * B * B, device=self.dev, dtype=torch.float32)
+                    dx_imm = torch.empty_like(x_imm)
+                    ops._call("sg2_cal_loss", 3, _p(x_imm), _p(labels), B, x_imm.shape[1], _p(ws),
+                              _p(parts[nD + i:nD + i + 1]), _p(dx_imm), _st())
+                _, dimgs[i], dcs[i] = D.backward(T, dprobs[0], dprobs[1], dx_imm, True, True, False, None)
+                if st is not main:
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    joins.append(ev)
+        for ev in joins:
+            main.wait_event(ev)
+        # ---------------- (3b) G backward + update, trainer.py:480-488
+        for dc in dcs:
             dmu.add_(dc)                         # mu is not detached in train_Gnet (trainer.py:438)
+        sinkG = GradSink(self.bG.views, self._sW[nD] if self.concurrent else None)
         self.G.backward(Tg, dimgs, dmu, dlogvar, sinkG)
         sinkG.finish()
         if self.all_reduce is not None:
             self.all_reduce(self.bG.grad)
         self.bG.adam(self.lr_g)                  # + EMA avg = 0.999 avg + 0.001 p (trainer.py:571-572)
-        # errG_total = sum errG_i + kl + cal (trainer.py:486): fold on device
-        eG.add_(kl).add_(cal)
+        # errG_total = sum_i errG_i + kl + sum_i cal_i (trainer.py:486)
+        cal = self.losses[nD + 2:nD + 3]
+        cal.add_(parts[nD:].sum())
+        self.losses[nD:nD + 1].add_(parts[:nD].sum()).add_(kl).add_(cal)
         return self.losses
 
 
