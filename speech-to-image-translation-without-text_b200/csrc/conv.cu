@@ -9,6 +9,8 @@
 #include "../../include/sg2b200.h"
 #include "common.cuh"
 #include "igemm.cuh"
+#include "halo_probe.cuh"
+#include "tile_conv.cuh"
 
 namespace sg2 {
 
@@ -132,6 +134,7 @@ struct GatherDesc {
   long long out_off[4], osx, osy, osb;
   int out_mode, splitk;
   float* stats;
+  int act;  // epilogue activation (tile kernel only): 0 none, 2 LeakyReLU(0.2)
 };
 
 template <int BN, int BK>
@@ -186,6 +189,207 @@ static int launch_fprop_t(const GatherDesc& d, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ tile-resident launch
+static long long* g_tile_dbg = nullptr;
+static int tile_mode() {
+  static int m = [] {
+    const char* e = getenv("SG2_TILE");
+    return e ? atoi(e) : 1;
+  }();
+  return m;
+}
+
+static int num_sms() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+static bool tile_eligible(const GatherDesc& d) {
+  return tile_mode() && d.out_mode == OUT_BF16 && d.splitk <= 1 && d.Wg >= kTileW && d.Hg >= kTileH;
+}
+
+struct TilePlan {
+  TileParams p;
+  int bn, bk;
+  size_t smem;
+};
+
+// Decide tile shape, weight residency, units and pipeline depths. Returns 0 (planned), 1 (use the gather kernel), <0 error.
+static int plan_tile(const GatherDesc& d, TilePlan& pl) {
+  TileParams& p = pl.p;
+  memset(&p, 0, sizeof(p));
+  const int bk = (d.Cin % 64 == 0) ? 64 : ((d.Cin % 32 == 0) ? 32 : 16);
+  const int row_b = bk * 2;
+  // ---- per-source window extents over all groups' taps; taps sorted by source
+  int mny[4], mxy[4], mnx[4], mxx[4], cnt[4] = {0, 0, 0, 0};
+  for (int s = 0; s < 4; ++s) mny[s] = mnx[s] = 127, mxy[s] = mxx[s] = -127;
+  for (int g = 0; g < d.ngroups; ++g)
+    for (int t = 0; t < d.ntaps; ++t) {
+      const TapF& tp = d.taps[g][t];
+      mny[tp.map] = tp.dy < mny[tp.map] ? tp.dy : mny[tp.map];
+      mxy[tp.map] = tp.dy > mxy[tp.map] ? tp.dy : mxy[tp.map];
+      mnx[tp.map] = tp.dx < mnx[tp.map] ? tp.dx : mnx[tp.map];
+      mxx[tp.map] = tp.dx > mxx[tp.map] ? tp.dx : mxx[tp.map];
+      if (g == 0) ++cnt[tp.map];
+    }
+  int ex = 0, ey = 0;
+  for (int s = 0; s < d.nmaps; ++s) {
+    if (cnt[s] == 0 || cnt[s] != cnt[0]) return 1;
+    ex = (mxx[s] - mnx[s]) > ex ? (mxx[s] - mnx[s]) : ex;
+    ey = (mxy[s] - mny[s]) > ey ? (mxy[s] - mny[s]) : ey;
+    p.org_x[s] = mnx[s];
+    p.org_y[s] = mny[s];
+  }
+  p.pitch = kTileW + ex;
+  p.ph = kTileH + ey;
+  p.nsrc = d.nmaps;
+  p.ntaps = d.ntaps;
+  p.ngroups = d.ngroups;
+  p.kchunks = d.Cin / bk;
+  p.src_begin[0] = 0;
+  for (int s = 0; s < d.nmaps; ++s) p.src_begin[s + 1] = p.src_begin[s] + cnt[s];
+  for (int g = 0; g < d.ngroups; ++g) {
+    int fill[4] = {0, 0, 0, 0};
+    for (int t = 0; t < d.ntaps; ++t) {
+      const TapF& tp = d.taps[g][t];
+      const int slot = p.src_begin[tp.map] + fill[tp.map]++;
+      if (slot >= p.src_begin[tp.map + 1]) return 1;  // groups disagree on taps per source
+      p.tap_off16[g][slot] = (uint32_t)(((tp.dy - p.org_y[tp.map]) * p.pitch + (tp.dx - p.org_x[tp.map])) * row_b) >> 4;
+      p.tap_kblk[g][slot] = t;
+    }
+  }
+  p.box_bytes = p.pitch * p.ph * row_b;
+  p.a_box_bytes = (p.box_bytes + 1023) & ~1023;
+  p.tiles_x = (d.Wg + kTileW - 1) / kTileW;
+  p.tiles_y = (d.Hg + kTileH - 1) / kTileH;
+  p.magic_img = (uint32_t)((0x100000000ULL + (unsigned)(p.tiles_x * p.tiles_y) - 1) / (unsigned)(p.tiles_x * p.tiles_y));
+  p.magic_x = (uint32_t)((0x100000000ULL + (unsigned)p.tiles_x - 1) / (unsigned)p.tiles_x);
+  p.B = d.B;
+  p.Wo = d.Wg;
+  p.Ho = d.Hg;
+  p.N = d.N;
+  for (int g = 0; g < 4; ++g) p.out_off[g] = d.out_off[g];
+  p.sb = d.osb;
+  p.sy = d.osy;
+  p.sx = d.osx;
+  p.out = d.out;
+  p.stats = d.stats;
+  p.act = d.act;
+  {
+    const char* e = getenv("SG2_TILE_DBG");
+    p.dbg = e ? atoi(e) : 0;
+    if (p.dbg & 64) {
+      static long long* buf = nullptr;
+      if (!buf) cudaMalloc(&buf, 1024 * 16 * sizeof(long long));
+      p.dbg_out = buf;
+      g_tile_dbg = buf;
+    }
+  }
+  const int pix_tiles = p.tiles_x * p.tiles_y * p.B;
+  const int bn0 = (d.N == 160 || d.N == 192)
+                      ? d.N
+                      : ((d.N % 256 == 0) ? 256
+                                          : ((d.N % 128 == 0) ? 128 : ((d.N % 64 == 0) ? 64 : ((d.N % 32 == 0) ? 32 : 16))));
+  const int budget = 200 * 1024;
+  const int taps_src = d.ntaps / d.nmaps;
+  int bn = bn0, b_total;
+  const int b_all = d.ntaps * d.Cin * bn0 * 2;
+  if (b_all + 2 * p.a_box_bytes <= budget && tile_mode() != 2) {
+    p.b_resident = 1;  // weight-stationary: this CTA's weight slice is loaded once
+    p.mt = 1;
+    p.tps = taps_src;
+    p.stages = 1;
+    p.na = (budget - b_all) / p.a_box_bytes;
+    b_total = b_all;
+  } else {
+    p.b_resident = 0;
+    p.mt = 1;
+    if (tile_mode() != 3) {
+      // two pixel tiles per unit halve the weight bytes per MMA; needs 2 x 2 x BN TMEM columns and enough units per CTA
+      const int bn2 = (d.N % 128 == 0) ? 128 : (d.N == 192 ? 96 : (d.N == 160 ? 80 : (bn0 <= 128 ? bn0 : 0)));
+      if (bn2) {
+        const int combos2 = d.ngroups * (d.N / bn2);
+        int lanes2 = num_sms() / combos2;
+        lanes2 = lanes2 < 1 ? 1 : lanes2;
+        if ((pix_tiles + 1) / 2 >= 2 * lanes2) {
+          p.mt = 2;
+          bn = bn2;
+        }
+      }
+    }
+    const int kb = bn * row_b;
+    int tps = 1;
+    for (int c = 1; c <= taps_src; ++c)
+      if (taps_src % c == 0 && c * kb <= 16 * 1024) tps = c;
+    p.tps = tps;
+    p.na = 2;
+    int stages = (budget - p.na * p.mt * p.a_box_bytes) / (tps * kb);
+    if (stages < 3) return 1;
+    p.stages = stages > 16 ? 16 : stages;
+    b_total = p.stages * tps * kb;
+    if (p.stages >= 5 && budget - p.na * p.mt * p.a_box_bytes - b_total >= p.mt * p.a_box_bytes) p.na = 3;
+  }
+  if (p.na > 4) p.na = 4;
+  for (int i = 0; i < taps_src; ++i) {
+    if (i % p.tps == 0) p.stage_start_mask |= 1u << i;
+    if ((i + 1) % p.tps == 0) p.stage_end_mask |= 1u << i;
+  }
+  p.n_tiles = d.N / bn;
+  const int combos = p.ngroups * p.n_tiles;
+  const int units = (pix_tiles + p.mt - 1) / p.mt;
+  int lanes = num_sms() / combos;
+  if (lanes < 1) lanes = 1;
+  if (lanes > units) lanes = units;
+  p.lanes = lanes;
+  pl.bn = bn;
+  pl.bk = bk;
+  pl.smem = size_t(p.na) * p.mt * p.a_box_bytes + b_total + 1024 + 512;
+  return 0;
+}
+
+template <int BN, int BK, int NT>
+static int launch_tile_t(const GatherDesc& d, TilePlan& pl, cudaStream_t st) {
+  TileParams& p = pl.p;
+  int rc;
+  for (int s = 0; s < d.nmaps; ++s)
+    if ((rc = make_act_map(&p.tmA[s], d.a[s], BK, p.pitch, p.ph, 1))) return rc;
+  if ((rc = make_w_map(&p.tmB, d.w, (long long)d.ngroups * d.N, (long long)d.ntaps * d.Cin, BK, BN))) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(tile_conv_kernel<BN, BK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+    if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(tile_conv<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  tile_conv_kernel<BN, BK, NT><<<dim3(p.ngroups * p.n_tiles * p.lanes), kTileThreads, pl.smem, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) SG2_FAIL((int)e, "tile_conv<%d,%d> launch: %s", BN, BK, cudaGetErrorString(e));
+  return 0;
+}
+
+// Returns 1 when the layer should run on the gather kernel instead.
+static int launch_tile(const GatherDesc& d, cudaStream_t st) {
+  TilePlan pl;
+  int rc = plan_tile(d, pl);
+  if (rc) return rc;
+  const int bn = pl.bn, bk = pl.bk;
+  const int nt = d.ntaps / d.nmaps;
+  if (nt != 4 && nt != 9) return 1;
+#define SG2_CASE(BN_, BK_)                                                   \
+  if (bn == BN_ && bk == BK_)                                                \
+    return nt == 9 ? launch_tile_t<BN_, BK_, 9>(d, pl, st) : launch_tile_t<BN_, BK_, 4>(d, pl, st);
+  SG2_CASE(256, 64) SG2_CASE(128, 64) SG2_CASE(64, 64) SG2_CASE(32, 64) SG2_CASE(16, 64)
+  SG2_CASE(256, 32) SG2_CASE(128, 32) SG2_CASE(64, 32) SG2_CASE(32, 32) SG2_CASE(16, 32)
+  SG2_CASE(256, 16) SG2_CASE(128, 16) SG2_CASE(64, 16) SG2_CASE(32, 16) SG2_CASE(16, 16)
+  SG2_CASE(160, 64) SG2_CASE(160, 32) SG2_CASE(192, 64) SG2_CASE(192, 32)
+  SG2_CASE(96, 64) SG2_CASE(96, 32) SG2_CASE(80, 64) SG2_CASE(80, 32)
+#undef SG2_CASE
+  return 1;
+}
+
 static int launch_fprop(const GatherDesc& d, cudaStream_t st) {
   if (d.Cin % 16) SG2_FAIL(SG2_EINVAL, "K per tap (%d) must be a multiple of 16", d.Cin);
   if (d.N % 16) SG2_FAIL(SG2_EINVAL, "N (%d) must be a multiple of 16", d.N);
@@ -194,6 +398,10 @@ static int launch_fprop(const GatherDesc& d, cudaStream_t st) {
                      ? d.N
                      : ((d.N % 256 == 0) ? 256
                                          : ((d.N % 128 == 0) ? 128 : ((d.N % 64 == 0) ? 64 : ((d.N % 32 == 0) ? 32 : 16))));
+  if (tile_eligible(d)) {
+    const int rc = launch_tile(d, st);
+    if (rc != 1) return rc;
+  }
 #define SG2_CASE(BN_, BK_) \
   if (bn == BN_ && bk == BK_) return launch_fprop_t<BN_, BK_>(d, st);
   SG2_CASE(256, 64) SG2_CASE(128, 64) SG2_CASE(64, 64) SG2_CASE(32, 64)
@@ -519,6 +727,54 @@ int sg2_conv_wgrad(int kind, const void* x, const void* dy, float* dwpk, int B, 
       SG2_FAIL(SG2_EINVAL, "unknown conv kind %d", kind);
   }
   return launch_wgrad(d, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// EXPERIMENT (tools/probe_halo.py): shifted-window UMMA descriptors over one halo tile; see halo_probe.cuh.
+template <int BN, int BK>
+static int launch_halo_probe(const void* x, const void* wpk, void* y, int B, int H, int W, int Cin, int Cout, int pitch,
+                             int bo_mode, cudaStream_t st) {
+  HaloProbeParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = make_act_map(&p.tmA, dense_view(x, B, H, W, Cin), BK, pitch, kHaloTH + 2, 1))) return rc;
+  if ((rc = make_w_map(&p.tmB, wpk, Cout, 9LL * Cin, BK, BN))) return rc;
+  p.kchunks = Cin / BK;
+  p.pitch = pitch;
+  p.bo_mode = bo_mode;
+  p.tiles_x = (W + kHaloTW - 1) / kHaloTW;
+  p.tiles_y = (H + kHaloTH - 1) / kHaloTH;
+  p.W = W;
+  p.H = H;
+  p.B = B;
+  p.N = Cout;
+  p.out = y;
+  p.stages = 4;
+  const int a_bytes = ((pitch * (kHaloTH + 2) * BK * 2) + 1023) & ~1023;
+  const size_t smem = 2 * a_bytes + p.stages * BN * BK * 2 + 1024 + 256;
+  cudaError_t e = cudaFuncSetAttribute(halo_probe_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(halo_probe): %s", cudaGetErrorString(e));
+  dim3 grid(p.tiles_x * p.tiles_y * B, Cout / BN, 1);
+  halo_probe_kernel<BN, BK><<<grid, kNumThreads, smem, st>>>(p);
+  SG2_LAUNCH_OK("halo_probe");
+}
+
+extern "C" {
+/* DIAGNOSTICS: copy the tile kernel's wait-cycle counters (SG2_TILE_DBG & 64) of the last launch to the host. */
+int sg2_tile_dbg_read(long long* host_out, int n) {
+  if (!g_tile_dbg) SG2_FAIL(SG2_EINVAL, "no tile debug buffer");
+  cudaDeviceSynchronize();
+  cudaMemcpy(host_out, g_tile_dbg, n * sizeof(long long), cudaMemcpyDeviceToHost);
+  return 0;
+}
+int sg2_probe_halo_fprop(const void* x, const void* wpk, void* y, int B, int H, int W, int Cin, int Cout, int pitch,
+                         int bo_mode, void* stream) {
+  if (pitch < 10 || pitch > 16) SG2_FAIL(SG2_EINVAL, "pitch %d", pitch);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cin % 64 == 0 && Cout % 64 == 0) return launch_halo_probe<64, 64>(x, wpk, y, B, H, W, Cin, Cout, pitch, bo_mode, st);
+  if (Cin % 32 == 0 && Cout % 32 == 0) return launch_halo_probe<32, 32>(x, wpk, y, B, H, W, Cin, Cout, pitch, bo_mode, st);
+  SG2_FAIL(SG2_EINVAL, "halo probe: unsupported channels %d -> %d", Cin, Cout);
 }
 
 }  // extern "C"

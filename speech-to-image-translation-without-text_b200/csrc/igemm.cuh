@@ -117,12 +117,15 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Issue loops run with the WHOLE warp convergent and one elected lane issuing (elect.sync): the compiler then keeps
+  // descriptors in uniform registers and emits back-to-back UTCHMMA/UTMALDG. A divergent `if (lane == 0)` body costs
+  // ~146 cycles per tcgen05.mma (tools/probe_mma.py) against a 64-cycle tensor floor at N = 128.
   if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nkb; ++it) {
+      mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&full[s], Cfg::kStageBytes);
         const int kb = kb_begin + it;
         const int tap = kb / p.kchunks;
@@ -133,28 +136,38 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
         tma_load_4d(&p.tmA[tp.map], &full[s], sa, ch * BK, x0 + tp.dx, y0 + tp.dy, b0);
         tma_load_2d(&p.tmB, &full[s], sb, kb * BK, n0 + g * p.N);
       }
+      __syncwarp();
+      if (++s == S) {
+        s = 0;
+        ph ^= 1;
+      }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 0, 0);
-      constexpr uint32_t swc = swizzle_code(Cfg::kSw);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + size_t(s) * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kABytes;
-        const uint64_t adesc = make_smem_desc(sa, 16, 8 * Cfg::kSw, swc);
-        const uint64_t bdesc = make_smem_desc(sb, 16, 8 * Cfg::kSw, swc);
+    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 0, 0);
+    constexpr uint32_t swc = swizzle_code(Cfg::kSw);
+    const uint64_t adesc0 = make_smem_desc(smem_u32(smem), 16, 8 * Cfg::kSw, swc);
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + Cfg::kABytes, 16, 8 * Cfg::kSw, swc);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nkb; ++it) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t so = uint64_t((uint32_t(s) * uint32_t(Cfg::kStageBytes)) >> 4);
+        const uint64_t adesc = adesc0 + so, bdesc = bdesc0 + so;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
+        for (int k = 0; k < BK / 16; ++k)
           umma_f16(tmem_base, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
-        }
         umma_commit(&empty[s]);
       }
-      umma_commit(tmem_full);
+      __syncwarp();
+      if (++s == S) {
+        s = 0;
+        ph ^= 1;
+      }
     }
+    if (elect_one()) umma_commit(tmem_full);
+    __syncwarp();
   } else {
     // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
     const int q = warp & 3;
@@ -317,13 +330,13 @@ __global__ void __launch_bounds__(kNumThreads) igemm_wgrad_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const JobW jb = p.jobs[job];
-      const uint32_t tx_bytes = a_chunks * Cfg::kAChunkBytes + b_chunks * Cfg::kBChunkBytes;
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+    const JobW jb = p.jobs[job];
+    const uint32_t tx_bytes = a_chunks * Cfg::kAChunkBytes + b_chunks * Cfg::kBChunkBytes;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nkb; ++it) {
+      mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&full[s], tx_bytes);
         int t = kb_begin + it;
         const int tx = t % p.tiles_x;
@@ -336,24 +349,28 @@ __global__ void __launch_bounds__(kNumThreads) igemm_wgrad_kernel(const __grid_c
         for (int c = 0; c < a_chunks; ++c)
           tma_load_4d(&p.tmA[jb.amap], &full[s], sa + c * Cfg::kAChunkBytes, m0 + c * CWA, x0, y0, b0);
         for (int c = 0; c < b_chunks; ++c)
-          tma_load_4d(&p.tmB[jb.bmap], &full[s], sb + c * Cfg::kBChunkBytes, n0 + c * CWB, x0 + jb.dx, y0 + jb.dy,
-                      b0);
+          tma_load_4d(&p.tmB[jb.bmap], &full[s], sb + c * Cfg::kBChunkBytes, n0 + c * CWB, x0 + jb.dx, y0 + jb.dy, b0);
+      }
+      __syncwarp();
+      if (++s == S) {
+        s = 0;
+        ph ^= 1;
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 1, 1);
-      constexpr uint32_t swa = swizzle_code(CWA * 2), swb = swizzle_code(CWB * 2);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + size_t(s) * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kABytes;
-        // MN-major: LBO = bytes between consecutive channel chunks, SBO = bytes between 8-pixel groups.
-        const uint64_t adesc = make_smem_desc(sa, Cfg::kAChunkBytes, 8 * CWA * 2, swa);
-        const uint64_t bdesc = make_smem_desc(sb, Cfg::kBChunkBytes, 8 * CWB * 2, swb);
+    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 1, 1);
+    constexpr uint32_t swa = swizzle_code(CWA * 2), swb = swizzle_code(CWB * 2);
+    // MN-major: LBO = bytes between consecutive channel chunks, SBO = bytes between 8-pixel groups.
+    const uint64_t adesc0 = make_smem_desc(smem_u32(smem), Cfg::kAChunkBytes, 8 * CWA * 2, swa);
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + Cfg::kABytes, Cfg::kBChunkBytes, 8 * CWB * 2, swb);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nkb; ++it) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t so = uint64_t((uint32_t(s) * uint32_t(Cfg::kStageBytes)) >> 4);
+        const uint64_t adesc = adesc0 + so, bdesc = bdesc0 + so;
 #pragma unroll
         for (int k = 0; k < kWgradBKP / 16; ++k) {
           const uint64_t ka = uint64_t((k * 16 * CWA * 2) >> 4);
@@ -362,8 +379,14 @@ __global__ void __launch_bounds__(kNumThreads) igemm_wgrad_kernel(const __grid_c
         }
         umma_commit(&empty[s]);
       }
-      umma_commit(tmem_full);
+      __syncwarp();
+      if (++s == S) {
+        s = 0;
+        ph ^= 1;
+      }
     }
+    if (elect_one()) umma_commit(tmem_full);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;

@@ -27,6 +27,9 @@ CONV_CASES = [  # kind, B, H, W, Cin, Cout
     (0, 2, 16, 16, 64, 64), (0, 3, 8, 8, 32, 32), (0, 2, 32, 32, 160, 64), (0, 2, 16, 16, 64, 192),
     (0, 5, 4, 4, 128, 256), (0, 2, 32, 32, 16, 32), (1, 3, 4, 4, 64, 64), (1, 2, 16, 16, 32, 32),
     (2, 2, 16, 16, 64, 128), (2, 5, 8, 8, 128, 256), (3, 1, 1, 640, 64, 64),
+    # tile-resident kernel (output grid >= 16 x 8): partial edge tiles, four parity-plane sources, every swizzle width
+    (0, 1, 24, 20, 32, 96), (2, 2, 32, 32, 64, 128), (2, 1, 48, 40, 32, 64), (1, 1, 24, 20, 64, 32),
+    (0, 2, 32, 16, 128, 256), (2, 1, 32, 32, 16, 32),
 ]
 
 
