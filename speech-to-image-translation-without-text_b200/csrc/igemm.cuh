@@ -43,21 +43,6 @@ struct FpropParams {
   float* stats;  // optional [2][N] fp32: per-channel sum / sum of squares of the (bf16-rounded) outputs, += (BN statistics)
 };
 
-// Column sums over the 32 lanes of a warp for 32 per-lane values: after the butterfly, lane l holds the sum of v[l].
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int j = 0; j < s; ++j) {
-      const float send = up ? v[j] : v[j + s];
-      const float keep = up ? v[j + s] : v[j];
-      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
-
 template <int BN, int BK>
 struct FpropCfg {
   static constexpr int kSw = BK * 2;  // swizzle span in bytes (128/64/32)

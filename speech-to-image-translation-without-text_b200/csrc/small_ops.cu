@@ -19,33 +19,50 @@ __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + __expf(-x))
 
 // ------------------------------------------------------------------------------------------ linear (tiny M)
 // out[m][n] = sum_k x(m,k) * w[n][k] (+ bias[n]);  x(m,k) = k < K1 ? x1[m][k] : x2[m][k-K1]  (cat(c_code, z))
-// One warp per output feature n; lanes stride K (coalesced weight row); M rows in chunks of 8.
+// Weight-bandwidth bound (M = batch rows <= 64): the activations are staged in shared memory (K chunks of 256), each
+// warp walks `npw` output features, lanes stride K (coalesced weight rows read ONCE), 32 batch rows accumulate in
+// registers and one butterfly transpose-sum per feature leaves row m's result in lane m.
+constexpr int kLinKC = 256;
+__device__ __forceinline__ float lin_x(const float* x1, int K1, const float* x2, int K2, int m, int k) {
+  return k < K1 ? x1[(long long)m * K1 + k] : x2[(long long)m * K2 + (k - K1)];
+}
 template <bool OUT_BF16>
-__global__ void linear_fwd_kernel(const float* __restrict__ x1, int K1, const float* __restrict__ x2, int K2,
-                                  const float* __restrict__ w, const float* __restrict__ bias, void* __restrict__ out,
-                                  int M, int N) {
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (n >= N) return;
+__global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ x1, int K1, const float* __restrict__ x2,
+                                                         int K2, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, void* __restrict__ out, int M,
+                                                         int N, int npw) {
+  __shared__ float xs[32][kLinKC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = K1 + K2;
-  const float* wr = w + (long long)n * K;
-  for (int m0 = 0; m0 < M; m0 += 8) {
-    float acc[8];
+  const int nchunks = (K + kLinKC - 1) / kLinKC;
+  const int nbase = (blockIdx.x * 8 + warp) * npw;
+  for (int m0 = 0; m0 < M; m0 += 32) {
+    for (int i = 0; i < npw; ++i) {
+      const int n = nbase + i;
+      float acc[32];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const float wv = wr[k];
+      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+      for (int c = 0; c < nchunks; ++c) {
+        if (nchunks > 1 || i == 0) {  // a single chunk stays staged for all features of the block
+          __syncthreads();
+          for (int e = threadIdx.x; e < 32 * kLinKC; e += 256) {
+            const int m = m0 + e / kLinKC, k = c * kLinKC + e % kLinKC;
+            xs[e / kLinKC][e % kLinKC] = (m < M && k < K) ? lin_x(x1, K1, x2, K2, m, k) : 0.f;
+          }
+          __syncthreads();
+        }
+        if (n < N) {
+          const int kend = min(kLinKC, K - c * kLinKC);
+          for (int kk = lane; kk < kend; kk += 32) {
+            const float wv = w[(long long)n * K + c * kLinKC + kk];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int m = m0 + j;
-        if (m < M) acc[j] += wv * (k < K1 ? x1[(long long)m * K1 + k] : x2[(long long)m * K2 + (k - K1)]);
+            for (int j = 0; j < 32; ++j) acc[j] = fmaf(wv, xs[j][kk], acc[j]);
+          }
+        }
       }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float s = warp_sum(acc[j]);
-      const int m = m0 + j;
-      if (lane == 0 && m < M) {
+      const float s = warp_transpose_sum(acc, lane);  // lane m: sum over k of row m0 + m
+      const int m = m0 + lane;
+      if (n < N && m < M) {
         const float v = s + (bias ? bias[n] : 0.f);
         if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[(long long)m * N + n] = __float2bfloat16_rn(v);
         else reinterpret_cast<float*>(out)[(long long)m * N + n] = v;
@@ -54,59 +71,79 @@ __global__ void linear_fwd_kernel(const float* __restrict__ x1, int K1, const fl
   }
 }
 
-// dw[n][k] (+)= sum_m dy[m][n] * x(m,k);  dbias[n] (+)= sum_m dy[m][n].   thread per (n, k) pair, k fastest.
+// dw[n][k] (+)= sum_m dy[m][n] * x(m,k);  dbias[n] (+)= sum_m dy[m][n].
+// block = 256 consecutive k (grid.y = k slabs) x kLinNB features (grid.x): thread k keeps its activation column in
+// registers, the dy columns of the block sit in shared memory (broadcast reads), dw rows are written coalesced.
+constexpr int kLinNB = 64;
 template <bool DY_BF16>
-__global__ void linear_bwd_w_kernel(const void* __restrict__ dy, const float* __restrict__ x1, int K1,
-                                    const float* __restrict__ x2, int K2, float* __restrict__ dw,
-                                    float* __restrict__ dbias, int M, int N, int accumulate) {
+__global__ void __launch_bounds__(256) linear_bwd_w_kernel(const void* __restrict__ dy, const float* __restrict__ x1,
+                                                           int K1, const float* __restrict__ x2, int K2,
+                                                           float* __restrict__ dw, float* __restrict__ dbias, int M, int N,
+                                                           int accumulate) {
+  __shared__ float ds[64][kLinNB];  // [m][n]
   const int K = K1 + K2;
-  const long long total = (long long)N * K;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % K);
-    const int n = (int)(i / K);
-    float acc = 0.f, accb = 0.f;
-    for (int m = 0; m < M; ++m) {
-      const float d = DY_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy)[(long long)m * N + n])
-                              : reinterpret_cast<const float*>(dy)[(long long)m * N + n];
-      acc += d * (k < K1 ? x1[(long long)m * K1 + k] : x2[(long long)m * K2 + (k - K1)]);
-      accb += d;
-    }
-    if (accumulate) dw[i] += acc; else dw[i] = acc;
-    if (dbias && k == 0) { if (accumulate) dbias[n] += accb; else dbias[n] = accb; }
+  const int n0 = blockIdx.x * kLinNB;
+  const int k = blockIdx.y * 256 + threadIdx.x;
+  for (int e = threadIdx.x; e < M * kLinNB; e += 256) {
+    const int m = e / kLinNB, n = n0 + e % kLinNB;
+    float d = 0.f;
+    if (n < N)
+      d = DY_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy)[(long long)m * N + n])
+                  : reinterpret_cast<const float*>(dy)[(long long)m * N + n];
+    ds[m][e % kLinNB] = d;
+  }
+  __syncthreads();
+  if (dbias && blockIdx.y == 0 && threadIdx.x < kLinNB && n0 + threadIdx.x < N) {
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) s += ds[m][threadIdx.x];
+    if (accumulate) dbias[n0 + threadIdx.x] += s; else dbias[n0 + threadIdx.x] = s;
+  }
+  if (k >= K) return;
+  float xr[64];
+#pragma unroll
+  for (int m = 0; m < 64; ++m) xr[m] = m < M ? lin_x(x1, K1, x2, K2, m, k) : 0.f;
+  const int nend = min(kLinNB, N - n0);
+  for (int j = 0; j < nend; ++j) {
+    float acc = 0.f;
+#pragma unroll
+    for (int m = 0; m < 64; ++m)
+      if (m < M) acc = fmaf(ds[m][j], xr[m], acc);
+    float* o = dw + (long long)(n0 + j) * K + k;
+    if (accumulate) *o += acc; else *o = acc;
   }
 }
 
 // dx[m][k] = sum_n dy[m][n] * w[n][k] for k < Kout (only the leading Kout inputs need a gradient).
-// grid.x = n-slabs; thread = k; atomics into a zeroed dx.
+// grid.x = feature slabs of kLinNB; thread = k; the slab's dy sits in shared memory, all batch rows accumulate in
+// registers while the weight rows are read once; fp32 atomics into a zeroed dx.
 template <bool DY_BF16>
-__global__ void linear_bwd_x_kernel(const void* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
-                                    int M, int N, int K, int Kout, int slab) {
-  const int k = threadIdx.x;
-  const int nb = blockIdx.x * slab;
-  const int ne = min(N, nb + slab);
-  for (int m0 = 0; m0 < M; m0 += 8) {
-    float acc[8];
+__global__ void __launch_bounds__(256) linear_bwd_x_kernel(const void* __restrict__ dy, const float* __restrict__ w,
+                                                           float* __restrict__ dx, int M, int N, int K, int Kout) {
+  __shared__ float ds[64][kLinNB];  // [m][n]
+  const int n0 = blockIdx.x * kLinNB;
+  for (int e = threadIdx.x; e < M * kLinNB; e += blockDim.x) {
+    const int m = e / kLinNB, n = n0 + e % kLinNB;
+    float d = 0.f;
+    if (n < N)
+      d = DY_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy)[(long long)m * N + n])
+                  : reinterpret_cast<const float*>(dy)[(long long)m * N + n];
+    ds[m][e % kLinNB] = d;
+  }
+  __syncthreads();
+  const int nend = min(kLinNB, N - n0);
+  for (int k = threadIdx.x; k < Kout; k += blockDim.x) {
+    float acc[64];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    if (k < Kout) {
-      for (int n = nb; n < ne; ++n) {
-        const float wv = w[(long long)n * K + k];
+    for (int m = 0; m < 64; ++m) acc[m] = 0.f;
+    for (int j = 0; j < nend; ++j) {
+      const float wv = w[(long long)(n0 + j) * K + k];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int m = m0 + j;
-          if (m < M) {
-            const float d = DY_BF16
-                                ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy)[(long long)m * N + n])
-                                : reinterpret_cast<const float*>(dy)[(long long)m * N + n];
-            acc[j] += d * wv;
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (m0 + j < M) atomicAdd(&dx[(long long)(m0 + j) * Kout + k], acc[j]);
+      for (int m = 0; m < 64; ++m)
+        if (m < M) acc[m] = fmaf(ds[m][j], wv, acc[m]);
     }
+#pragma unroll
+    for (int m = 0; m < 64; ++m)
+      if (m < M) atomicAdd(&dx[(long long)m * Kout + k], acc[m]);
   }
 }
 
@@ -362,40 +399,52 @@ extern "C" {
 int sg2_linear_fwd(const float* x1, int K1, const float* x2, int K2, const float* w, const float* bias, void* out,
                    int out_bf16, int M, int N, void* stream) {
   if (M < 1 || M > 4096) SG2_FAIL(SG2_EINVAL, "linear_fwd: M=%d", M);
-  const int wpb = 8;
-  dim3 grid((N + wpb - 1) / wpb), block(wpb * 32);
+  // features per warp: enough to amortise the activation staging, few enough to fill the SMs (8 warps per block)
+  int npw = N / (8 * 148 * 2);
+  npw = npw < 1 ? 1 : (npw > 8 ? 8 : npw);
+  dim3 grid((N + 8 * npw - 1) / (8 * npw)), block(256);
   if (out_bf16)
-    linear_fwd_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(x1, K1, x2, K2, w, bias, out, M, N);
+    linear_fwd_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(x1, K1, x2, K2, w, bias, out, M, N, npw);
   else
-    linear_fwd_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(x1, K1, x2, K2, w, bias, out, M, N);
+    linear_fwd_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(x1, K1, x2, K2, w, bias, out, M, N, npw);
   SG2_LAUNCH_OK("linear_fwd");
 }
 
 int sg2_linear_bwd_w(const void* dy, int dy_bf16, const float* x1, int K1, const float* x2, int K2, float* dw,
                      float* dbias, int M, int N, int accumulate, void* stream) {
-  const long long total = (long long)N * (K1 + K2);
-  if (dy_bf16)
-    linear_bwd_w_kernel<true><<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(dy, x1, K1, x2, K2, dw, dbias, M, N,
-                                                                               accumulate);
-  else
-    linear_bwd_w_kernel<false><<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(dy, x1, K1, x2, K2, dw, dbias, M, N,
-                                                                                accumulate);
+  const int K = K1 + K2;
+  dim3 grid((N + kLinNB - 1) / kLinNB, (K + 255) / 256);
+  for (int m0 = 0; m0 < M; m0 += 64) {  // batch rows in slabs of 64 (the kernel keeps one activation column in registers)
+    const int mc = M - m0 < 64 ? M - m0 : 64;
+    const int acc = (accumulate || m0 > 0) ? 1 : 0;
+    const float* x1o = x1 + (size_t)m0 * K1;
+    const float* x2o = x2 ? x2 + (size_t)m0 * K2 : nullptr;
+    if (dy_bf16)
+      linear_bwd_w_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)m0 * N, x1o, K1, x2o, K2, dw, dbias, mc, N, acc);
+    else
+      linear_bwd_w_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(dy) + (size_t)m0 * N,
+                                                                         x1o, K1, x2o, K2, dw, dbias, mc, N, acc);
+  }
   SG2_LAUNCH_OK("linear_bwd_w");
 }
 
 int sg2_linear_bwd_x(const void* dy, int dy_bf16, const float* w, float* dx, int M, int N, int K, int Kout,
                      void* stream) {
-  if (Kout > 1024 || Kout > K) SG2_FAIL(SG2_EINVAL, "linear_bwd_x: Kout=%d", Kout);
+  if (Kout > K) SG2_FAIL(SG2_EINVAL, "linear_bwd_x: Kout=%d", Kout);
   cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)M * Kout, (cudaStream_t)stream);
   if (e != cudaSuccess) SG2_FAIL((int)e, "linear_bwd_x memset: %s", cudaGetErrorString(e));
-  const int slab = 64;
-  const int threads = ((Kout + 31) / 32) * 32;
-  if (dy_bf16)
-    linear_bwd_x_kernel<true><<<(N + slab - 1) / slab, threads, 0, (cudaStream_t)stream>>>(dy, w, dx, M, N, K, Kout,
-                                                                                          slab);
-  else
-    linear_bwd_x_kernel<false><<<(N + slab - 1) / slab, threads, 0, (cudaStream_t)stream>>>(dy, w, dx, M, N, K, Kout,
-                                                                                           slab);
+  int threads = ((Kout + 31) / 32) * 32;
+  threads = threads > 256 ? 256 : threads;
+  for (int m0 = 0; m0 < M; m0 += 64) {
+    const int mc = M - m0 < 64 ? M - m0 : 64;
+    if (dy_bf16)
+      linear_bwd_x_kernel<true><<<(N + kLinNB - 1) / kLinNB, threads, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)m0 * N, w, dx + (size_t)m0 * Kout, mc, N, K, Kout);
+    else
+      linear_bwd_x_kernel<false><<<(N + kLinNB - 1) / kLinNB, threads, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const float*>(dy) + (size_t)m0 * N, w, dx + (size_t)m0 * Kout, mc, N, K, Kout);
+  }
   SG2_LAUNCH_OK("linear_bwd_x");
 }
 
