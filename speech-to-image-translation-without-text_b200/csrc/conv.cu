@@ -11,6 +11,7 @@
 #include "igemm.cuh"
 #include "halo_probe.cuh"
 #include "tile_conv.cuh"
+#include "tile_wgrad.cuh"
 
 namespace sg2 {
 
@@ -468,7 +469,154 @@ static int launch_wgrad_t(const WgradDesc& d, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ tile-resident wgrad
+static int tile_wgrad_mode() {
+  static int m = [] {
+    const char* e = getenv("SG2_TILE_WGRAD");
+    return e ? atoi(e) : 1;
+  }();
+  return m;
+}
+
+// Returns 1 when the layer should run on the gather-form wgrad kernel instead.
+static int launch_tile_wgrad(const WgradDesc& d, cudaStream_t st) {
+  if (!tile_wgrad_mode() || d.Wg < kTileW || d.Hg < kTileH) return 1;
+  TileWgradParams p;
+  memset(&p, 0, sizeof(p));
+  // ---- groups = distinct (dy source, x source) pairs; taps of a group = its jobs in order
+  int gcount[4] = {0, 0, 0, 0};
+  int mny[4], mxy[4], mnx[4], mxx[4];
+  for (int s = 0; s < 4; ++s) mny[s] = mnx[s] = 127, mxy[s] = mxx[s] = -127;
+  for (int j = 0; j < d.njobs; ++j) {
+    const JobW& jb = d.jobs[j];
+    mny[jb.bmap] = jb.dy < mny[jb.bmap] ? jb.dy : mny[jb.bmap];
+    mxy[jb.bmap] = jb.dy > mxy[jb.bmap] ? jb.dy : mxy[jb.bmap];
+    mnx[jb.bmap] = jb.dx < mnx[jb.bmap] ? jb.dx : mnx[jb.bmap];
+    mxx[jb.bmap] = jb.dx > mxx[jb.bmap] ? jb.dx : mxx[jb.bmap];
+  }
+  int ex = 0, ey = 0;
+  for (int s = 0; s < d.nbmaps; ++s) {
+    if (mny[s] > mxy[s]) return 1;
+    ex = (mxx[s] - mnx[s]) > ex ? (mxx[s] - mnx[s]) : ex;
+    ey = (mxy[s] - mny[s]) > ey ? (mxy[s] - mny[s]) : ey;
+    p.org_x[s] = mnx[s];
+    p.org_y[s] = mny[s];
+  }
+  p.pitch = kTileW + ex;
+  p.ph = kTileH + ey;
+  // Small pixel grids with wide channels amortise neither the pipeline ramp nor the 128 x (taps x BN) fp32 epilogue.
+  if (d.Cout > 128 && (long long)d.B * d.Wg * d.Hg < 128LL * 16 * num_sms()) return 1;
+  // Cin tile = UMMA N: pick the candidate with the least tensor time per pixel tile; an MMA of N columns costs
+  // max(N/2, 32 + N/4) cycles (tensor floor vs. the SMEM read of its 128-row dy operand), times taps x Cin/N of them.
+  int bn = 0;
+  long long best = -1;
+  const int cands[] = {256, 192, 160, 128, 96, 64, 32, 16};
+  for (int c : cands) {
+    if (c > d.Cin || d.Cin % c) continue;
+    const int floor_c = c / 2 > 32 + c / 4 ? c / 2 : 32 + c / 4;
+    int tc = 1;
+    for (int k = 1; k <= 16 && k <= 512 / c; ++k) tc = k;   // taps per CTA cap (refined below)
+    const long long cost = (long long)(d.Cin / c) * floor_c + (tc < 3 ? 100000 : 0);  // < 3 taps per CTA reloads dy too often
+    if (best < 0 || cost < best) best = cost, bn = c;
+  }
+  if (!bn) return 1;
+  const int cwb = bn % 64 == 0 ? 64 : (bn % 32 == 0 ? 32 : 16);
+  const int co_tile = d.Cout < kBlockM ? d.Cout : kBlockM;
+  const int cwa = co_tile % 64 == 0 ? 64 : (co_tile % 32 == 0 ? 32 : (co_tile % 16 == 0 ? 16 : 0));
+  if (!cwa) return 1;
+  const int row_b = cwb * 2;
+  for (int j = 0; j < d.njobs; ++j) {
+    const JobW& jb = d.jobs[j];
+    int g = -1;
+    for (int k = 0; k < p.ngroups; ++k)
+      if (p.a_src[k] == jb.amap && p.b_src[k] == jb.bmap) g = k;
+    if (g < 0) {
+      if (p.ngroups == 4) return 1;
+      g = p.ngroups++;
+      p.a_src[g] = jb.amap;
+      p.b_src[g] = jb.bmap;
+    }
+    const int t = gcount[g]++;
+    if (t >= 16) return 1;
+    p.tap_off16[g][t] = (uint32_t)(((jb.dy - p.org_y[jb.bmap]) * p.pitch + (jb.dx - p.org_x[jb.bmap])) * row_b) >> 4;
+    p.tap_job[g][t] = j;
+  }
+  for (int g = 1; g < p.ngroups; ++g)
+    if (gcount[g] != gcount[0]) return 1;
+  p.ntaps = gcount[0];
+  const int cap = 512 / bn;
+  int taps_cta = 1;
+  for (int c = 1; c <= p.ntaps && c <= cap; ++c)
+    if (p.ntaps % c == 0) taps_cta = c;
+  p.taps_cta = taps_cta;
+  p.tap_sets = p.ntaps / taps_cta;
+  p.njobs = d.njobs;
+  p.cwa = cwa;
+  p.cwb = cwb;
+  p.a_chunks = co_tile / cwa;
+  p.b_chunks = bn / cwb;
+  p.a_box_bytes = kTileW * kTileH * cwa * 2;
+  p.a_chunk_bytes = p.a_box_bytes;  // 128 rows x >= 32 B: already a multiple of 1024
+  p.b_box_bytes = p.pitch * p.ph * row_b;
+  p.b_chunk_bytes = (p.b_box_bytes + 1023) & ~1023;
+  p.bn = bn;
+  p.m_tiles = (d.Cout + kBlockM - 1) / kBlockM;
+  p.n_tiles = d.Cin / bn;
+  p.tiles_x = (d.Wg + kTileW - 1) / kTileW;
+  p.tiles_y = (d.Hg + kTileH - 1) / kTileH;
+  p.B = d.B;
+  p.magic_img = (uint32_t)((0x100000000ULL + (unsigned)(p.tiles_x * p.tiles_y) - 1) / (unsigned)(p.tiles_x * p.tiles_y));
+  p.magic_x = (uint32_t)((0x100000000ULL + (unsigned)p.tiles_x - 1) / (unsigned)p.tiles_x);
+  p.Cout = d.Cout;
+  p.Cin = d.Cin;
+  p.dw = d.dw;
+  const int pix_tiles = p.tiles_x * p.tiles_y * p.B;
+  const int base = p.ngroups * p.tap_sets * p.m_tiles * p.n_tiles;
+  int lanes = (num_sms() + base - 1) / base;
+  if (lanes > pix_tiles) lanes = pix_tiles;
+  if (lanes < 1) lanes = 1;
+  p.lanes = lanes;
+  const int stage_bytes = (kBlockM / cwa) * p.a_chunk_bytes + p.b_chunks * p.b_chunk_bytes;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages < 2) return 1;
+  if (stages > 4) stages = 4;
+  p.stages = stages;
+  {
+    static int merge_on = [] {
+      const char* e = getenv("SG2_WGRAD_MERGE");
+      return e ? atoi(e) : 1;
+    }();
+    bool ok = merge_on && p.ntaps == 9 && p.b_chunks == 1 && taps_cta % 3 == 0 && 3 * bn <= 256;
+    const uint32_t px16 = (uint32_t)row_b >> 4;
+    for (int g = 0; ok && g < p.ngroups; ++g)
+      for (int r = 0; r < 3; ++r)
+        ok = ok && p.tap_off16[g][3 * r + 1] == p.tap_off16[g][3 * r] + px16 &&
+             p.tap_off16[g][3 * r + 2] == p.tap_off16[g][3 * r] + 2 * px16;
+    p.merge3 = ok ? 1 : 0;
+  }
+  int rc;
+  for (int i = 0; i < d.namaps; ++i)
+    if ((rc = make_act_map(&p.tmA[i], d.a[i], cwa, kTileW, kTileH, 1))) return rc;
+  for (int i = 0; i < d.nbmaps; ++i)
+    if ((rc = make_act_map(&p.tmB[i], d.b[i], cwb, p.pitch, p.ph, 1))) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(tile_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+    if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(tile_wgrad): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  const size_t smem = size_t(stages) * stage_bytes + 1024 + 256;
+  tile_wgrad_kernel<<<dim3(base * lanes), kNumThreads, smem, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) SG2_FAIL((int)e, "tile_wgrad launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 static int launch_wgrad(const WgradDesc& d, cudaStream_t st) {
+  {
+    const int rc = launch_tile_wgrad(d, st);
+    if (rc != 1) return rc;
+  }
   if (d.Cout % 32 || d.Cin % 16) SG2_FAIL(SG2_EINVAL, "wgrad needs Cout %% 32 == 0 and Cin %% 16 == 0 (%d, %d)", d.Cout, d.Cin);
   const int cwa = (d.Cout % 64 == 0) ? 64 : 32;
   const int cwb = (d.Cin % 64 == 0) ? 64 : ((d.Cin % 32 == 0) ? 32 : 16);

@@ -177,7 +177,7 @@ class ConvBlock:
 
 class HeadBlock:
     """GET_IMAGE_G (model.py:287-298): conv3x3 C->3 + tanh; output NCHW fp32 image."""
-    CP = 32
+    CP = 16
 
     def __init__(self, conv):
         self.conv = conv

@@ -22,13 +22,13 @@ G = (1, 1, 1)
 LAYERS = [
     ("G.up1", UPCONV, 4, 1024, 1024, ACT_GLU, G), ("G.up2", UPCONV, 8, 512, 512, ACT_GLU, G),
     ("G.up3", UPCONV, 16, 256, 256, ACT_GLU, G), ("G.up4", UPCONV, 32, 128, 128, ACT_GLU, G),
-    ("G.head1", CONV3, 64, 64, 32, None, G),
+    ("G.head1", CONV3, 64, 64, 16, None, G),
     ("G.joint2", CONV3, 64, 192, 128, ACT_GLU, G), ("G.res2a", CONV3, 64, 64, 128, ACT_GLU, (2, 2, 2)),
     ("G.res2b", CONV3, 64, 64, 64, ACT_NONE, (2, 2, 2)), ("G.up_s2", UPCONV, 64, 64, 64, ACT_GLU, G),
-    ("G.head2", CONV3, 128, 32, 32, None, G),
+    ("G.head2", CONV3, 128, 32, 16, None, G),
     ("G.joint3", CONV3, 128, 160, 64, ACT_GLU, G), ("G.res3a", CONV3, 128, 32, 64, ACT_GLU, (2, 2, 2)),
     ("G.res3b", CONV3, 128, 32, 32, ACT_NONE, (2, 2, 2)), ("G.up_s3", UPCONV, 128, 32, 32, ACT_GLU, G),
-    ("G.head3", CONV3, 256, 16, 32, None, G),
+    ("G.head3", CONV3, 256, 16, 16, None, G),
 ]
 D = (4, 4, 3)
 for S in (64, 128, 256):
