@@ -19,6 +19,7 @@ extern "C" {
 
 #define SG2_EINVAL (-1)  /* unsupported shape / argument */
 #define SG2_EDRIVER (-2) /* cuTensorMapEncodeTiled unavailable or failed */
+#define SG2_ENOFUSE (-3) /* the requested epilogue fusion is not possible for this shape: call the separate kernel */
 
 /* Convolution kinds on the path. */
 enum {
@@ -56,9 +57,11 @@ int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad_oihw, int Cout, in
  *   wgrad : dwpk[Cout][jobs][Cin] += dy^T (x) im2col(x)   (fp32, red.global.add)
  * out_mode: SG2_OUT_BF16 store, SG2_OUT_F32_ATOMIC (split-K accumulate into a zeroed fp32 buffer), SG2_OUT_F32_STORE.
  * stats (fprop, optional): fp32 [2][Cout], += per-channel sum and sum of squares of the bf16 outputs, computed in the
- * epilogue from the TMEM accumulators (the BatchNorm batch statistics, consumed by sg2_bn_act_fwd). */
+ * epilogue from the TMEM accumulators (the BatchNorm batch statistics, consumed by sg2_bn_act_fwd). stats_groups > 1:
+ * the batch is `stats_groups` equal sub-batches with separate statistics, stats [groups][2][Cout]; returns SG2_ENOFUSE
+ * when a pixel tile of this shape would straddle two sub-batches (use sg2_bn_stats then). */
 int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mode, int B, int H, int W, int Cin,
-                   int Cout, int splitk, float* stats, void* stream);
+                   int Cout, int splitk, float* stats, int stats_groups, void* stream);
 int sg2_conv_dgrad(int kind, const void* dy, const void* wpkT, void* dx, int out_mode, int B, int H, int W, int Cin,
                    int Cout, int splitk, void* stream);
 int sg2_conv_wgrad(int kind, const void* x, const void* dy, float* dwpk, int B, int H, int W, int Cin, int Cout,
@@ -68,21 +71,25 @@ int sg2_conv_wgrad(int kind, const void* x, const void* dy, float* dwpk, int B, 
  * nn.BatchNorm2d/1d train mode (model.py:137,147,158,161,218,361,372,387-394): batch mean, biased variance,
  * eps, momentum; running_var gets the unbiased variance; num_batches_tracked += 1.
  * stats: fp32 [2][C] per-channel sum / sum of squares, accumulated (+=) into a ZEROED workspace either by the conv
- * epilogue (sg2_conv_fprop), by sg2_f32_to_bf16_stats (split-K accumulators, fc outputs) or by sg2_bn_stats. */
-int sg2_bn_stats(const void* x, long long P, int C, float* stats, void* stream);
-int sg2_f32_to_bf16_stats(const float* x, void* y, long long P, int C, float* stats, void* stream);
+ * epilogue (sg2_conv_fprop), by sg2_f32_to_bf16_stats (split-K accumulators, fc outputs) or by sg2_bn_stats.
+ * groups > 1: the P rows are `groups` consecutive equal slabs (sub-batches), each normalised on its OWN statistics
+ * (stats [groups][2][C], mean/rstd [groups][C], sums [groups][2][C]) — the same arithmetic as `groups` separate
+ * nn.BatchNorm calls (train_Dnet's real / wrong / fake passes, trainer.py:390-392); running statistics are updated
+ * once per group in order, num_batches_tracked += groups, dgamma/dbeta sum over the groups. */
+int sg2_bn_stats(const void* x, long long P, int C, int groups, float* stats, void* stream);
+int sg2_f32_to_bf16_stats(const float* x, void* y, long long P, int C, int groups, float* stats, void* stream);
 int sg2_bn_eval_prepare(const float* running_mean, const float* running_var, float eps, float* mean, float* rstd,
                         int C, void* stream);
 /* out = act(bn(x)) (+ residual, ACT_NONE only). GLU (model.py:112-122) halves the channel count.
  * train: stats != NULL -> mean/rstd are derived in-kernel, written to mean/rstd (saved for backward) and the running
  * statistics are updated.  eval: stats == NULL, mean/rstd are inputs.  mean == NULL: no BatchNorm (D stem). */
 int sg2_bn_act_fwd(const void* x, const float* stats, float* mean, float* rstd, const float* gamma, const float* beta,
-                   const void* residual, void* out, long long P, int C, int act, float eps, float momentum,
+                   const void* residual, void* out, long long P, int C, int groups, int act, float eps, float momentum,
                    float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
 /* dx (shape of x) from dout (shape of out); dgamma/dbeta (=|+=). sums: fp64 [2][C] ZEROED workspace. Two launches. */
 int sg2_bn_act_bwd(const void* x, const void* dout, const float* mean, const float* rstd, const float* gamma,
                    const float* beta, double* sums, void* dx, float* dgamma, float* dbeta, int accumulate,
-                   long long P, int C, int act, void* stream);
+                   long long P, int C, int groups, int act, void* stream);
 int sg2_lrelu_bwd(const void* x, const void* dout, void* dx, long long n, void* stream);
 int sg2_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
 int sg2_f32_to_bf16(const float* in, void* out, long long n, void* stream);

@@ -59,9 +59,15 @@ def lib():
     return _lib
 
 
+class NoFuse(RuntimeError):
+    """SG2_ENOFUSE: the requested epilogue fusion does not apply to this shape (the caller runs the separate kernel)."""
+
+
 def check(rc, what):
     if rc != 0:
         msg = lib().sg2_last_error().decode(errors="replace")
+        if rc == -3:
+            raise NoFuse(f"sg2b200: {what}: {msg}")
         raise RuntimeError(f"sg2b200: {what} failed (rc={rc}): {msg}")
 
 

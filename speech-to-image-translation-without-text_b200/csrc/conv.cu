@@ -135,6 +135,7 @@ struct GatherDesc {
   long long out_off[4], osx, osy, osb;
   int out_mode, splitk;
   float* stats;
+  int stats_bg;  // images per statistics group (0: one)
   int act;  // epilogue activation (tile kernel only): 0 none, 2 LeakyReLU(0.2)
 };
 
@@ -170,6 +171,9 @@ static int launch_fprop_t(const GatherDesc& d, cudaStream_t st) {
   p.out = d.out;
   p.out_mode = d.out_mode;
   p.stats = d.stats;
+  p.stats_bg = d.stats_bg;
+  if (d.stats && d.stats_bg > 0 && (d.stats_bg % p.nb))
+    SG2_FAIL(SG2_ENOFUSE, "fused BN statistics: a %d-image tile would straddle statistics groups of %d images", p.nb, d.stats_bg);
   const int smax = max_stages(Cfg::kStageBytes);
   int stages = smax;
   if (stages > KB / p.splitk + 1) stages = KB / p.splitk + 1;
@@ -279,6 +283,7 @@ static int plan_tile(const GatherDesc& d, TilePlan& pl) {
   p.sx = d.osx;
   p.out = d.out;
   p.stats = d.stats;
+  p.stats_bg = d.stats_bg;
   p.act = d.act;
   {
     const char* e = getenv("SG2_TILE_DBG");
@@ -379,6 +384,7 @@ static int launch_tile(const GatherDesc& d, cudaStream_t st) {
   const int bn = pl.bn, bk = pl.bk;
   const int nt = d.ntaps / d.nmaps;
   if (nt != 4 && nt != 9) return 1;
+  if (d.stats && d.stats_bg > 0 && (bn + 31) / 32 > 4) return 1;  // grouped statistics need the register-held sums
 #define SG2_CASE(BN_, BK_)                                                   \
   if (bn == BN_ && bk == BK_)                                                \
     return nt == 9 ? launch_tile_t<BN_, BK_, 9>(d, pl, st) : launch_tile_t<BN_, BK_, 4>(d, pl, st);
@@ -646,10 +652,14 @@ int sg2_version(void) { return 1; }
 const char* sg2_last_error(void) { return g_err; }
 
 int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mode, int B, int H, int W, int Cin,
-                   int Cout, int splitk, float* stats, void* stream) {
+                   int Cout, int splitk, float* stats, int stats_groups, void* stream) {
   GatherDesc d;
   memset(&d, 0, sizeof(d));
   d.stats = stats;
+  if (stats && stats_groups > 1) {
+    if (B % stats_groups) SG2_FAIL(SG2_EINVAL, "conv_fprop: batch %d in %d statistics groups", B, stats_groups);
+    d.stats_bg = B / stats_groups;
+  }
   if (stats && (out_mode != SG2_OUT_BF16 || splitk > 1))
     SG2_FAIL(SG2_EINVAL, "fused BN statistics need SG2_OUT_BF16 without split-K");
   d.Cin = Cin;

@@ -203,6 +203,11 @@ __global__ void unpack_wgrad_kernel(int kind, const float* __restrict__ dwpk, fl
 template <bool IN_F32>
 __global__ void bn_stats_kernel(const void* __restrict__ xin, uint4* __restrict__ y, long long P, int vc, int cpb,
                                 int rpb, float* __restrict__ stats, int C) {
+  // blockIdx.z = statistics group: rows [z * P, (z + 1) * P) of the tensor, sums into stats[z][2][C]
+  if (IN_F32) xin = reinterpret_cast<const float*>(xin) + (long long)blockIdx.z * P * C;
+  else xin = reinterpret_cast<const uint4*>(xin) + (long long)blockIdx.z * P * vc;
+  if (y) y += (long long)blockIdx.z * P * vc;
+  stats += (long long)blockIdx.z * 2 * C;
   const int col = blockIdx.x * cpb + threadIdx.x % cpb;
   const int rl = threadIdx.x / cpb;
   float s[8], q[8];
@@ -274,9 +279,33 @@ __global__ void bn_act_fwd_kernel(const uint4* __restrict__ x, const float* __re
   const int col = blockIdx.x * cpb + threadIdx.x % cpb;  // output vector column
   const int rl = threadIdx.x / cpb;
   const int C = vc_in * 8;
+  // blockIdx.z = statistics group (rows [z * P, (z + 1) * P)): each group of the batch is normalised on its own
+  // statistics, exactly like separate nn.BatchNorm calls on the group's samples (train_Dnet's real / wrong / fake passes).
+  const int gz = blockIdx.z, ngroups = gridDim.z;
+  x += (long long)gz * P * vc_in;
+  out += (long long)gz * P * vc_out;
+  if (residual) residual += (long long)gz * P * vc_out;
+  const float* stats_all = stats;
+  if (stats) stats += (long long)gz * 2 * C;
+  if (mean) { mean += (long long)gz * C; rstd += (long long)gz * C; }
+  if (mean_out) { mean_out += (long long)gz * C; rstd_out += (long long)gz * C; }
   const bool writer = stats && blockIdx.y == 0 && rl == 0;
   const double invP = 1.0 / (double)P;
-  if (writer && nbt && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;
+  if (writer && nbt && gz == 0 && blockIdx.x == 0 && threadIdx.x == 0) *nbt += ngroups;
+  // running statistics: updated once per group, in group order, by group 0's writer threads
+  auto update_running = [&](int c) {
+    if (!rmean || gz != 0) return;
+    float rm = rmean[c], rv = rvar[c];
+    for (int g = 0; g < ngroups; ++g) {
+      float m, r, var;
+      stat_mean_rstd(stats_all + (long long)g * 2 * C, C, c, invP, eps, m, r, var);
+      const float unb = P > 1 ? var * (float)((double)P / (double)(P - 1)) : var;
+      rm = (1.f - momentum) * rm + momentum * m;
+      rv = (1.f - momentum) * rv + momentum * unb;
+    }
+    rmean[c] = rm;
+    rvar[c] = rv;
+  };
   float sc0[8], sh0[8], sc1[8], sh1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -286,11 +315,7 @@ __global__ void bn_act_fwd_kernel(const uint4* __restrict__ x, const float* __re
       if (stats) stat_mean_rstd(stats, C, c, invP, eps, m, r, var); else { m = mean[c]; r = rstd[c]; }
       if (writer) {
         mean_out[c] = m; rstd_out[c] = r;
-        if (rmean) {
-          const float unb = P > 1 ? var * (float)((double)P / (double)(P - 1)) : var;
-          rmean[c] = (1.f - momentum) * rmean[c] + momentum * m;
-          rvar[c] = (1.f - momentum) * rvar[c] + momentum * unb;
-        }
+        update_running(c);
       }
       sc0[j] = gamma[c] * r;
       sh0[j] = beta[c] - m * sc0[j];
@@ -303,11 +328,7 @@ __global__ void bn_act_fwd_kernel(const uint4* __restrict__ x, const float* __re
       if (stats) stat_mean_rstd(stats, C, c2, invP, eps, m, r, var); else { m = mean[c2]; r = rstd[c2]; }
       if (writer) {
         mean_out[c2] = m; rstd_out[c2] = r;
-        if (rmean) {
-          const float unb = P > 1 ? var * (float)((double)P / (double)(P - 1)) : var;
-          rmean[c2] = (1.f - momentum) * rmean[c2] + momentum * m;
-          rvar[c2] = (1.f - momentum) * rvar[c2] + momentum * unb;
-        }
+        update_running(c2);
       }
       sc1[j] = gamma[c2] * r;
       sh1[j] = beta[c2] - m * sc1[j];
@@ -365,6 +386,11 @@ __global__ void bn_act_bwd_reduce_kernel(const uint4* __restrict__ x, const uint
                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                          const float* __restrict__ gamma, const float* __restrict__ beta, long long P,
                                          int vc_in, int vc_out, int cpb, int rpb, double* __restrict__ sums, int C) {
+  x += (long long)blockIdx.z * P * vc_in;       // blockIdx.z = statistics group (see bn_act_fwd_kernel)
+  dout += (long long)blockIdx.z * P * vc_out;
+  mean += (long long)blockIdx.z * C;
+  rstd += (long long)blockIdx.z * C;
+  sums += (long long)blockIdx.z * 2 * C;
   const int col = blockIdx.x * cpb + threadIdx.x % cpb;
   const int rl = threadIdx.x / cpb;
   float sc0[8], sh0[8], sc1[8], sh1[8], m0[8], r0[8], m1[8], r1[8];
@@ -430,18 +456,31 @@ __global__ void bn_act_bwd_apply_kernel(const uint4* __restrict__ x, const uint4
                                         const double* __restrict__ sums, long long P, int vc_in, int vc_out, int cpb,
                                         int rpb, uint4* __restrict__ dx, int C, float* __restrict__ dgamma,
                                         float* __restrict__ dbeta, int accumulate) {
+  const int gz = blockIdx.z, ngroups = gridDim.z;   // statistics group (see bn_act_fwd_kernel)
+  const double* sums_all = sums;
+  x += (long long)gz * P * vc_in;
+  dout += (long long)gz * P * vc_out;
+  dx += (long long)gz * P * vc_in;
+  mean += (long long)gz * C;
+  rstd += (long long)gz * C;
+  sums += (long long)gz * 2 * C;
   const int col = blockIdx.x * cpb + threadIdx.x % cpb;
   const int rl = threadIdx.x / cpb;
   const float invP = 1.f / (float)P;
-  if (dgamma && blockIdx.y == 0 && rl == 0) {   // dgamma = sum dz * xhat, dbeta = sum dz
+  if (dgamma && gz == 0 && blockIdx.y == 0 && rl == 0) {   // dgamma = sum dz * xhat, dbeta = sum dz (over all groups)
+    auto total = [&](int idx) {
+      double t = 0.0;
+      for (int g = 0; g < ngroups; ++g) t += sums_all[(long long)g * 2 * C + idx];
+      return (float)t;
+    };
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = col * 8 + j;
-      const float db = (float)sums[c], dg = (float)sums[C + c];
+      const float db = total(c), dg = total(C + c);
       if (accumulate) { dgamma[c] += dg; dbeta[c] += db; } else { dgamma[c] = dg; dbeta[c] = db; }
       if (ACT == ACT_GLU) {
         const int c2 = c + vc_out * 8;
-        const float db2 = (float)sums[c2], dg2 = (float)sums[C + c2];
+        const float db2 = total(c2), dg2 = total(C + c2);
         if (accumulate) { dgamma[c2] += dg2; dbeta[c2] += db2; } else { dgamma[c2] = dg2; dbeta[c2] = db2; }
       }
     }
@@ -741,16 +780,22 @@ int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad, int Cout, int Cin
   return launch_ok("unpack_wgrad");
 }
 
-int sg2_bn_stats(const void* x, long long P, int C, float* stats, void* stream) {
+int sg2_bn_stats(const void* x, long long P, int C, int groups, float* stats, void* stream) {
   if (C % 8) EW_FAIL(SG2_EINVAL, "bn_stats: C %% 8");
+  if (groups < 1 || P % groups) EW_FAIL(SG2_EINVAL, "bn_stats: %lld rows in %d groups", P, groups);
+  P /= groups;
   Geo g = make_geo(P, C, 148 * 4);
+  g.grid.z = groups;
   bn_stats_kernel<false><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(x, nullptr, P, g.vc, g.cpb, g.rpb, stats, C);
   return launch_ok("bn_stats");
 }
 
-int sg2_f32_to_bf16_stats(const float* x, void* y, long long P, int C, float* stats, void* stream) {
+int sg2_f32_to_bf16_stats(const float* x, void* y, long long P, int C, int groups, float* stats, void* stream) {
   if (C % 8) EW_FAIL(SG2_EINVAL, "f32_to_bf16_stats: C %% 8");
+  if (groups < 1 || P % groups) EW_FAIL(SG2_EINVAL, "f32_to_bf16_stats: %lld rows in %d groups", P, groups);
+  P /= groups;
   Geo g = make_geo(P, C, 148 * 4);
+  g.grid.z = groups;
   bn_stats_kernel<true><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(x, (uint4*)y, P, g.vc, g.cpb, g.rpb, stats, C);
   return launch_ok("f32_to_bf16_stats");
 }
@@ -763,11 +808,14 @@ int sg2_bn_eval_prepare(const float* running_mean, const float* running_var, flo
 }
 
 int sg2_bn_act_fwd(const void* x, const float* stats, float* mean, float* rstd, const float* gamma, const float* beta,
-                   const void* residual, void* out, long long P, int C, int act, float eps, float momentum,
+                   const void* residual, void* out, long long P, int C, int groups, int act, float eps, float momentum,
                    float* running_mean, float* running_var, long long* num_batches_tracked, void* stream) {
   const int Cout = act == ACT_GLU ? C / 2 : C;
   if (Cout % 8) EW_FAIL(SG2_EINVAL, "bn_act_fwd: channels %% 8");
+  if (groups < 1 || P % groups) EW_FAIL(SG2_EINVAL, "bn_act_fwd: %lld rows in %d groups", P, groups);
+  P /= groups;
   Geo g = make_geo(P, Cout, 148 * 4);
+  g.grid.z = groups;
   const int has_bn = (mean != nullptr);
   if (stats && !mean) EW_FAIL(SG2_EINVAL, "bn_act_fwd: stats given without mean/rstd outputs");
   cudaStream_t st = (cudaStream_t)stream;
@@ -781,10 +829,13 @@ int sg2_bn_act_fwd(const void* x, const float* stats, float* mean, float* rstd, 
 
 int sg2_bn_act_bwd(const void* x, const void* dout, const float* mean, const float* rstd, const float* gamma,
                    const float* beta, double* sums, void* dx, float* dgamma, float* dbeta, int accumulate,
-                   long long P, int C, int act, void* stream) {
+                   long long P, int C, int groups, int act, void* stream) {
   const int Cout = act == ACT_GLU ? C / 2 : C;
   if (Cout % 8) EW_FAIL(SG2_EINVAL, "bn_act_bwd: channels %% 8");
+  if (groups < 1 || P % groups) EW_FAIL(SG2_EINVAL, "bn_act_bwd: %lld rows in %d groups", P, groups);
+  P /= groups;
   Geo g = make_geo(P, Cout, 148 * 4);
+  g.grid.z = groups;
   cudaStream_t st = (cudaStream_t)stream;
 #define RARGS (const uint4*)x, (const uint4*)dout, mean, rstd, gamma, beta, P, C / 8, Cout / 8, g.cpb, g.rpb, sums, C
 #define AARGS (const uint4*)x, (const uint4*)dout, mean, rstd, gamma, beta, sums, P, C / 8, Cout / 8, g.cpb, g.rpb, (uint4*)dx, C, dgamma, dbeta, accumulate

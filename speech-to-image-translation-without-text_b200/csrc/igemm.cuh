@@ -40,7 +40,8 @@ struct FpropParams {
   void* out;
   int out_mode;
   int stages;
-  float* stats;  // optional [2][N] fp32: per-channel sum / sum of squares of the (bf16-rounded) outputs, += (BN statistics)
+  float* stats;  // optional [groups][2][N] fp32: per-channel sum / sum of squares of the (bf16-rounded) outputs, += (BN statistics)
+  int stats_bg;  // images per statistics group (0: one group); a tile never straddles groups (checked on the host)
 };
 
 template <int BN, int BK>
@@ -224,9 +225,10 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
     }
     if (do_stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* st = p.stats + (p.stats_bg > 0 ? (long long)(b0 / p.stats_bg) * 2 * p.N : 0);
       for (int i = et; i < BN; i += 128) {
-        atomicAdd(&p.stats[n0 + i], s_stats[i]);
-        atomicAdd(&p.stats[p.N + n0 + i], s_stats[SN + i]);
+        atomicAdd(&st[n0 + i], s_stats[i]);
+        atomicAdd(&st[p.N + n0 + i], s_stats[SN + i]);
       }
     }
     tc_fence_before();

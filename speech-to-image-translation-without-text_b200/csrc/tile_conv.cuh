@@ -46,7 +46,8 @@ struct TileParams {
   int Wo, Ho, N;
   long long out_off[4], sb, sy, sx;
   void* out;
-  float* stats;    // optional [2][N] fp32 (+=): per-channel sum / sum of squares of the bf16-rounded outputs
+  float* stats;    // optional [groups][2][N] fp32 (+=): per-channel sum / sum of squares of the bf16-rounded outputs
+  int stats_bg;    // images per statistics group (0: the whole batch is one group)
   int stages;      // weight ring depth (ring mode), in stages of `tps` taps
   int tps;         // taps per weight stage (divides the taps of every source)
   uint32_t stage_start_mask, stage_end_mask;  // bit i: tap i of a step opens / closes a weight stage (ring mode)
@@ -380,6 +381,27 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
+    // register-held statistics belong to one statistics group (sub-batch) at a time; tiles arrive in image order
+    int cur_grp = -1;
+    auto flush_stats = [&](int grp) {
+      if constexpr (Cfg::kRegStats) {
+        float* st = p.stats + (long long)grp * 2 * p.N;
+#pragma unroll
+        for (int ci = 0; ci < Cfg::kCPW; ++ci) {
+          const int c0 = (half + 2 * ci) * 32;
+          if (c0 < BN) {
+            const float cs = warp_transpose_sum(acc_s[ci], lane);
+            const float cq = warp_transpose_sum(acc_q[ci], lane);
+            if (c0 + lane < BN) {
+              atomicAdd(&st[n0 + c0 + lane], cs);
+              atomicAdd(&st[p.N + n0 + c0 + lane], cq);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc_s[ci][j] = acc_q[ci][j] = 0.f;
+          }
+        }
+      }
+    };
     const bool tm_on = (p.dbg & 64) != 0;
     long long w_tf = 0;
     const long long tstart = clock64();
@@ -396,6 +418,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
         tile_decode(p, tile_ok ? t : pix_tiles - 1, tiles_img, b, ty, tx);
         const int y = ty * kTileH + yi, x = tx * kTileW + xi;
         const bool valid = tile_ok && (x < p.Wo) && (y < p.Ho);
+        if (do_stats && Cfg::kRegStats && tile_ok) {
+          const int grp = p.stats_bg > 0 ? b / p.stats_bg : 0;
+          if (grp != cur_grp) {
+            if (cur_grp >= 0) flush_stats(cur_grp);
+            cur_grp = grp;
+          }
+        }
         __nv_bfloat16* dst_row = reinterpret_cast<__nv_bfloat16*>(p.out) + p.out_off[g] + (long long)b * p.sb +
                                  (long long)y * p.sy + (long long)x * p.sx + n0;
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t((acc * MT + m) * BN);
@@ -481,18 +510,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
     }
     if (do_stats) {
       if constexpr (Cfg::kRegStats) {
-#pragma unroll
-        for (int ci = 0; ci < Cfg::kCPW; ++ci) {
-          const int c0 = (half + 2 * ci) * 32;
-          if (c0 < BN) {
-            const float cs = warp_transpose_sum(acc_s[ci], lane);
-            const float cq = warp_transpose_sum(acc_q[ci], lane);
-            if (c0 + lane < BN) {
-              atomicAdd(&p.stats[n0 + c0 + lane], cs);
-              atomicAdd(&p.stats[p.N + n0 + c0 + lane], cq);
-            }
-          }
-        }
+        if (cur_grp >= 0) flush_stats(cur_grp);
       } else {
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int i = et; i < BN; i += 256) {

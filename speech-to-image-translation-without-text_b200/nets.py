@@ -133,7 +133,9 @@ class ConvBlock:
         self.kind, self.conv, self.bn, self.act = kind, conv, bn, act
         self.op = ConvOperand(kind, conv.weight)
 
-    def fwd(self, x, training, residual=None):
+    def fwd(self, x, training, residual=None, groups=1):
+        """groups > 1: the batch is `groups` equal sub-batches with separate BatchNorm statistics (the batched
+        real / wrong / fake passes of train_Dnet, trainer.py:390-392)."""
         wpk, _ = self.op.packs()
         bn = self.bn
         if bn is None:
@@ -142,9 +144,9 @@ class ConvBlock:
         gamma, beta = bn.weight.detach(), bn.bias.detach()
         if training:
             # batch statistics come out of the conv epilogue (or the split-K fp32->bf16 pass): no pass over y
-            st = ops.bn_stats32(self.op.Cout, x.device)
-            y, _ = ops.conv_fprop(self.kind, x, wpk, self.op.Cout, stats=st)
-            out, mean, rstd = ops.bn_act_fwd(y, gamma, beta, self.act, residual, stats=st,
+            st = ops.bn_stats32(self.op.Cout, x.device, groups)
+            y, _ = ops.conv_fprop(self.kind, x, wpk, self.op.Cout, stats=st, groups=groups)
+            out, mean, rstd = ops.bn_act_fwd(y, gamma, beta, self.act, residual, stats=st, groups=groups,
                                              running=(bn.running_mean, bn.running_var, bn.num_batches_tracked))
         else:
             y = ops.conv_fprop(self.kind, x, wpk, self.op.Cout)
@@ -152,7 +154,7 @@ class ConvBlock:
             out = ops.bn_act_fwd(y, gamma, beta, self.act, residual, mean=mean, rstd=rstd)
         return out, (x, y, mean, rstd)
 
-    def bwd(self, saved, dout, sink, need_dx=True, need_w=True):
+    def bwd(self, saved, dout, sink, need_dx=True, need_w=True, groups=1):
         x, y, mean, rstd = saved
         if self.bn is not None:
             if need_w:
@@ -161,7 +163,7 @@ class ConvBlock:
                 dg = db = None
                 acc = False
             dy = ops.bn_act_bwd(y, dout, mean, rstd, self.bn.weight.detach(), self.bn.bias.detach(), self.act,
-                                dg, db, acc)
+                                dg, db, acc, groups=groups)
         elif self.act == ACT_LRELU:
             dy = ops.lrelu_bwd(y, dout)
         else:
@@ -371,17 +373,20 @@ class DEngine:
     def params(self):
         return [p for p in self.net.parameters()]
 
-    def forward(self, img, c, training, out_cond=None, out_uncond=None):
-        T = {}
+    def forward(self, img, c, training, out_cond=None, out_uncond=None, groups=1):
+        """groups > 1: img / c hold `groups` equal sub-batches that the reference runs as separate D passes (separate
+        BatchNorm batches, trainer.py:390-392); everything else is per sample, so one pass over the concatenation
+        gives the same result."""
+        T = {"groups": groups}
         x, T["stem"] = self.stem.fwd(img)
         T["trunk"] = []
         for blk in self.trunk:
-            x, sv = blk.fwd(x, training)
+            x, sv = blk.fwd(x, training, groups=groups)
             T["trunk"].append(sv)
         T["x_code"] = x
         x_imm = ops.nhwc_to_nchw_f32(x)
         cat = ops.concat_c(c, x)
-        h, T["joint"] = self.joint.fwd(cat, training)
+        h, T["joint"] = self.joint.fwd(cat, training, groups=groups)
         T["h"] = h
         lg, ul = self.net.logits[0], self.net.uncond_logits[0]
         cond = ops.logits_fwd(h, lg.weight.detach(), lg.bias.detach(), out_cond)
@@ -393,6 +398,7 @@ class DEngine:
         """-> (grads dict or None when an external sink is used, dimg or None, dc or None)"""
         own = sink is None
         sink = GradSink() if own else sink
+        groups = T.get("groups", 1)
         lg, ul = self.net.logits[0], self.net.uncond_logits[0]
         x, h = T["x_code"], T["h"]
         B = x.shape[0]
@@ -405,7 +411,7 @@ class DEngine:
             dh = torch.empty_like(h)
             ops.logits_bwd(dcond, T["cond"], h, lg.weight.detach(), dh, False,
                            sink.g[lg.weight] if need_w else None, sink.g[lg.bias] if need_w else None)
-            dcat = self.joint.bwd(T["joint"], dh, sink, need_w=need_w)
+            dcat = self.joint.bwd(T["joint"], dh, sink, need_w=need_w, groups=groups)
             dx = ops.concat_c_bwd(dcat, self.E, dc)
         elif need_w:
             for p in (self.joint.conv.weight, self.joint.bn.weight, self.joint.bn.bias):
@@ -423,6 +429,6 @@ class DEngine:
         if dx is None:
             raise RuntimeError("sg2b200: D backward without any output gradient")
         for blk, sv in zip(reversed(self.trunk), reversed(T["trunk"])):
-            dx = blk.bwd(sv, dx, sink, need_w=need_w)
+            dx = blk.bwd(sv, dx, sink, need_w=need_w, groups=groups)
         dimg = self.stem.bwd(T["stem"], dx, sink, need_dimg, need_w=need_w)
         return (sink.finish() if own else None), dimg, (dc if need_dc else None)

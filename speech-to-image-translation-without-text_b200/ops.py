@@ -121,25 +121,31 @@ def _auto_split(m_rows, n_cols, k_blocks):
     return max(1, s)
 
 
-def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None):
-    """x (B,H,W,Cin) bf16 -> y bf16 (B,Ho,Wo,Cout). With `stats` (fp32 [2*Cout], zeroed) the epilogue also accumulates
-    the per-channel sum / sum of squares (in the epilogue, or in the fp32->bf16 pass of a split-K layer); returns (y, True)."""
+def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, groups=1):
+    """x (B,H,W,Cin) bf16 -> y bf16 (B,Ho,Wo,Cout). With `stats` (fp32 [groups*2*Cout], zeroed) the per-channel sum /
+    sum of squares of each of the `groups` sub-batches is accumulated too (in the conv epilogue, in the fp32->bf16 pass
+    of a split-K layer, or by sg2_bn_stats when a pixel tile would straddle sub-batches); returns (y, True)."""
     B, H, W, Cin = x.shape
     fl = flop_scale * _conv_flops(kind, B, H, W, Cin, Cout)
     Ho, Wo = _out_hw(kind, H, W)
     taps = {CONV3: 9, UPCONV: 4, CONV4S2: 16, GEMM: 1}[kind]
-    groups = 4 if kind == UPCONV else 1
+    pgroups = 4 if kind == UPCONV else 1          # output parity groups (separate GEMMs)
     if splitk is None:
-        splitk = _auto_split(B * Ho * Wo // groups, Cout, taps * max(1, Cin // 64))
+        splitk = _auto_split(B * Ho * Wo // pgroups, Cout, taps * max(1, Cin // 64))
     if splitk > 1:
         y32 = torch.zeros((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
         _conv_call("sg2_conv_fprop", 2, fl, kind, _p(x), _p(wpk), _p(y32), OUT_F32_ATOMIC, B, H, W, Cin, Cout, splitk,
-                   None, _st())
+                   None, 1, _st())
         if stats is None:
             return f32_to_bf16(y32)
-        return f32_to_bf16_stats(y32, stats), True
+        return f32_to_bf16_stats(y32, stats, groups), True
     y = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
-    _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, 1, _p(stats), _st())
+    try:
+        _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, 1, _p(stats),
+                   groups, _st())
+    except _lib.NoFuse:
+        _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, 1, None, 1, _st())
+        bn_stats(y.view(-1, Cout), stats, groups)
     return y if stats is None else (y, True)
 
 
@@ -220,21 +226,21 @@ def arena_reset(device):
     a.buf.zero_()
 
 
-def bn_stats32(C, device):
-    """Zeroed fp32 [2][C] slot for the per-channel sum / sum of squares (filled by a conv epilogue or bn_stats)."""
-    return _arena(device).take(2 * C * 4, torch.float32)
+def bn_stats32(C, device, groups=1):
+    """Zeroed fp32 [groups][2][C] slot for the per-channel sum / sum of squares (filled by a conv epilogue or bn_stats)."""
+    return _arena(device).take(groups * 2 * C * 4, torch.float32)
 
 
-def bn_stats(x2d, stats):
+def bn_stats(x2d, stats, groups=1):
     P, C = x2d.shape
-    _call("sg2_bn_stats", 1, _p(x2d), P, C, _p(stats), _st())
+    _call("sg2_bn_stats", 1, _p(x2d), P, C, groups, _p(stats), _st())
 
 
-def f32_to_bf16_stats(x32, stats):
+def f32_to_bf16_stats(x32, stats, groups=1):
     """fp32 [..., C] -> bf16 copy, and += per-channel sums of the rounded values into `stats`."""
     C = x32.shape[-1]
     y = torch.empty(x32.shape, device=x32.device, dtype=torch.bfloat16)
-    _call("sg2_f32_to_bf16_stats", 1, _p(x32), _p(y), x32.numel() // C, C, _p(stats), _st())
+    _call("sg2_f32_to_bf16_stats", 1, _p(x32), _p(y), x32.numel() // C, C, groups, _p(stats), _st())
     return y
 
 
@@ -246,35 +252,36 @@ def bn_eval_stats(rmean, rvar):
     return mean, rstd
 
 
-def bn_act_fwd(x, gamma, beta, act, residual=None, stats=None, mean=None, rstd=None, running=None):
+def bn_act_fwd(x, gamma, beta, act, residual=None, stats=None, mean=None, rstd=None, running=None, groups=1):
     """out = act(bn(x)) (+ residual).
     train: stats (fp32 sums) given -> returns (out, mean, rstd) with mean/rstd derived in the kernel; `running` =
            (running_mean, running_var, num_batches_tracked) is updated like nn.BatchNorm does.
-    eval : mean/rstd given.   no BN: gamma is None."""
+    eval : mean/rstd given.   no BN: gamma is None.
+    groups > 1: the rows are `groups` equal sub-batches, each normalised on its own statistics (mean/rstd [groups][C])."""
     C = x.shape[-1]
     P = x.numel() // C
     out = torch.empty(x.shape[:-1] + ((C // 2) if act == ACT_GLU else C,), device=x.device, dtype=torch.bfloat16)
     if gamma is None:
-        _call("sg2_bn_act_fwd", 1, _p(x), None, None, None, None, None, _p(residual), _p(out), P, C, act, BN_EPS,
+        _call("sg2_bn_act_fwd", 1, _p(x), None, None, None, None, None, _p(residual), _p(out), P, C, 1, act, BN_EPS,
               BN_MOMENTUM, None, None, None, _st())
         return out
     if stats is not None:
-        mr = torch.empty(2 * C, device=x.device, dtype=torch.float32)
-        mean, rstd = mr[:C], mr[C:]
+        mr = torch.empty(2, groups * C, device=x.device, dtype=torch.float32)
+        mean, rstd = mr[0], mr[1]
     rm, rv, nbt = running if (running is not None and stats is not None) else (None, None, None)
     _call("sg2_bn_act_fwd", 1, _p(x), _p(stats), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(out), P, C,
-          act, BN_EPS, BN_MOMENTUM, _p(rm), _p(rv), _p(nbt), _st())
+          groups, act, BN_EPS, BN_MOMENTUM, _p(rm), _p(rv), _p(nbt), _st())
     return (out, mean, rstd) if stats is not None else out
 
 
-def bn_act_bwd(x, dout, mean, rstd, gamma, beta, act, dgamma=None, dbeta=None, accumulate=False):
+def bn_act_bwd(x, dout, mean, rstd, gamma, beta, act, dgamma=None, dbeta=None, accumulate=False, groups=1):
     """-> dx (shape of x, bf16); dgamma/dbeta (fp32, = or +=) are written into the given tensors."""
     C = x.shape[-1]
     P = x.numel() // C
     dx = torch.empty_like(x)
-    sums = _arena(x.device).take(2 * C * 8, torch.float64)
+    sums = _arena(x.device).take(groups * 2 * C * 8, torch.float64)
     _call("sg2_bn_act_bwd", 2, _p(x), _p(dout), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(sums), _p(dx),
-          _p(dgamma), _p(dbeta), int(accumulate), P, C, act, _st())
+          _p(dgamma), _p(dbeta), int(accumulate), P, C, groups, act, _st())
     return dx
 
 

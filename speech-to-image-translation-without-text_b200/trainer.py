@@ -89,6 +89,7 @@ class FusedTrainer:
         self.bD = [FlatBucket(d) for d in self.netsD]
         self.all_reduce = all_reduce          # callable(flat_grad_tensor) or None (single GPU)
         self.concurrent = os.environ.get("SG2_CONCURRENT", "1") != "0"   # one stream per discriminator (see step())
+        self.batched_d = os.environ.get("SG2_BATCHED_D", "1") != "0"     # real/wrong/fake D passes as one 3B pass
         dev = self.bG.flat.device
         self.dev = dev
         # loss scalars: errD[i], errG_total, kl, cal
@@ -138,6 +139,7 @@ class FusedTrainer:
         dlogvar = torch.empty_like(logvar)
         kl = self.losses[nD + 1:nD + 2]
         ops._call("sg2_kl_loss", 1, _p(mu), _p(logvar), mu.numel(), self.kl, _p(kl), _p(dmu), _p(dlogvar), _st())
+        mu3 = mu.repeat(3, 1) if self.batched_d else None
         fork = torch.cuda.Event()
         fork.record(main)
         dimgs, dcs, joins = [None] * nD, [None] * nD, []
@@ -151,15 +153,29 @@ class FusedTrainer:
                 # ---------------- (2) update D_i, trainer.py:375-427
                 bucket = self.bD[i]
                 sink = GradSink(bucket.views, self._sW[i] if self.concurrent else None)
-                tapes = []
-                probs = torch.empty(6, B, device=self.dev, dtype=torch.float32)
-                for k, img in enumerate((real[i], wrong[i], fake[i])):
-                    _, _, _, T = D.forward(img, mu, True, probs[2 * k], probs[2 * k + 1])
-                    tapes.append(T)
-                # targets: real -> 1,1 ; wrong -> cond 0, uncond 1 (trainer.py:400-401) ; fake -> 0,0
-                dprobs = self._bce(probs, (1, 1, 0, 1, 0, 0), (1, u, 1, u, 1, u), self.losses[i:i + 1])
-                for k, T in enumerate(tapes):
-                    D.backward(T, dprobs[2 * k], dprobs[2 * k + 1], None, False, False, True, sink)
+                if self.batched_d:
+                    # real | wrong | fake in ONE pass of 3B samples with per-sub-batch BatchNorm statistics: the same
+                    # arithmetic as the reference's three passes (trainer.py:390-392), a third of the launches, and
+                    # three times the GEMM rows for D's latency- and weight-bound layers.
+                    imgs3 = torch.cat((real[i], wrong[i], fake[i]), 0)
+                    probs = torch.empty(2, 3 * B, device=self.dev, dtype=torch.float32)
+                    _, _, _, T3 = D.forward(imgs3, mu3, True, probs[0], probs[1], groups=3)
+                    # rows of probs.view(6, B): cond(real, wrong, fake), uncond(real, wrong, fake)
+                    # targets: real -> 1,1 ; wrong -> cond 0, uncond 1 (trainer.py:400-401) ; fake -> 0,0
+                    dprobs = self._bce(probs.view(6, B), (1, 0, 0, 1, 1, 0), (1, 1, 1, u, u, u), self.losses[i:i + 1])
+                    dprobs = dprobs.view(2, 3 * B)
+                    D.backward(T3, dprobs[0], dprobs[1], None, False, False, True, sink)
+                    tapes = [T3]
+                else:
+                    tapes = []
+                    probs = torch.empty(6, B, device=self.dev, dtype=torch.float32)
+                    for k, img in enumerate((real[i], wrong[i], fake[i])):
+                        _, _, _, T = D.forward(img, mu, True, probs[2 * k], probs[2 * k + 1])
+                        tapes.append(T)
+                    # targets: real -> 1,1 ; wrong -> cond 0, uncond 1 (trainer.py:400-401) ; fake -> 0,0
+                    dprobs = self._bce(probs, (1, 1, 0, 1, 0, 0), (1, u, 1, u, 1, u), self.losses[i:i + 1])
+                    for k, T in enumerate(tapes):
+                        D.backward(T, dprobs[2 * k], dprobs[2 * k + 1], None, False, False, True, sink)
                 sink.finish()
                 del tapes
                 if self.all_reduce is not None:
