@@ -119,18 +119,20 @@ __global__ void __launch_bounds__(256) linear_bwd_w_kernel(const void* __restric
 template <bool DY_BF16>
 __global__ void __launch_bounds__(256) linear_bwd_x_kernel(const void* __restrict__ dy, const float* __restrict__ w,
                                                            float* __restrict__ dx, int M, int N, int K, int Kout) {
-  __shared__ float ds[64][kLinNB];  // [m][n]
-  const int n0 = blockIdx.x * kLinNB;
-  for (int e = threadIdx.x; e < M * kLinNB; e += blockDim.x) {
-    const int m = e / kLinNB, n = n0 + e % kLinNB;
+  constexpr int NBX = 4 * kLinNB;          // features per block: 4x fewer fp32 atomics per dx element
+  extern __shared__ float dsx[];           // [m][NBX]
+  float (*ds)[NBX] = reinterpret_cast<float (*)[NBX]>(dsx);
+  const int n0 = blockIdx.x * NBX;
+  for (int e = threadIdx.x; e < M * NBX; e += blockDim.x) {
+    const int m = e / NBX, n = n0 + e % NBX;
     float d = 0.f;
     if (n < N)
       d = DY_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy)[(long long)m * N + n])
                   : reinterpret_cast<const float*>(dy)[(long long)m * N + n];
-    ds[m][e % kLinNB] = d;
+    ds[m][e % NBX] = d;
   }
   __syncthreads();
-  const int nend = min(kLinNB, N - n0);
+  const int nend = min(NBX, N - n0);
   for (int k = threadIdx.x; k < Kout; k += blockDim.x) {
     float acc[64];
 #pragma unroll
@@ -400,7 +402,7 @@ int sg2_linear_fwd(const float* x1, int K1, const float* x2, int K2, const float
                    int out_bf16, int M, int N, void* stream) {
   if (M < 1 || M > 4096) SG2_FAIL(SG2_EINVAL, "linear_fwd: M=%d", M);
   // features per warp: enough to amortise the activation staging, few enough to fill the SMs (8 warps per block)
-  int npw = N / (8 * 148 * 2);
+  int npw = N / (8 * 148 * 8);
   npw = npw < 1 ? 1 : (npw > 8 ? 8 : npw);
   dim3 grid((N + 8 * npw - 1) / (8 * npw)), block(256);
   if (out_bf16)
@@ -432,6 +434,12 @@ int sg2_linear_bwd_w(const void* dy, int dy_bf16, const float* x1, int K1, const
 int sg2_linear_bwd_x(const void* dy, int dy_bf16, const float* w, float* dx, int M, int N, int K, int Kout,
                      void* stream) {
   if (Kout > K) SG2_FAIL(SG2_EINVAL, "linear_bwd_x: Kout=%d", Kout);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(linear_bwd_x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 4 * kLinNB * 4);
+    cudaFuncSetAttribute(linear_bwd_x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 4 * kLinNB * 4);
+    attr = true;
+  }
   cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)M * Kout, (cudaStream_t)stream);
   if (e != cudaSuccess) SG2_FAIL((int)e, "linear_bwd_x memset: %s", cudaGetErrorString(e));
   int threads = ((Kout + 31) / 32) * 32;
@@ -439,10 +447,10 @@ int sg2_linear_bwd_x(const void* dy, int dy_bf16, const float* w, float* dx, int
   for (int m0 = 0; m0 < M; m0 += 64) {
     const int mc = M - m0 < 64 ? M - m0 : 64;
     if (dy_bf16)
-      linear_bwd_x_kernel<true><<<(N + kLinNB - 1) / kLinNB, threads, 0, (cudaStream_t)stream>>>(
+      linear_bwd_x_kernel<true><<<(N + 4 * kLinNB - 1) / (4 * kLinNB), threads, mc * 4 * kLinNB * sizeof(float), (cudaStream_t)stream>>>(
           reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)m0 * N, w, dx + (size_t)m0 * Kout, mc, N, K, Kout);
     else
-      linear_bwd_x_kernel<false><<<(N + kLinNB - 1) / kLinNB, threads, 0, (cudaStream_t)stream>>>(
+      linear_bwd_x_kernel<false><<<(N + 4 * kLinNB - 1) / (4 * kLinNB), threads, mc * 4 * kLinNB * sizeof(float), (cudaStream_t)stream>>>(
           reinterpret_cast<const float*>(dy) + (size_t)m0 * N, w, dx + (size_t)m0 * Kout, mc, N, K, Kout);
   }
   SG2_LAUNCH_OK("linear_bwd_x");

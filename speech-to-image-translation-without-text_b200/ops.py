@@ -22,6 +22,9 @@ def launches():
     return _launches
 
 
+_prof = None   # see profile_begin()
+
+
 def _st():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -33,6 +36,8 @@ def _p(t):
         raise RuntimeError("sg2b200 kernels need CUDA tensors (there is no CPU fallback)")
     if not t.is_contiguous():
         raise RuntimeError("sg2b200: non-contiguous tensor passed to a kernel")
+    if _prof is not None:
+        _prof["keep"].append(t)      # recorded launches are replayed later: their operands must stay allocated
     return t.data_ptr()
 
 
@@ -42,21 +47,25 @@ def _call(name, n_launch, *args):
     _lib.call(name, *args)
 
 
-# ---- optional live profiling of the convolution kernels (bench.py's roofline): CUDA events around each launch
-_prof = None
-
+# ---- optional recording of the convolution launches of a step (bench.py's roofline): every conv call made while
+# recording is kept (entry point, raw arguments, executed FLOPs, operand tensors) so that the caller can replay exactly
+# those launches, back to back in one CUDA graph, and time them with CUDA events without any host launch gaps.
 
 def profile_begin():
     global _prof
-    _prof = {"events": [], "flops": 0.0}
+    _prof = {"calls": [], "keep": []}
 
 
 def profile_end():
+    """-> (list of (name, args, flops), list of the tensors those calls reference)."""
     global _prof
-    torch.cuda.synchronize()
     p, _prof = _prof, None
-    ms = sum(e0.elapsed_time(e1) for e0, e1 in p["events"])
-    return {"conv": {"ms": ms, "flops": p["flops"], "n": len(p["events"])}}
+    return p["calls"], p["keep"]
+
+
+def replay_call(name, args):
+    """Re-issue a recorded conv call on the CURRENT stream (the stream is the last C argument)."""
+    _lib.call(name, *(tuple(args[:-1]) + (_st(),)))
 
 
 _TAPS_EFF = {0: 9, 1: 16, 2: 16, 3: 1}
@@ -69,14 +78,9 @@ def _conv_flops(kind, B, H, W, Cin, Cout):
 
 
 def _conv_call(name, n_launch, flops, *args):
-    if _prof is None:
-        return _call(name, n_launch, *args)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     _call(name, n_launch, *args)
-    e1.record()
-    _prof["events"].append((e0, e1))
-    _prof["flops"] += flops
+    if _prof is not None:
+        _prof["calls"].append((name, args, flops))
 
 
 # ------------------------------------------------------------------------------------------ weights
