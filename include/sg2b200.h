@@ -42,12 +42,17 @@ const char* sg2_last_error(void);
  *   UPCONV3x3 wpk [4][Cout][4][Cin]   wpkT [1][Cin][16][Cout]   (3x3 taps pre-summed per output parity)
  *   CONV4x4S2 wpk [1][Cout][16][Cin]  wpkT [4][Cin][4][Cout]
  *   GEMM      wpk [Cout][Cin]         wpkT [Cin][Cout]
- * Cout_pad/Cin_pad >= Cout/Cin give the padded operand extents (zero filled). Either output may be NULL. */
-int sg2_pack_weights(int kind, const float* w_oihw, void* wpk, void* wpkT, int Cout, int Cin, int Cout_pad,
-                     int Cin_pad, void* stream);
+ * Cout_pad/Cin_pad >= Cout/Cin give the padded operand extents (zero filled). Either output may be NULL.
+ * src_ohwi / dst_ohwi = 1: the fp32 master (gradient) is stored [Cout][kh][kw][Cin] instead of OIHW — the layout the
+ * fused trainer keeps its flat parameter buckets in, where the CONV3x3 / CONV4x4S2 fprop operand is a plain bf16 cast
+ * of the master (written by sg2_adam_ema) and sg2_conv_wgrad accumulates straight into the gradient bucket. */
+int sg2_pack_weights(int kind, const float* w, void* wpk, void* wpkT, int Cout, int Cin, int Cout_pad,
+                     int Cin_pad, int src_ohwi, void* stream);
+/* dgrad operand from the bf16 fprop operand (CONV3x3 / CONV4x4S2 / GEMM, unpadded): per-tap [Cout][Cin] transpose. */
+int sg2_pack_transpose(int kind, const void* wpk, void* wpkT, int Cout, int Cin, void* stream);
 /* dwpk [Cout_pad][jobs][Cin_pad] fp32 (what sg2_conv_wgrad accumulates) -> OIHW fp32 gradient (+= if accumulate). */
-int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad_oihw, int Cout, int Cin, int Cout_pad, int Cin_pad,
-                     int accumulate, void* stream);
+int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad, int Cout, int Cin, int Cout_pad, int Cin_pad,
+                     int accumulate, int dst_ohwi, void* stream);
 
 /* ---- convolutions (tcgen05 implicit GEMM, TMA operands) ------------------------------------------------
  * B,H,W,Cin are the FORWARD input extents of the layer; Cout its output channels. Replaces cuDNN fprop /
@@ -137,7 +142,8 @@ int sg2_cal_loss(const float* x, const int* labels, int B, int F, float* ws, flo
  * writes bc = {1 - beta1^t, sqrt(1 - beta2^t)} (device-resident so CUDA-graph replays stay correct). */
 int sg2_adam_tick(int* step, float* bc, float beta1, float beta2, void* stream);
 int sg2_adam_ema(float* p, const float* g, float* m, float* v, float* avg, long long n, float lr, float beta1,
-                 float beta2, float eps, const float* bc, float ema_decay, void* stream);
+                 float beta2, float eps, const float* bc, float ema_decay, void* p_bf16 /* optional bf16 mirror of p */,
+                 void* stream);
 
 /* EXPERIMENT (not part of the product path): conv3x3 fprop with one halo tile per channel chunk and shifted UMMA
  * descriptors per tap; used by tools/probe_halo.py to validate the addressing scheme on hardware. */

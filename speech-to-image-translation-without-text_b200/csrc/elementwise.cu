@@ -85,17 +85,26 @@ __device__ __forceinline__ void pack_offsets(int kind, int co, int slot, int ci,
 // the OIHW read is a contiguous run per output channel, the two packs are written in 64-byte / 32-byte runs.
 constexpr int kPackCo = 16, kPackCi = 32;
 __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk,
-                                    __nv_bfloat16* __restrict__ wpkT, int Cout, int Cin, int CoP, int CiP) {
+                                    __nv_bfloat16* __restrict__ wpkT, int Cout, int Cin, int CoP, int CiP,
+                                    int src_ohwi) {
   __shared__ float tile[kPackCo][kPackCi][17];
   const int kk = (kind == SG2_CONV3x3 || kind == SG2_UPCONV3x3) ? 9 : ((kind == SG2_GEMM) ? 1 : 16);   // source taps
   const int slots = (kind == SG2_CONV3x3) ? 9 : ((kind == SG2_GEMM) ? 1 : 16);                         // packed slots
   const int ci_tiles = (CiP + kPackCi - 1) / kPackCi, co_tiles = (CoP + kPackCo - 1) / kPackCo;
   for (int blk = blockIdx.x; blk < ci_tiles * co_tiles; blk += gridDim.x) {
     const int co0 = (blk / ci_tiles) * kPackCo, ci0 = (blk % ci_tiles) * kPackCi;
-    for (int e = threadIdx.x; e < kPackCo * kPackCi * kk; e += blockDim.x) {
-      const int t = e % kk, cl = (e / kk) % kPackCi, ol = e / (kk * kPackCi);
-      const int co = co0 + ol, ci = ci0 + cl;
-      tile[ol][cl][t] = (co < Cout && ci < Cin) ? w[((long long)co * Cin + ci) * kk + t] : 0.f;
+    if (src_ohwi) {   // master stored [Cout][kh][kw][Cin]: ci is the contiguous axis
+      for (int e = threadIdx.x; e < kPackCo * kPackCi * kk; e += blockDim.x) {
+        const int cl = e % kPackCi, t = (e / kPackCi) % kk, ol = e / (kk * kPackCi);
+        const int co = co0 + ol, ci = ci0 + cl;
+        tile[ol][cl][t] = (co < Cout && ci < Cin) ? w[((long long)co * kk + t) * Cin + ci] : 0.f;
+      }
+    } else {
+      for (int e = threadIdx.x; e < kPackCo * kPackCi * kk; e += blockDim.x) {
+        const int t = e % kk, cl = (e / kk) % kPackCi, ol = e / (kk * kPackCi);
+        const int co = co0 + ol, ci = ci0 + cl;
+        tile[ol][cl][t] = (co < Cout && ci < Cin) ? w[((long long)co * Cin + ci) * kk + t] : 0.f;
+      }
     }
     __syncthreads();
     for (int pass = 0; pass < 2; ++pass) {
@@ -132,13 +141,52 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_
   }
 }
 
+// dgrad operand from the bf16 fprop operand (CONV3x3 / CONV4x4S2 / GEMM, no channel padding): per tap a [Cout][Cin] ->
+// [Cin][Cout] transpose, 64 x 64 tiles through shared memory so that reads run along ci and writes along co.
+__global__ void __launch_bounds__(256) pack_transpose_kernel(int kind, const __nv_bfloat16* __restrict__ wpk,
+                                                             __nv_bfloat16* __restrict__ wpkT, int Cout, int Cin) {
+  __shared__ __nv_bfloat16 tile[64][72];
+  const int slots = (kind == SG2_CONV3x3) ? 9 : ((kind == SG2_GEMM) ? 1 : 16);
+  const int ci_tiles = (Cin + 63) / 64, co_tiles = (Cout + 63) / 64;
+  const long long nblk = (long long)ci_tiles * co_tiles * slots;
+  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int slot = (int)(blk % slots);
+    const int ct = (int)((blk / slots) % ci_tiles), ot = (int)(blk / ((long long)slots * ci_tiles));
+    const int co0 = ot * 64, ci0 = ct * 64;
+    for (int e = threadIdx.x; e < 64 * 8; e += 256) {       // 64 rows (co) x 8 vectors of 8 ci
+      const int r = e >> 3, v8 = e & 7;
+      const int co = co0 + r, ci = ci0 + v8 * 8;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (co < Cout && ci < Cin) val = *reinterpret_cast<const uint4*>(wpk + ((long long)co * slots + slot) * Cin + ci);
+      *reinterpret_cast<uint4*>(&tile[r][v8 * 8]) = val;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 64 * 8; e += 256) {       // 64 rows (ci) x 8 vectors of 8 co
+      const int r = e >> 3, v8 = e & 7;
+      const int ci = ci0 + r, co = co0 + v8 * 8;
+      if (ci < Cin && co < Cout) {
+        __nv_bfloat16 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = tile[v8 * 8 + j][r];
+        long long fo, to;
+        pack_offsets(kind, co, slot, ci, Cout, Cin, fo, to);
+        *reinterpret_cast<uint4*>(wpkT + to) = *reinterpret_cast<const uint4*>(v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // 3-channel stem (tiny): GEMM over im2col rows, k = (kh*4+kw)*3 + c, padded to CiP.
 __global__ void pack_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk,
-                                 __nv_bfloat16* __restrict__ wpkT, int Cout, int CoP, int CiP) {
+                                 __nv_bfloat16* __restrict__ wpkT, int Cout, int CoP, int CiP, int src_ohwi) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < CoP * CiP; i += gridDim.x * blockDim.x) {
     const int ci = i % CiP, co = i / CiP;
     float v = 0.f;
-    if (co < Cout && ci < 48) { const int c = ci % 3, t = ci / 3; v = w[((long long)co * 3 + c) * 16 + t]; }
+    if (co < Cout && ci < 48) {
+      const int c = ci % 3, t = ci / 3;
+      v = src_ohwi ? w[(long long)co * 48 + ci] : w[((long long)co * 3 + c) * 16 + t];
+    }
     const __nv_bfloat16 bv = __float2bfloat16_rn(v);
     if (wpk) wpk[(long long)co * CiP + ci] = bv;
     if (wpkT) wpkT[(long long)ci * CoP + co] = bv;
@@ -149,14 +197,14 @@ __global__ void pack_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __r
 // reads run along ci (contiguous in dwpk), writes along (ci, tap) (contiguous in OIHW); the transpose goes
 // through shared memory so both sides are coalesced.
 __global__ void unpack_wgrad_kernel(int kind, const float* __restrict__ dwpk, float* __restrict__ grad, int Cout,
-                                    int Cin, int CoP, int CiP, int accumulate) {
+                                    int Cin, int CoP, int CiP, int accumulate, int dst_ohwi) {
   __shared__ float tile[16][33];
   const int kk = (kind == SG2_CONV3x3 || kind == SG2_UPCONV3x3) ? 9 : ((kind == SG2_GEMM) ? 1 : 16);
   const int jobs = (kind == SG2_CONV3x3) ? 9 : ((kind == SG2_GEMM || kind == SG2_STEM4x4) ? 1 : 16);
   if (kind == SG2_STEM4x4) {  // grad[co][c][t] <- dwpk[co][0][t*3 + c]   (tiny: 64 x 48)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Cout * 48; i += gridDim.x * blockDim.x) {
       const int t = i % 16, c = (i / 16) % 3, co = i / 48;
-      const float v = dwpk[(long long)co * CiP + t * 3 + c];
+      const float v = dst_ohwi ? dwpk[(long long)co * CiP + i % 48] : dwpk[(long long)co * CiP + t * 3 + c];
       if (accumulate) grad[i] += v; else grad[i] = v;
     }
     return;
@@ -173,7 +221,7 @@ __global__ void unpack_wgrad_kernel(int kind, const float* __restrict__ dwpk, fl
     __syncthreads();
     const int nci = min(32, Cin - ci0);
     for (int e = threadIdx.x; e < nci * kk; e += blockDim.x) {
-      const int l = e / kk, t = e % kk;
+      const int l = dst_ohwi ? e % nci : e / kk, t = dst_ohwi ? e / nci : e % kk;
       float v = 0.f;
       if (kind == SG2_UPCONV3x3) {
         const int kh = t / 3, kw = t % 3;
@@ -189,7 +237,7 @@ __global__ void unpack_wgrad_kernel(int kind, const float* __restrict__ dwpk, fl
       } else {
         v = tile[t][l];
       }
-      const long long o = ((long long)co * Cin + ci0) * kk + e;
+      const long long o = dst_ohwi ? ((long long)co * kk + t) * Cin + ci0 + l : ((long long)co * Cin + ci0) * kk + e;
       if (accumulate) grad[o] += v; else grad[o] = v;
     }
     __syncthreads();
@@ -753,30 +801,41 @@ using namespace sg2;
 extern "C" {
 
 int sg2_pack_weights(int kind, const float* w, void* wpk, void* wpkT, int Cout, int Cin, int CoP, int CiP,
-                     void* stream) {
+                     int src_ohwi, void* stream) {
   if (kind < 0 || kind > 4 || CoP < Cout || CiP < Cin) EW_FAIL(SG2_EINVAL, "pack_weights: bad arguments");
   if (kind == SG2_STEM4x4 && Cin != 48) EW_FAIL(SG2_EINVAL, "pack_weights: stem expects Cin == 48 (3 x 4 x 4)");
   if (kind == SG2_STEM4x4) {
     pack_stem_kernel<<<grid1d((long long)CoP * CiP), 256, 0, (cudaStream_t)stream>>>(
-        w, (__nv_bfloat16*)wpk, (__nv_bfloat16*)wpkT, Cout, CoP, CiP);
+        w, (__nv_bfloat16*)wpk, (__nv_bfloat16*)wpkT, Cout, CoP, CiP, src_ohwi);
     return launch_ok("pack_stem");
   }
   long long nblk = (long long)((CoP + kPackCo - 1) / kPackCo) * ((CiP + kPackCi - 1) / kPackCi);
   if (nblk > 148 * 16) nblk = 148 * 16;
   pack_weights_kernel<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(
-      kind, w, (__nv_bfloat16*)wpk, (__nv_bfloat16*)wpkT, Cout, Cin, CoP, CiP);
+      kind, w, (__nv_bfloat16*)wpk, (__nv_bfloat16*)wpkT, Cout, Cin, CoP, CiP, src_ohwi);
   return launch_ok("pack_weights");
 }
 
+int sg2_pack_transpose(int kind, const void* wpk, void* wpkT, int Cout, int Cin, void* stream) {
+  if (kind != SG2_CONV3x3 && kind != SG2_CONV4x4S2 && kind != SG2_GEMM) EW_FAIL(SG2_EINVAL, "pack_transpose: kind %d", kind);
+  if ((Cout % 8) || (Cin % 8)) EW_FAIL(SG2_EINVAL, "pack_transpose: channels %% 8");
+  const int slots = (kind == SG2_CONV3x3) ? 9 : ((kind == SG2_GEMM) ? 1 : 16);
+  long long nblk = (long long)((Cout + 63) / 64) * ((Cin + 63) / 64) * slots;
+  if (nblk > 148 * 16) nblk = 148 * 16;
+  pack_transpose_kernel<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(kind, (const __nv_bfloat16*)wpk,
+                                                                          (__nv_bfloat16*)wpkT, Cout, Cin);
+  return launch_ok("pack_transpose");
+}
+
 int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad, int Cout, int Cin, int CoP, int CiP, int accumulate,
-                     void* stream) {
+                     int dst_ohwi, void* stream) {
   if (kind < 0 || kind > 4) EW_FAIL(SG2_EINVAL, "unpack_wgrad: bad kind");
   const int kk = (kind == SG2_CONV3x3 || kind == SG2_UPCONV3x3) ? 9 : ((kind == SG2_GEMM || kind == SG2_STEM4x4) ? 1 : 16);
   (void)kk;
   long long nblk = (long long)Cout * ((Cin + 31) / 32);
   if (nblk > 148 * 32) nblk = 148 * 32;
   unpack_wgrad_kernel<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(
-      kind, dwpk, grad, Cout, Cin, CoP, CiP, accumulate);
+      kind, dwpk, grad, Cout, Cin, CoP, CiP, accumulate, dst_ohwi);
   return launch_ok("unpack_wgrad");
 }
 

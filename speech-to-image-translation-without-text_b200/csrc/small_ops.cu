@@ -262,7 +262,8 @@ __global__ void adam_tick_kernel(int* __restrict__ step, float* __restrict__ bc,
 }
 __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, float* __restrict__ avg, long long n, float lr, float b1,
-                                float b2, float eps, const float* __restrict__ bc, float ema_decay) {
+                                float b2, float eps, const float* __restrict__ bc, float ema_decay,
+                                __nv_bfloat16* __restrict__ p_bf16) {
   const float bc1 = bc[0], bc2_sqrt = bc[1];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -274,6 +275,7 @@ __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     const float pi = p[i] - (lr / bc1) * (mi / denom);
     p[i] = pi;
+    if (p_bf16) p_bf16[i] = __float2bfloat16_rn(pi);   // bf16 mirror = the conv operand pack of OHWI-stored weights
     if (avg) avg[i] = ema_decay * avg[i] + (1.f - ema_decay) * pi;
   }
 }
@@ -517,9 +519,9 @@ int sg2_adam_tick(int* step, float* bc, float beta1, float beta2, void* stream) 
 }
 
 int sg2_adam_ema(float* p, const float* g, float* m, float* v, float* avg, long long n, float lr, float beta1,
-                 float beta2, float eps, const float* bc, float ema_decay, void* stream) {
+                 float beta2, float eps, const float* bc, float ema_decay, void* p_bf16, void* stream) {
   adam_ema_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, avg, n, lr, beta1, beta2, eps, bc,
-                                                              ema_decay);
+                                                              ema_decay, (__nv_bfloat16*)p_bf16);
   SG2_LAUNCH_OK("adam_ema");
 }
 

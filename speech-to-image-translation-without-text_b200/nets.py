@@ -29,23 +29,53 @@ class ConvOperand:
         # algorithmic / executed FLOP ratio of the padded operand (image heads pad 3 -> 32, stems pad 48 -> 64)
         self.flop_scale = (self.Cout * self.Cin) / float(self.CoP * self.CiP)
 
+    # ---- OHWI fast path (FusedTrainer's FlatBucket): the fp32 master of a conv weight is stored [Cout][kh][kw][Cin];
+    # `weight._sg2_ohwi` is that contiguous master, `_sg2_wpk` its bf16 mirror (kept current by the Adam kernel) and
+    # `_sg2_dw` the matching slice of the flat gradient bucket. For CONV3x3 / CONV4x4S2 without channel padding the
+    # mirror IS the fprop operand and the packed wgrad accumulator IS the gradient: no pack, no unpack.
+    def _ohwi(self):
+        return getattr(self.weight, "_sg2_ohwi", None)
+
+    def _direct(self):
+        return (self._ohwi() is not None and self.kind in (CONV3, CONV4S2) and self.CoP == self.Cout
+                and self.CiP == self.Cin and self.Cout % 8 == 0 and self.Cin % 8 == 0)
+
     def packs(self):
         w = self.weight
         # _sg2_version: bumped by FlatBucket.adam(), whose kernel updates the weights behind torch's back
         key = (w.data_ptr(), w._version, getattr(w, "_sg2_version", 0), w.device)
+        oh = self._ohwi()
+        if self._direct():
+            if key != self._key:
+                if self._key is None or key[1] != self._key[1]:
+                    ops.f32_to_bf16(oh, out=w._sg2_wpk)      # torch-side write to the master: refresh the bf16 mirror
+                self.wpk = w._sg2_wpk
+                if self.wpkT is None or self.wpkT.device != w.device:
+                    _, s2 = ops.pack_shapes(self.kind, self.CoP, self.CiP)
+                    self.wpkT = torch.empty(s2, device=w.device, dtype=torch.bfloat16)
+                ops.pack_transpose(self.kind, self.wpk, self.wpkT, self.Cout, self.Cin)
+                self._key = key
+            return self.wpk, self.wpkT
         if key != self._key:
             s1, s2 = ops.pack_shapes(GEMM if self.kind == STEM else self.kind, self.CoP, self.CiP)
             if self.wpk is None or self.wpk.device != w.device:
                 self.wpk = torch.empty(s1, device=w.device, dtype=torch.bfloat16)
                 self.wpkT = torch.empty(s2, device=w.device, dtype=torch.bfloat16)
-            ops.pack_weights(self.kind, w.detach(), self.wpk, self.wpkT, self.Cout, self.Cin, self.CoP, self.CiP)
+            ops.pack_weights(self.kind, w.detach() if oh is None else oh, self.wpk, self.wpkT, self.Cout, self.Cin,
+                             self.CoP, self.CiP, ohwi=oh is not None)
             self._key = key
         return self.wpk, self.wpkT
 
-    def wgrad_begin(self, device):
+    def wgrad_begin(self, device, prezeroed=False):
+        """prezeroed: the caller cleared the whole flat gradient bucket (direct accumulation needs no fill here)."""
+        if self._direct():
+            self.dwpk = self.weight._sg2_dw
+            if not prezeroed:
+                self.dwpk.zero_()
+            return
         k = GEMM if self.kind == STEM else self.kind
         shape = (self.CoP, ops.JOBS[k], self.CiP)
-        if self.dwpk is None or self.dwpk.device != device:
+        if self.dwpk is None or self.dwpk.device != device or self.dwpk.shape != shape:
             self.dwpk = torch.empty(shape, device=device, dtype=torch.float32)
         self.dwpk.zero_()
 
@@ -54,7 +84,16 @@ class ConvOperand:
         ops.conv_wgrad(GEMM if self.kind == STEM else self.kind, x, dy, self.dwpk, flop_scale=self.flop_scale)
 
     def wgrad_finish(self, out=None):
-        """packed fp32 accumulator -> OIHW fp32 gradient (written into `out` if given)."""
+        """packed fp32 accumulator -> fp32 gradient in the master's layout (written into `out` if given)."""
+        oh = self._ohwi()
+        if oh is not None:
+            w = self.weight
+            if not self._direct():                             # direct: accumulated in place in the gradient bucket
+                ops.unpack_wgrad(self.kind, self.dwpk, w._sg2_dw, self.Cout, self.Cin, self.CoP, self.CiP, False, ohwi=True)
+            if out is not None:
+                return out                                     # = the OIHW-shaped view of that bucket slice
+            Co, Ci, kh, kw = w.shape        # module API (autograd owns the result): hand out a private OIHW copy
+            return w._sg2_dw.view(Co, kh, kw, Ci).permute(0, 3, 1, 2).contiguous()
         g = torch.empty_like(self.weight) if out is None else out
         ops.unpack_wgrad(self.kind, self.dwpk, g, self.Cout, self.Cin, self.CoP, self.CiP, False)
         return g
@@ -67,10 +106,11 @@ class GradSink:
     BN / linear / logit gradients accumulate in place. `views` optionally maps parameter -> preallocated
     fp32 tensor (a slice of a flat gradient bucket) that receives the result."""
 
-    def __init__(self, views=None, side_stream=None):
+    def __init__(self, views=None, side_stream=None, prezeroed=False):
         self.g = {}
         self.views = views or {}
         self.pending = []
+        self.prezeroed = prezeroed     # the flat gradient bucket behind `views` was cleared by the caller
         # Weight gradients hang off the backward chain (only the optimiser consumes them), so they can run on a
         # side stream next to the dgrad / BatchNorm-backward chain; finish() joins.
         self.side = side_stream
@@ -96,7 +136,7 @@ class GradSink:
     def conv(self, op, x, dy):
         if self.side is None:
             if op not in self.pending:
-                op.wgrad_begin(x.device)
+                op.wgrad_begin(x.device, self.prezeroed)
                 self.pending.append(op)
             op.wgrad_add(x, dy)
             return
@@ -106,7 +146,7 @@ class GradSink:
         with torch.cuda.stream(self.side):
             self.side.wait_event(ev)
             if op not in self.pending:
-                op.wgrad_begin(x.device)
+                op.wgrad_begin(x.device, self.prezeroed)
                 self.pending.append(op)
             op.wgrad_add(x, dy)
 

@@ -97,12 +97,18 @@ def pack_shapes(kind, CoP, CiP):
     return (CoP, CiP), (CiP, CoP)
 
 
-def pack_weights(kind, w, wpk, wpkT, Cout, Cin, CoP, CiP):
-    _call("sg2_pack_weights", 1, kind, _p(w), _p(wpk), _p(wpkT), Cout, Cin, CoP, CiP, _st())
+def pack_weights(kind, w, wpk, wpkT, Cout, Cin, CoP, CiP, ohwi=False):
+    """fp32 master (OIHW, or [Cout][kh][kw][Cin] when ohwi) -> bf16 fprop / dgrad operand packs."""
+    _call("sg2_pack_weights", 1, kind, _p(w), _p(wpk), _p(wpkT), Cout, Cin, CoP, CiP, int(ohwi), _st())
 
 
-def unpack_wgrad(kind, dwpk, grad, Cout, Cin, CoP, CiP, accumulate):
-    _call("sg2_unpack_wgrad", 1, kind, _p(dwpk), _p(grad), Cout, Cin, CoP, CiP, int(accumulate), _st())
+def pack_transpose(kind, wpk, wpkT, Cout, Cin):
+    """dgrad operand from the bf16 fprop operand (per-tap [Cout][Cin] -> [Cin][Cout] transpose)."""
+    _call("sg2_pack_transpose", 1, kind, _p(wpk), _p(wpkT), Cout, Cin, _st())
+
+
+def unpack_wgrad(kind, dwpk, grad, Cout, Cin, CoP, CiP, accumulate, ohwi=False):
+    _call("sg2_unpack_wgrad", 1, kind, _p(dwpk), _p(grad), Cout, Cin, CoP, CiP, int(accumulate), int(ohwi), _st())
 
 
 # ------------------------------------------------------------------------------------------ convolutions
@@ -301,8 +307,9 @@ def add_bf16(a, b, out=None):
     return out
 
 
-def f32_to_bf16(x):
-    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+def f32_to_bf16(x, out=None):
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
     _call("sg2_f32_to_bf16", 1, _p(x), _p(out), x.numel(), _st())
     return out
 

@@ -25,29 +25,54 @@ _st = ops._st
 _p = ops._p
 
 
+def _is_ohwi(p):
+    """Conv weights (except the Cout = 1 logit convs, which run as dot products) are stored [Cout][kh][kw][Cin]."""
+    return p.dim() == 4 and p.shape[0] > 1
+
+
 class FlatBucket:
-    """All parameters of one network as views of a single flat fp32 buffer (+ grad / Adam m, v / optional EMA)."""
+    """All parameters of one network as views of a single flat fp32 buffer (+ grad / Adam m, v / optional EMA).
+
+    Conv weights are STORED in the layout the kernels consume, [Cout][kh][kw][Cin] ("OHWI"), and exposed to torch as
+    OIHW-shaped strided views (`p.data`), so state_dict / load_state_dict / checkpoints keep the reference's shapes.
+    Adam, EMA and the NCCL all-reduce are elementwise over the flat buffers and do not care about the layout; what it
+    buys: the bf16 fprop operand of a CONV3x3 / CONV4x4S2 layer is a plain cast of the master (the Adam kernel writes
+    it as a bf16 mirror of the bucket) and the wgrad kernels accumulate straight into the gradient bucket."""
 
     def __init__(self, net, with_ema=False):
         self.params = [p for p in net.parameters()]
         dev = self.params[0].device
         sizes = [p.numel() for p in self.params]
-        pad = lambda n: -(-n // 4) * 4           # keep every view 16-byte aligned
+        pad = lambda n: -(-n // 8) * 8           # keep every fp32 view 32-byte (bf16 mirror 16-byte, TMA) aligned
         offs, total = [], 0
         for n in sizes:
             offs.append(total)
             total += pad(n)
         self.n = total
+        self.offs = offs
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat16 = torch.zeros(total, device=dev, dtype=torch.bfloat16)
         self.grad = torch.zeros_like(self.flat)
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
         self.views = {}
         with torch.no_grad():
             for p, o, n in zip(self.params, offs, sizes):
-                self.flat[o:o + n].copy_(p.detach().reshape(-1))
-                p.data = self.flat[o:o + n].view(p.shape)
-                self.views[p] = self.grad[o:o + n].view(p.shape)
+                if _is_ohwi(p):
+                    Co, Ci, kh, kw = p.shape
+                    store = self.flat[o:o + n].view(Co, kh, kw, Ci)
+                    store.copy_(p.detach().permute(0, 2, 3, 1))
+                    p.data = store.permute(0, 3, 1, 2)
+                    gstore = self.grad[o:o + n].view(Co, kh, kw, Ci)
+                    self.views[p] = gstore.permute(0, 3, 1, 2)
+                    p._sg2_ohwi = store.view(Co, kh * kw, Ci)
+                    p._sg2_wpk = self.flat16[o:o + n].view(Co, kh * kw, Ci)
+                    p._sg2_dw = gstore.view(Co, kh * kw, Ci)
+                else:
+                    self.flat[o:o + n].copy_(p.detach().reshape(-1))
+                    p.data = self.flat[o:o + n].view(p.shape)
+                    self.views[p] = self.grad[o:o + n].view(p.shape)
+        ops.f32_to_bf16(self.flat, out=self.flat16)
         self.avg = self.flat.clone() if with_ema else None     # trainer.py:494 copy_G_params
         self.step = torch.zeros(1, device=dev, dtype=torch.int32)
         self.bc = torch.zeros(2, device=dev, dtype=torch.float32)
@@ -55,7 +80,7 @@ class FlatBucket:
     def adam(self, lr, beta1=0.5, beta2=0.999, eps=1e-8, ema_decay=0.999):
         ops._call("sg2_adam_tick", 1, _p(self.step), _p(self.bc), beta1, beta2, _st())
         ops._call("sg2_adam_ema", 1, _p(self.flat), _p(self.grad), _p(self.m), _p(self.v), _p(self.avg), self.n,
-                  lr, beta1, beta2, eps, _p(self.bc), ema_decay, _st())
+                  lr, beta1, beta2, eps, _p(self.bc), ema_decay, _p(self.flat16), _st())
         self.dirty()
 
     def dirty(self):
@@ -65,11 +90,14 @@ class FlatBucket:
 
     def ema_params(self):
         """EMA weights as a list shaped like net.parameters() (what trainer.py:256 load_params() copies in)."""
-        out, o = [], 0
-        for p in self.params:
+        out = []
+        for p, o in zip(self.params, self.offs):
             n = p.numel()
-            out.append(self.avg[o:o + n].view(p.shape))
-            o += -(-n // 4) * 4
+            if _is_ohwi(p):
+                Co, Ci, kh, kw = p.shape
+                out.append(self.avg[o:o + n].view(Co, kh, kw, Ci).permute(0, 3, 1, 2))
+            else:
+                out.append(self.avg[o:o + n].view(p.shape))
         return out
 
 
@@ -152,7 +180,8 @@ class FusedTrainer:
                     ops.arena_reset(self.dev)
                 # ---------------- (2) update D_i, trainer.py:375-427
                 bucket = self.bD[i]
-                sink = GradSink(bucket.views, self._sW[i] if self.concurrent else None)
+                bucket.grad.zero_()                 # conv weight gradients accumulate straight into the bucket
+                sink = GradSink(bucket.views, self._sW[i] if self.concurrent else None, prezeroed=True)
                 if self.batched_d:
                     # real | wrong | fake in ONE pass of 3B samples with per-sub-batch BatchNorm statistics: the same
                     # arithmetic as the reference's three passes (trainer.py:390-392), a third of the launches, and
@@ -201,7 +230,8 @@ class FusedTrainer:
         # ---------------- (3b) G backward + update, trainer.py:480-488
         for dc in dcs:
             dmu.add_(dc)                         # mu is not detached in train_Gnet (trainer.py:438)
-        sinkG = GradSink(self.bG.views, self._sW[nD] if self.concurrent else None)
+        self.bG.grad.zero_()
+        sinkG = GradSink(self.bG.views, self._sW[nD] if self.concurrent else None, prezeroed=True)
         self.G.backward(Tg, dimgs, dmu, dlogvar, sinkG)
         sinkG.finish()
         if self.all_reduce is not None:

@@ -52,6 +52,16 @@ def test_conv_fprop_dgrad_wgrad(kind, B, H, W, Ci, Co):
     ops.pack_weights(kind, w.detach().contiguous(), wpk, wpkT, Co, Ci, Co, Ci)
     rk, rkT = pack_ref(kind, w.detach())
     assert torch.equal(wpk, rk.bfloat16()) and torch.equal(wpkT, rkT.bfloat16())     # packing is bit-exact
+    # the fused trainer stores masters [Cout][kh][kw][Cin]: same packs from that layout, and the dgrad operand as a
+    # per-tap transpose of the bf16 fprop operand
+    w_ohwi = w.detach().permute(0, 2, 3, 1).contiguous()
+    wpk2, wpkT2 = torch.empty_like(wpk), torch.empty_like(wpkT)
+    ops.pack_weights(kind, w_ohwi, wpk2, wpkT2, Co, Ci, Co, Ci, ohwi=True)
+    assert torch.equal(wpk2, wpk) and torch.equal(wpkT2, wpkT)
+    if kind != 1 and Co % 8 == 0 and Ci % 8 == 0:
+        wpkT3 = torch.full_like(wpkT, float("nan"))
+        ops.pack_transpose(kind, wpk, wpkT3, Co, Ci)
+        assert torch.equal(wpkT3, wpkT)
     xn = x.detach().permute(0, 2, 3, 1).contiguous().bfloat16()
     dyn = dy.permute(0, 2, 3, 1).contiguous().bfloat16()
     y = ops.conv_fprop(kind, xn, wpk, Co, splitk=1)
@@ -70,6 +80,9 @@ def test_conv_fprop_dgrad_wgrad(kind, B, H, W, Ci, Co):
     gk = torch.empty_like(dw_ref)
     ops.unpack_wgrad(kind, dwpk, gk, Co, Ci, Co, Ci, False)
     assert torch.allclose(gk, unpack_wgrad_ref(kind, dwpk, Co, Ci), atol=1e-5)          # unpack is a pure permute/sum
+    gk2 = torch.empty(Co, k, k, Ci, device="cuda")
+    ops.unpack_wgrad(kind, dwpk, gk2, Co, Ci, Co, Ci, False, ohwi=True)
+    assert torch.equal(gk2.permute(0, 3, 1, 2), gk)
     assert _rel(gk, dw_ref) < 5e-3
 
 
@@ -264,5 +277,5 @@ def test_losses_and_adam():
         opt.step()
         avg_ref.mul_(0.999).add_(pr.detach(), alpha=0.001)
         ops._call("sg2_adam_tick", 1, step.data_ptr(), bc.data_ptr(), 0.5, 0.999, ops._st())
-        ops._call("sg2_adam_ema", 1, p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), avg.data_ptr(), n, 2e-4, 0.5, 0.999, 1e-8, bc.data_ptr(), 0.999, ops._st())
+        ops._call("sg2_adam_ema", 1, p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), avg.data_ptr(), n, 2e-4, 0.5, 0.999, 1e-8, bc.data_ptr(), 0.999, None, ops._st())
     assert _rel(p, pr.detach()) < 1e-6 and _rel(avg, avg_ref) < 1e-6

@@ -127,7 +127,7 @@ def run_case(kind, B, H, W, Ci, Co, splitk, reps):
     wpk_k = torch.empty_like(wpk)
     wpkT_k = torch.empty_like(wpkT)
     wd = w.detach().contiguous()
-    _lib.call("sg2_pack_weights", kind, wd.data_ptr(), wpk_k.data_ptr(), wpkT_k.data_ptr(), Co, Ci, Co, Ci,
+    _lib.call("sg2_pack_weights", kind, wd.data_ptr(), wpk_k.data_ptr(), wpkT_k.data_ptr(), Co, Ci, Co, Ci, 0,
               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     pack_ok = bool(torch.equal(wpk_k, wpk)) and bool(torch.equal(wpkT_k, wpkT))
@@ -189,7 +189,7 @@ def run_case(kind, B, H, W, Ci, Co, splitk, reps):
     torch.cuda.synchronize()
     res["checks"].append(err_report("wgrad", unpack_wgrad_ref(kind, dwpk, Co, Ci).permute(0, 2, 3, 1), dw_ref.permute(0, 2, 3, 1)))
     gk = torch.zeros_like(dw_ref)
-    _lib.call("sg2_unpack_wgrad", kind, dwpk.data_ptr(), gk.data_ptr(), Co, Ci, Co, Ci, 0, st)
+    _lib.call("sg2_unpack_wgrad", kind, dwpk.data_ptr(), gk.data_ptr(), Co, Ci, Co, Ci, 0, 0, st)
     torch.cuda.synchronize()
     res["unpack_maxdiff"] = (gk - unpack_wgrad_ref(kind, dwpk, Co, Ci)).abs().max().item()
     if reps:
