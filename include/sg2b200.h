@@ -64,9 +64,10 @@ int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad, int Cout, int Cin
  * stats (fprop, optional): fp32 [2][Cout], += per-channel sum and sum of squares of the bf16 outputs, computed in the
  * epilogue from the TMEM accumulators (the BatchNorm batch statistics, consumed by sg2_bn_act_fwd). stats_groups > 1:
  * the batch is `stats_groups` equal sub-batches with separate statistics, stats [groups][2][Cout]; returns SG2_ENOFUSE
- * when a pixel tile of this shape would straddle two sub-batches (use sg2_bn_stats then). */
+ * when a pixel tile of this shape would straddle two sub-batches (use sg2_bn_stats then).
+ * act (fprop): 0, or SG2_ACT_LRELU applied in the epilogue (layers without BatchNorm: the D stems, model.py:383-384). */
 int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mode, int B, int H, int W, int Cin,
-                   int Cout, int splitk, float* stats, int stats_groups, void* stream);
+                   int Cout, int splitk, float* stats, int stats_groups, int act, void* stream);
 int sg2_conv_dgrad(int kind, const void* dy, const void* wpkT, void* dx, int out_mode, int B, int H, int W, int Cin,
                    int Cout, int splitk, void* stream);
 int sg2_conv_wgrad(int kind, const void* x, const void* dy, float* dwpk, int B, int H, int W, int Cin, int Cout,

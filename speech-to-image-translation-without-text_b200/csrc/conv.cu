@@ -172,6 +172,7 @@ static int launch_fprop_t(const GatherDesc& d, cudaStream_t st) {
   p.out_mode = d.out_mode;
   p.stats = d.stats;
   p.stats_bg = d.stats_bg;
+  p.act = d.act;
   if (d.stats && d.stats_bg > 0 && (d.stats_bg % p.nb))
     SG2_FAIL(SG2_ENOFUSE, "fused BN statistics: a %d-image tile would straddle statistics groups of %d images", p.nb, d.stats_bg);
   const int smax = max_stages(Cfg::kStageBytes);
@@ -652,10 +653,13 @@ int sg2_version(void) { return 1; }
 const char* sg2_last_error(void) { return g_err; }
 
 int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mode, int B, int H, int W, int Cin,
-                   int Cout, int splitk, float* stats, int stats_groups, void* stream) {
+                   int Cout, int splitk, float* stats, int stats_groups, int act, void* stream) {
   GatherDesc d;
   memset(&d, 0, sizeof(d));
   d.stats = stats;
+  if (act != 0 && act != SG2_ACT_LRELU) SG2_FAIL(SG2_EINVAL, "conv_fprop: epilogue activation %d", act);
+  if (act && (stats || out_mode != SG2_OUT_BF16 || splitk > 1)) SG2_FAIL(SG2_EINVAL, "conv_fprop: fused activation needs a plain bf16 epilogue");
+  d.act = act;
   if (stats && stats_groups > 1) {
     if (B % stats_groups) SG2_FAIL(SG2_EINVAL, "conv_fprop: batch %d in %d statistics groups", B, stats_groups);
     d.stats_bg = B / stats_groups;

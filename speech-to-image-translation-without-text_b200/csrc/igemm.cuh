@@ -42,6 +42,7 @@ struct FpropParams {
   int stages;
   float* stats;  // optional [groups][2][N] fp32: per-channel sum / sum of squares of the (bf16-rounded) outputs, += (BN statistics)
   int stats_bg;  // images per statistics group (0: one group); a tile never straddles groups (checked on the host)
+  int act;       // epilogue activation: 0 none, 2 LeakyReLU(0.2) (layers without BatchNorm: the D stems)
 };
 
 template <int BN, int BK>
@@ -179,6 +180,13 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
       uint32_t v[32];
       tmem_ld_32x32(taddr + c0, v);
       tmem_ld_wait();
+      if (p.act == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float f = __uint_as_float(v[j]);
+          v[j] = __float_as_uint(f > 0.f ? f : 0.2f * f);
+        }
+      }
       if (do_stats) {
         // statistics of what BatchNorm will read back: the bf16-rounded outputs of the valid rows
         float a[32], qq[32];

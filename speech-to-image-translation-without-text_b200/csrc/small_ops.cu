@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) linear_bwd_w_kernel(const void* __restric
 template <bool DY_BF16>
 __global__ void __launch_bounds__(256) linear_bwd_x_kernel(const void* __restrict__ dy, const float* __restrict__ w,
                                                            float* __restrict__ dx, int M, int N, int K, int Kout) {
-  constexpr int NBX = 4 * kLinNB;          // features per block: 4x fewer fp32 atomics per dx element
+  constexpr int NBX = kLinNB;              // features per block
   extern __shared__ float dsx[];           // [m][NBX]
   float (*ds)[NBX] = reinterpret_cast<float (*)[NBX]>(dsx);
   const int n0 = blockIdx.x * NBX;
@@ -137,11 +137,18 @@ __global__ void __launch_bounds__(256) linear_bwd_x_kernel(const void* __restric
     float acc[64];
 #pragma unroll
     for (int m = 0; m < 64; ++m) acc[m] = 0.f;
-    for (int j = 0; j < nend; ++j) {
-      const float wv = w[(long long)(n0 + j) * K + k];
+    for (int j0 = 0; j0 < nend; j0 += 8) {      // 8 weight rows in flight per thread
+      float wv[8];
 #pragma unroll
-      for (int m = 0; m < 64; ++m)
-        if (m < M) acc[m] = fmaf(ds[m][j], wv, acc[m]);
+      for (int u = 0; u < 8; ++u) wv[u] = j0 + u < nend ? w[(long long)(n0 + j0 + u) * K + k] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (j0 + u < nend) {
+#pragma unroll
+          for (int m = 0; m < 64; ++m)
+            if (m < M) acc[m] = fmaf(ds[m][j0 + u], wv[u], acc[m]);
+        }
+      }
     }
 #pragma unroll
     for (int m = 0; m < 64; ++m)
@@ -449,10 +456,10 @@ int sg2_linear_bwd_x(const void* dy, int dy_bf16, const float* w, float* dx, int
   for (int m0 = 0; m0 < M; m0 += 64) {
     const int mc = M - m0 < 64 ? M - m0 : 64;
     if (dy_bf16)
-      linear_bwd_x_kernel<true><<<(N + 4 * kLinNB - 1) / (4 * kLinNB), threads, mc * 4 * kLinNB * sizeof(float), (cudaStream_t)stream>>>(
+      linear_bwd_x_kernel<true><<<(N + kLinNB - 1) / kLinNB, threads, mc * kLinNB * sizeof(float), (cudaStream_t)stream>>>(
           reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)m0 * N, w, dx + (size_t)m0 * Kout, mc, N, K, Kout);
     else
-      linear_bwd_x_kernel<false><<<(N + 4 * kLinNB - 1) / (4 * kLinNB), threads, mc * 4 * kLinNB * sizeof(float), (cudaStream_t)stream>>>(
+      linear_bwd_x_kernel<false><<<(N + kLinNB - 1) / kLinNB, threads, mc * kLinNB * sizeof(float), (cudaStream_t)stream>>>(
           reinterpret_cast<const float*>(dy) + (size_t)m0 * N, w, dx + (size_t)m0 * Kout, mc, N, K, Kout);
   }
   SG2_LAUNCH_OK("linear_bwd_x");

@@ -379,9 +379,10 @@ class StemBlock:
         B, _, S, _ = img.shape
         col = ops.stem_im2col(img)
         wpk, _ = self.op.packs()
-        y = ops.conv_fprop(GEMM, col, wpk, self.op.Cout, flop_scale=self.op.flop_scale).view(B, S // 2, S // 2, self.op.Cout)
-        out = ops.bn_act_fwd(y, None, None, ACT_LRELU)
-        return out, (col, y, B, S)
+        # LeakyReLU runs in the GEMM epilogue; backward only needs the sign, and sign(lrelu(y)) == sign(y)
+        out = ops.conv_fprop(GEMM, col, wpk, self.op.Cout, flop_scale=self.op.flop_scale, act=ACT_LRELU)
+        out = out.view(B, S // 2, S // 2, self.op.Cout)
+        return out, (col, out, B, S)
 
     def bwd(self, saved, dout, sink, need_dimg, need_w=True):
         col, y, B, S = saved

@@ -131,7 +131,7 @@ def _auto_split(m_rows, n_cols, k_blocks):
     return max(1, s)
 
 
-def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, groups=1):
+def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, groups=1, act=ACT_NONE):
     """x (B,H,W,Cin) bf16 -> y bf16 (B,Ho,Wo,Cout). With `stats` (fp32 [groups*2*Cout], zeroed) the per-channel sum /
     sum of squares of each of the `groups` sub-batches is accumulated too (in the conv epilogue, in the fp32->bf16 pass
     of a split-K layer, or by sg2_bn_stats when a pixel tile would straddle sub-batches); returns (y, True)."""
@@ -141,20 +141,20 @@ def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, grou
     taps = {CONV3: 9, UPCONV: 4, CONV4S2: 16, GEMM: 1}[kind]
     pgroups = 4 if kind == UPCONV else 1          # output parity groups (separate GEMMs)
     if splitk is None:
-        splitk = _auto_split(B * Ho * Wo // pgroups, Cout, taps * max(1, Cin // 64))
+        splitk = 1 if act else _auto_split(B * Ho * Wo // pgroups, Cout, taps * max(1, Cin // 64))
     if splitk > 1:
         y32 = torch.zeros((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
         _conv_call("sg2_conv_fprop", 2, fl, kind, _p(x), _p(wpk), _p(y32), OUT_F32_ATOMIC, B, H, W, Cin, Cout, splitk,
-                   None, 1, _st())
+                   None, 1, 0, _st())
         if stats is None:
             return f32_to_bf16(y32)
         return f32_to_bf16_stats(y32, stats, groups), True
     y = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
     try:
         _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, 1, _p(stats),
-                   groups, _st())
+                   groups, act, _st())
     except _lib.NoFuse:
-        _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, 1, None, 1, _st())
+        _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, 1, None, 1, act, _st())
         bn_stats(y.view(-1, Cout), stats, groups)
     return y if stats is None else (y, True)
 
