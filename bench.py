@@ -319,6 +319,7 @@ def run_ours(args):
                     "step_tflops_reference_equivalent": GF_PER_IMAGE_NECESSARY * B / ms_step}
 
     if rank != 0:
+        sdist.shutdown()
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -341,6 +342,7 @@ def run_ours(args):
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(out))
+    sdist.shutdown()
 
 
 def main():

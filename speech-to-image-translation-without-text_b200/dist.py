@@ -48,3 +48,9 @@ def broadcast_state(modules, src=0):
     for m in modules:
         for t in list(m.parameters()) + list(m.buffers()):
             dist.broadcast(t.data, src=src)
+
+
+def shutdown():
+    """Tear the process group down (avoids the NCCL 'destroy_process_group() was not called' warning at exit)."""
+    if dist.is_initialized():
+        dist.destroy_process_group()
