@@ -106,11 +106,15 @@ class GradSink:
     BN / linear / logit gradients accumulate in place. `views` optionally maps parameter -> preallocated
     fp32 tensor (a slice of a flat gradient bucket) that receives the result."""
 
-    def __init__(self, views=None, side_stream=None, prezeroed=False):
+    def __init__(self, views=None, side_stream=None, prezeroed=False, on_ready=None):
         self.g = {}
         self.views = views or {}
         self.pending = []
         self.prezeroed = prezeroed     # the flat gradient bucket behind `views` was cleared by the caller
+        # on_ready(weight): called (on the stream the wgrad ran on) as soon as a conv weight's gradient is complete, i.e.
+        # after its single wgrad launch of this sink — lets the caller all-reduce and Adam-update that layer while the
+        # rest of the backward pass is still running. Only valid when every conv sees exactly one backward pass.
+        self.on_ready = on_ready
         # Weight gradients hang off the backward chain (only the optimiser consumes them), so they can run on a
         # side stream next to the dgrad / BatchNorm-backward chain; finish() joins.
         self.side = side_stream
@@ -135,20 +139,26 @@ class GradSink:
 
     def conv(self, op, x, dy):
         if self.side is None:
-            if op not in self.pending:
-                op.wgrad_begin(x.device, self.prezeroed)
-                self.pending.append(op)
-            op.wgrad_add(x, dy)
+            self._wgrad(op, x, dy)
             return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         self.keep.append((x, dy))              # keep the operands alive until the side stream has consumed them
         with torch.cuda.stream(self.side):
             self.side.wait_event(ev)
-            if op not in self.pending:
-                op.wgrad_begin(x.device, self.prezeroed)
-                self.pending.append(op)
+            self._wgrad(op, x, dy)
+
+    def _wgrad(self, op, x, dy):
+        if self.on_ready is not None:
+            op.wgrad_begin(x.device, self.prezeroed)
             op.wgrad_add(x, dy)
+            self.g[op.weight] = op.wgrad_finish(self.views.get(op.weight))
+            self.on_ready(op.weight)
+            return
+        if op not in self.pending:
+            op.wgrad_begin(x.device, self.prezeroed)
+            self.pending.append(op)
+        op.wgrad_add(x, dy)
 
     def finish(self):
         if self.side is None:

@@ -44,12 +44,20 @@ class FlatBucket:
         dev = self.params[0].device
         sizes = [p.numel() for p in self.params]
         pad = lambda n: -(-n // 8) * 8           # keep every fp32 view 32-byte (bf16 mirror 16-byte, TMA) aligned
-        offs, total = [], 0
-        for n in sizes:
-            offs.append(total)
-            total += pad(n)
+        # placement: the small parameters (BatchNorm, linear, biases, logit convs) first, as one contiguous head region,
+        # then the conv weights — so that each conv weight AND the whole head are contiguous ranges (per-layer
+        # all-reduce / Adam while backward is still running, one call for the rest).
+        offs, total = [None] * len(sizes), 0
+        for want_conv in (False, True):
+            for i, (p, n) in enumerate(zip(self.params, sizes)):
+                if _is_ohwi(p) == want_conv:
+                    offs[i] = total
+                    total += pad(n)
+            if not want_conv:
+                self.head_n = total
         self.n = total
         self.offs = offs
+        self.range_of = {p: (o, pad(n)) for p, o, n in zip(self.params, offs, sizes)}
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat16 = torch.zeros(total, device=dev, dtype=torch.bfloat16)
         self.grad = torch.zeros_like(self.flat)
@@ -78,10 +86,21 @@ class FlatBucket:
         self.bc = torch.zeros(2, device=dev, dtype=torch.float32)
 
     def adam(self, lr, beta1=0.5, beta2=0.999, eps=1e-8, ema_decay=0.999):
-        ops._call("sg2_adam_tick", 1, _p(self.step), _p(self.bc), beta1, beta2, _st())
-        ops._call("sg2_adam_ema", 1, _p(self.flat), _p(self.grad), _p(self.m), _p(self.v), _p(self.avg), self.n,
-                  lr, beta1, beta2, eps, _p(self.bc), ema_decay, _p(self.flat16), _st())
+        """One optimiser step over the whole bucket."""
+        self.adam_tick(beta1, beta2)
+        self.adam_range(0, self.n, lr, beta1, beta2, eps, ema_decay)
         self.dirty()
+
+    def adam_tick(self, beta1=0.5, beta2=0.999):
+        """Advance the device-side step counter / bias corrections: once per optimiser step, before any adam_range()."""
+        ops._call("sg2_adam_tick", 1, _p(self.step), _p(self.bc), beta1, beta2, _st())
+
+    def adam_range(self, o, n, lr, beta1=0.5, beta2=0.999, eps=1e-8, ema_decay=0.999):
+        """Adam (+EMA, + bf16 mirror) on elements [o, o+n) of the bucket, on the current stream."""
+        sl = slice(o, o + n)
+        ops._call("sg2_adam_ema", 1, _p(self.flat[sl]), _p(self.grad[sl]), _p(self.m[sl]), _p(self.v[sl]),
+                  _p(self.avg[sl]) if self.avg is not None else None, n, lr, beta1, beta2, eps, _p(self.bc), ema_decay,
+                  _p(self.flat16[sl]), _st())
 
     def dirty(self):
         """The Adam kernel wrote the weights behind torch's back: invalidate the cached bf16 operand packs."""
@@ -118,6 +137,7 @@ class FusedTrainer:
         self.all_reduce = all_reduce          # callable(flat_grad_tensor) or None (single GPU)
         self.concurrent = os.environ.get("SG2_CONCURRENT", "1") != "0"   # one stream per discriminator (see step())
         self.batched_d = os.environ.get("SG2_BATCHED_D", "1") != "0"     # real/wrong/fake D passes as one 3B pass
+        self.layerwise = os.environ.get("SG2_LAYERWISE_OPT", "1") != "0"  # per-layer all-reduce + Adam during backward
         dev = self.bG.flat.device
         self.dev = dev
         # loss scalars: errD[i], errG_total, kl, cal
@@ -125,6 +145,30 @@ class FusedTrainer:
         self._tables = {}
 
     # ------------------------------------------------------------------ helpers
+    def _layerwise(self, bucket, lr):
+        """-> (on_ready, finish): all-reduce + Adam of each conv weight as soon as its wgrad is done (on the wgrad side
+        stream, overlapping the rest of backward), then the small parameters and any leftover in finish()."""
+        bucket.adam_tick()
+        done = set()
+
+        def ready(w):
+            o, n = bucket.range_of[w]
+            if self.all_reduce is not None:
+                self.all_reduce(bucket.grad[o:o + n])
+            bucket.adam_range(o, n, lr)
+            done.add(w)
+
+        def finish():
+            if self.all_reduce is not None:
+                self.all_reduce(bucket.grad[:bucket.head_n])
+            bucket.adam_range(0, bucket.head_n, lr)
+            for w in bucket.params:
+                if w not in done and bucket.range_of[w][0] >= bucket.head_n:
+                    ready(w)
+            bucket.dirty()
+
+        return ready, finish
+
     def _bce(self, probs, targets, weights, loss_slot):
         """probs (nvec, B) -> dprobs (nvec, B); adds sum_v w_v * BCE(probs[v], t_v) to loss_slot."""
         nvec, B = probs.shape
@@ -181,7 +225,8 @@ class FusedTrainer:
                 # ---------------- (2) update D_i, trainer.py:375-427
                 bucket = self.bD[i]
                 bucket.grad.zero_()                 # conv weight gradients accumulate straight into the bucket
-                sink = GradSink(bucket.views, self._sW[i] if self.concurrent else None, prezeroed=True)
+                ready, fin = self._layerwise(bucket, self.lr_d) if (self.batched_d and self.layerwise) else (None, None)
+                sink = GradSink(bucket.views, self._sW[i] if self.concurrent else None, prezeroed=True, on_ready=ready)
                 if self.batched_d:
                     # real | wrong | fake in ONE pass of 3B samples with per-sub-batch BatchNorm statistics: the same
                     # arithmetic as the reference's three passes (trainer.py:390-392), a third of the launches, and
@@ -207,9 +252,12 @@ class FusedTrainer:
                         D.backward(T, dprobs[2 * k], dprobs[2 * k + 1], None, False, False, True, sink)
                 sink.finish()
                 del tapes
-                if self.all_reduce is not None:
-                    self.all_reduce(bucket.grad)
-                bucket.adam(self.lr_d)
+                if fin is not None:
+                    fin()
+                else:
+                    if self.all_reduce is not None:
+                        self.all_reduce(bucket.grad)
+                    bucket.adam(self.lr_d)
                 # ---------------- (3a) D_i's share of the G step, trainer.py:436-446 (updated D weights, live fake, mu)
                 probs = torch.empty(2, B, device=self.dev, dtype=torch.float32)
                 _, _, x_imm, T = D.forward(fake[i], mu, True, probs[0], probs[1])
@@ -231,12 +279,16 @@ class FusedTrainer:
         for dc in dcs:
             dmu.add_(dc)                         # mu is not detached in train_Gnet (trainer.py:438)
         self.bG.grad.zero_()
-        sinkG = GradSink(self.bG.views, self._sW[nD] if self.concurrent else None, prezeroed=True)
+        ready, fin = self._layerwise(self.bG, self.lr_g) if self.layerwise else (None, None)
+        sinkG = GradSink(self.bG.views, self._sW[nD] if self.concurrent else None, prezeroed=True, on_ready=ready)
         self.G.backward(Tg, dimgs, dmu, dlogvar, sinkG)
         sinkG.finish()
-        if self.all_reduce is not None:
-            self.all_reduce(self.bG.grad)
-        self.bG.adam(self.lr_g)                  # + EMA avg = 0.999 avg + 0.001 p (trainer.py:571-572)
+        if fin is not None:
+            fin()                                # + EMA avg = 0.999 avg + 0.001 p (trainer.py:571-572)
+        else:
+            if self.all_reduce is not None:
+                self.all_reduce(self.bG.grad)
+            self.bG.adam(self.lr_g)
         # errG_total = sum_i errG_i + kl + sum_i cal_i (trainer.py:486)
         cal = self.losses[nD + 2:nD + 3]
         cal.add_(parts[nD:].sum())
