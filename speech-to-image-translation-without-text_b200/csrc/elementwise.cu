@@ -313,15 +313,61 @@ __global__ void bn_eval_prepare_kernel(const float* rmean, const float* rvar, fl
 // ============================================================================================ BN apply (+act)
 enum { ACT_NONE = 0, ACT_GLU = 1, ACT_LRELU = 2 };
 
+// Row streaming for the large [P][C] tensors. With 16-byte register loads each thread keeps two or three loads in
+// flight and the 100+-register GLU kernels fit two blocks per SM: ~16 KB in flight per SM, ~2.5 TB/s. STAGED variants
+// instead pull row tiles of ~16 KB through a 4-deep shared-memory ring with cp.async.bulk (the TMA engine, one elected
+// thread issues, mbarrier completion), so ~100-190 KB per SM are in flight regardless of register use; the math then
+// reads its operands from shared memory. body(xs, ds, ri, rg): xs/ds = row-major tiles, ri = row inside them,
+// rg = row of the whole tensor (for the outputs).
+constexpr int kStStages = 4;
+template <bool WITH_D, typename F>
+__device__ __forceinline__ void staged_rows(const uint4* __restrict__ x, const uint4* __restrict__ d, long long P,
+                                            int vc_in, int vc_out, int R, int rl, int rpb, F&& body) {
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  __shared__ uint64_t st_full[kStStages];
+  const int xv = R * vc_in, dv = WITH_D ? R * vc_out : 0;   // uint4 vectors per stage
+  const long long tiles = (P + R - 1) / R;
+  const int lane_id = blockIdx.y, nl = gridDim.y;
+  const long long my_tiles = lane_id < tiles ? (tiles - lane_id + nl - 1) / nl : 0;
+  uint4* ring = reinterpret_cast<uint4*>(st_smem);
+  auto issue = [&](long long i) {
+    const long long t = lane_id + i * nl;
+    const int s = (int)(i % kStStages);
+    const long long r0 = t * R;
+    const int rows = (int)((P - r0) < R ? (P - r0) : R);
+    uint4* sx = ring + (size_t)s * (xv + dv);
+    mbar_expect_tx(&st_full[s], (uint32_t)rows * (uint32_t)(vc_in + (WITH_D ? vc_out : 0)) * 16u);
+    bulk_g2s(sx, x + r0 * vc_in, (uint32_t)rows * vc_in * 16u, &st_full[s]);
+    if (WITH_D) bulk_g2s(sx + xv, d + r0 * vc_out, (uint32_t)rows * vc_out * 16u, &st_full[s]);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStStages; ++s) mbar_init(&st_full[s], 1);
+    fence_barrier_init();
+    for (long long i = 0; i < my_tiles && i < kStStages; ++i) issue(i);
+  }
+  __syncthreads();
+  for (long long i = 0; i < my_tiles; ++i) {
+    const int s = (int)(i % kStStages);
+    mbar_wait(&st_full[s], (uint32_t)((i / kStStages) & 1));
+    const long long r0 = (lane_id + i * nl) * (long long)R;
+    const int rows = (int)((P - r0) < R ? (P - r0) : R);
+    const uint4* sx = ring + (size_t)s * (xv + dv);
+    for (int r = rl; r < rows; r += rpb) body(sx, sx + xv, (long long)r, r0 + r);
+    __syncthreads();
+    if (threadIdx.x == 0 && i + kStStages < my_tiles) issue(i + kStStages);
+  }
+}
+
 // out = act(bn(x)) (+ residual).  GLU: out[:, c] = bn(x)[:, c] * sigmoid(bn(x)[:, c + C/2]), out has C/2 channels.
-template <int ACT>
+template <int ACT, bool STAGED>
 __global__ void bn_act_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ mean,
                                   const float* __restrict__ rstd, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, const uint4* __restrict__ residual,
                                   uint4* __restrict__ out, long long P, int vc_in, int vc_out, int cpb, int rpb,
                                   int has_bn, const float* __restrict__ stats, float eps, float momentum,
                                   float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                  float* __restrict__ rmean, float* __restrict__ rvar, long long* __restrict__ nbt) {
+                                  float* __restrict__ rmean, float* __restrict__ rvar, long long* __restrict__ nbt,
+                                  int tile_rows) {
   // stats != NULL: train mode — mean/rstd are derived here from the sums the conv epilogue accumulated; the first
   // row-block also saves them for backward and updates the running statistics (momentum, unbiased variance).
   const int col = blockIdx.x * cpb + threadIdx.x % cpb;  // output vector column
@@ -382,12 +428,12 @@ __global__ void bn_act_fwd_kernel(const uint4* __restrict__ x, const float* __re
       sh1[j] = beta[c2] - m * sc1[j];
     }
   }
-  for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += (long long)gridDim.y * rpb) {
+  auto body = [&](const uint4* xs, const uint4* /*ds*/, long long ri, long long r) {
     float a[8], o[8];
-    unpack8(x[r * vc_in + col], a);
+    unpack8(xs[ri * vc_in + col], a);
     if (ACT == ACT_GLU) {
       float g[8];
-      unpack8(x[r * vc_in + col + vc_out], g);
+      unpack8(xs[ri * vc_in + col + vc_out], g);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = (a[j] * sc0[j] + sh0[j]) * sigmoidf_(g[j] * sc1[j] + sh1[j]);
     } else if (ACT == ACT_LRELU) {
@@ -404,6 +450,11 @@ __global__ void bn_act_fwd_kernel(const uint4* __restrict__ x, const float* __re
       }
     }
     out[r * vc_out + col] = pack8(o);
+  };
+  if (STAGED) {
+    staged_rows<false>(x, nullptr, P, vc_in, vc_out, tile_rows, rl, rpb, body);
+  } else {
+    for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += (long long)gridDim.y * rpb) body(x, nullptr, r, r);
   }
 }
 
@@ -429,11 +480,12 @@ __device__ __forceinline__ void bn_act_dz(const float (&a)[8], const float (&g)[
 }
 
 // pass 1: sums[0][c] = sum dz, sums[1][c] = sum dz * xhat   (per input channel c, fp64 atomics)
-template <int ACT>
+template <int ACT, bool STAGED>
 __global__ void bn_act_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dout,
                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                          const float* __restrict__ gamma, const float* __restrict__ beta, long long P,
-                                         int vc_in, int vc_out, int cpb, int rpb, double* __restrict__ sums, int C) {
+                                         int vc_in, int vc_out, int cpb, int rpb, double* __restrict__ sums, int C,
+                                         int tile_rows) {
   x += (long long)blockIdx.z * P * vc_in;       // blockIdx.z = statistics group (see bn_act_fwd_kernel)
   dout += (long long)blockIdx.z * P * vc_out;
   mean += (long long)blockIdx.z * C;
@@ -456,17 +508,22 @@ __global__ void bn_act_bwd_reduce_kernel(const uint4* __restrict__ x, const uint
   float s0[8], t0[8], s1[8], t1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s0[j] = t0[j] = s1[j] = t1[j] = 0.f;
-  for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += (long long)gridDim.y * rpb) {
+  auto body = [&](const uint4* xs, const uint4* ds, long long ri, long long /*r*/) {
     float a[8], g[8], d[8], dz0[8], dz1[8];
-    unpack8(x[r * vc_in + col], a);
-    if (ACT == ACT_GLU) unpack8(x[r * vc_in + col + vc_out], g);
-    unpack8(dout[r * vc_out + col], d);
+    unpack8(xs[ri * vc_in + col], a);
+    if (ACT == ACT_GLU) unpack8(xs[ri * vc_in + col + vc_out], g);
+    unpack8(ds[ri * vc_out + col], d);
     bn_act_dz<ACT>(a, g, d, sc0, sh0, sc1, sh1, dz0, dz1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       s0[j] += dz0[j]; t0[j] += dz0[j] * (a[j] - m0[j]) * r0[j];
       if (ACT == ACT_GLU) { s1[j] += dz1[j]; t1[j] += dz1[j] * (g[j] - m1[j]) * r1[j]; }
     }
+  };
+  if (STAGED) {
+    staged_rows<true>(x, dout, P, vc_in, vc_out, tile_rows, rl, rpb, body);
+  } else {
+    for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += (long long)gridDim.y * rpb) body(x, dout, r, r);
   }
   __shared__ float sh[4][256][8];
 #pragma unroll
@@ -497,13 +554,13 @@ __global__ void bn_act_bwd_reduce_kernel(const uint4* __restrict__ x, const uint
 }
 
 // pass 2: dx = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat))
-template <int ACT>
+template <int ACT, bool STAGED>
 __global__ void bn_act_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dout,
                                         const float* __restrict__ mean, const float* __restrict__ rstd,
                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                         const double* __restrict__ sums, long long P, int vc_in, int vc_out, int cpb,
                                         int rpb, uint4* __restrict__ dx, int C, float* __restrict__ dgamma,
-                                        float* __restrict__ dbeta, int accumulate) {
+                                        float* __restrict__ dbeta, int accumulate, int tile_rows) {
   const int gz = blockIdx.z, ngroups = gridDim.z;   // statistics group (see bn_act_fwd_kernel)
   const double* sums_all = sums;
   x += (long long)gz * P * vc_in;
@@ -547,11 +604,11 @@ __global__ void bn_act_bwd_apply_kernel(const uint4* __restrict__ x, const uint4
       k1[j] = (float)sums[c2] * invP; l1[j] = (float)sums[C + c2] * invP;
     } else { m1[j] = r1[j] = sc1[j] = sh1[j] = k1[j] = l1[j] = 0.f; }
   }
-  for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += (long long)gridDim.y * rpb) {
+  auto body = [&](const uint4* xs, const uint4* ds, long long ri, long long r) {
     float a[8], g[8], d[8], dz0[8], dz1[8], o[8];
-    unpack8(x[r * vc_in + col], a);
-    if (ACT == ACT_GLU) unpack8(x[r * vc_in + col + vc_out], g);
-    unpack8(dout[r * vc_out + col], d);
+    unpack8(xs[ri * vc_in + col], a);
+    if (ACT == ACT_GLU) unpack8(xs[ri * vc_in + col + vc_out], g);
+    unpack8(ds[ri * vc_out + col], d);
     bn_act_dz<ACT>(a, g, d, sc0, sh0, sc1, sh1, dz0, dz1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = sc0[j] * (dz0[j] - k0[j] - (a[j] - m0[j]) * r0[j] * l0[j]);
@@ -561,6 +618,11 @@ __global__ void bn_act_bwd_apply_kernel(const uint4* __restrict__ x, const uint4
       for (int j = 0; j < 8; ++j) o[j] = sc1[j] * (dz1[j] - k1[j] - (g[j] - m1[j]) * r1[j] * l1[j]);
       dx[r * vc_in + col + vc_out] = pack8(o);
     }
+  };
+  if (STAGED) {
+    staged_rows<true>(x, dout, P, vc_in, vc_out, tile_rows, rl, rpb, body);
+  } else {
+    for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += (long long)gridDim.y * rpb) body(x, dout, r, r);
   }
 }
 
@@ -798,6 +860,34 @@ static inline unsigned grid1d(long long n, int threads = 256) {
 
 using namespace sg2;
 
+// Staged (cp.async.bulk) geometry for a [P][C] tensor: one block spans all columns; ~16 KB row tiles.
+struct StagedGeo {
+  bool ok;
+  int tile_rows;
+  unsigned lanes;
+  size_t smem;
+};
+static StagedGeo make_staged(const Geo& g, long long P, int vc_in, int vc_out, bool with_d) {
+  StagedGeo sg{false, 0, 0, 0};
+  static int on = [] {
+    const char* e = getenv("SG2_BN_STAGED");
+    return e ? atoi(e) : 1;
+  }();
+  if (!on || g.grid.x != 1 || P * vc_in * 16 < (4LL << 20)) return sg;   // small tensors are latency bound anyway
+  int k = 16384 / (g.rpb * vc_in * 16);
+  if (k < 1) k = 1;
+  sg.tile_rows = g.rpb * k;
+  const long long tiles = (P + sg.tile_rows - 1) / sg.tile_rows;
+  sg.lanes = (unsigned)(tiles < 296 ? tiles : 296);
+  sg.smem = (size_t)kStStages * sg.tile_rows * (vc_in + (with_d ? vc_out : 0)) * 16 + 128;
+  sg.ok = sg.smem <= 100 * 1024;
+  return sg;
+}
+template <typename K>
+static void staged_attr(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+}
+
 extern "C" {
 
 int sg2_pack_weights(int kind, const float* w, void* wpk, void* wpkT, int Cout, int Cin, int CoP, int CiP,
@@ -878,10 +968,25 @@ int sg2_bn_act_fwd(const void* x, const float* stats, float* mean, float* rstd, 
   const int has_bn = (mean != nullptr);
   if (stats && !mean) EW_FAIL(SG2_EINVAL, "bn_act_fwd: stats given without mean/rstd outputs");
   cudaStream_t st = (cudaStream_t)stream;
-#define ARGS (const uint4*)x, mean, rstd, gamma, beta, (const uint4*)residual, (uint4*)out, P, C / 8, Cout / 8, g.cpb, g.rpb, has_bn, stats, eps, momentum, mean, rstd, running_mean, running_var, num_batches_tracked
-  if (act == ACT_GLU) bn_act_fwd_kernel<ACT_GLU><<<g.grid, g.block, 0, st>>>(ARGS);
-  else if (act == ACT_LRELU) bn_act_fwd_kernel<ACT_LRELU><<<g.grid, g.block, 0, st>>>(ARGS);
-  else bn_act_fwd_kernel<ACT_NONE><<<g.grid, g.block, 0, st>>>(ARGS);
+  const StagedGeo sg = make_staged(g, P, C / 8, Cout / 8, false);
+  static bool attr = false;
+  if (!attr) {
+    staged_attr(bn_act_fwd_kernel<ACT_GLU, true>);
+    staged_attr(bn_act_fwd_kernel<ACT_LRELU, true>);
+    staged_attr(bn_act_fwd_kernel<ACT_NONE, true>);
+    attr = true;
+  }
+#define ARGS (const uint4*)x, mean, rstd, gamma, beta, (const uint4*)residual, (uint4*)out, P, C / 8, Cout / 8, g.cpb, g.rpb, has_bn, stats, eps, momentum, mean, rstd, running_mean, running_var, num_batches_tracked, sg.tile_rows
+  if (sg.ok) {
+    dim3 grid(1, sg.lanes, groups);
+    if (act == ACT_GLU) bn_act_fwd_kernel<ACT_GLU, true><<<grid, g.block, sg.smem, st>>>(ARGS);
+    else if (act == ACT_LRELU) bn_act_fwd_kernel<ACT_LRELU, true><<<grid, g.block, sg.smem, st>>>(ARGS);
+    else bn_act_fwd_kernel<ACT_NONE, true><<<grid, g.block, sg.smem, st>>>(ARGS);
+  } else {
+    if (act == ACT_GLU) bn_act_fwd_kernel<ACT_GLU, false><<<g.grid, g.block, 0, st>>>(ARGS);
+    else if (act == ACT_LRELU) bn_act_fwd_kernel<ACT_LRELU, false><<<g.grid, g.block, 0, st>>>(ARGS);
+    else bn_act_fwd_kernel<ACT_NONE, false><<<g.grid, g.block, 0, st>>>(ARGS);
+  }
 #undef ARGS
   return launch_ok("bn_act_fwd");
 }
@@ -896,18 +1001,32 @@ int sg2_bn_act_bwd(const void* x, const void* dout, const float* mean, const flo
   Geo g = make_geo(P, Cout, 148 * 4);
   g.grid.z = groups;
   cudaStream_t st = (cudaStream_t)stream;
-#define RARGS (const uint4*)x, (const uint4*)dout, mean, rstd, gamma, beta, P, C / 8, Cout / 8, g.cpb, g.rpb, sums, C
-#define AARGS (const uint4*)x, (const uint4*)dout, mean, rstd, gamma, beta, sums, P, C / 8, Cout / 8, g.cpb, g.rpb, (uint4*)dx, C, dgamma, dbeta, accumulate
-  if (act == ACT_GLU) {
-    bn_act_bwd_reduce_kernel<ACT_GLU><<<g.grid, g.block, 0, st>>>(RARGS);
-    bn_act_bwd_apply_kernel<ACT_GLU><<<g.grid, g.block, 0, st>>>(AARGS);
-  } else if (act == ACT_LRELU) {
-    bn_act_bwd_reduce_kernel<ACT_LRELU><<<g.grid, g.block, 0, st>>>(RARGS);
-    bn_act_bwd_apply_kernel<ACT_LRELU><<<g.grid, g.block, 0, st>>>(AARGS);
-  } else {
-    bn_act_bwd_reduce_kernel<ACT_NONE><<<g.grid, g.block, 0, st>>>(RARGS);
-    bn_act_bwd_apply_kernel<ACT_NONE><<<g.grid, g.block, 0, st>>>(AARGS);
+  const StagedGeo sg = make_staged(g, P, C / 8, Cout / 8, true);
+  static bool attr = false;
+  if (!attr) {
+    staged_attr(bn_act_bwd_reduce_kernel<ACT_GLU, true>);
+    staged_attr(bn_act_bwd_reduce_kernel<ACT_LRELU, true>);
+    staged_attr(bn_act_bwd_reduce_kernel<ACT_NONE, true>);
+    staged_attr(bn_act_bwd_apply_kernel<ACT_GLU, true>);
+    staged_attr(bn_act_bwd_apply_kernel<ACT_LRELU, true>);
+    staged_attr(bn_act_bwd_apply_kernel<ACT_NONE, true>);
+    attr = true;
   }
+#define RARGS (const uint4*)x, (const uint4*)dout, mean, rstd, gamma, beta, P, C / 8, Cout / 8, g.cpb, g.rpb, sums, C, sg.tile_rows
+#define AARGS (const uint4*)x, (const uint4*)dout, mean, rstd, gamma, beta, sums, P, C / 8, Cout / 8, g.cpb, g.rpb, (uint4*)dx, C, dgamma, dbeta, accumulate, sg.tile_rows
+#define SG2_BWD(ACT_)                                                                       \
+  if (sg.ok) {                                                                              \
+    dim3 grid(1, sg.lanes, groups);                                                         \
+    bn_act_bwd_reduce_kernel<ACT_, true><<<grid, g.block, sg.smem, st>>>(RARGS);            \
+    bn_act_bwd_apply_kernel<ACT_, true><<<grid, g.block, sg.smem, st>>>(AARGS);             \
+  } else {                                                                                  \
+    bn_act_bwd_reduce_kernel<ACT_, false><<<g.grid, g.block, 0, st>>>(RARGS);               \
+    bn_act_bwd_apply_kernel<ACT_, false><<<g.grid, g.block, 0, st>>>(AARGS);                \
+  }
+  if (act == ACT_GLU) { SG2_BWD(ACT_GLU) }
+  else if (act == ACT_LRELU) { SG2_BWD(ACT_LRELU) }
+  else { SG2_BWD(ACT_NONE) }
+#undef SG2_BWD
 #undef RARGS
 #undef AARGS
   return launch_ok("bn_act_bwd");

@@ -115,6 +115,10 @@ class GradSink:
         # after its single wgrad launch of this sink — lets the caller all-reduce and Adam-update that layer while the
         # rest of the backward pass is still running. Only valid when every conv sees exactly one backward pass.
         self.on_ready = on_ready
+        # on_repack(op): optional; called on the side stream once the layer's weight has been updated (on_ready) AND its
+        # own dgrad — the last reader of the old dgrad operand — has been issued: the caller re-packs the layer's bf16
+        # operands there, off the critical path, instead of lazily at the next forward.
+        self.on_repack = None
         # Weight gradients hang off the backward chain (only the optimiser consumes them), so they can run on a
         # side stream next to the dgrad / BatchNorm-backward chain; finish() joins.
         self.side = side_stream
@@ -147,6 +151,19 @@ class GradSink:
         with torch.cuda.stream(self.side):
             self.side.wait_event(ev)
             self._wgrad(op, x, dy)
+
+    def dgrad_done(self, op):
+        """The layer's dgrad (if any) has been issued on the current stream."""
+        if self.on_repack is None or self.on_ready is None:
+            return
+        if self.side is None:
+            self.on_repack(op)
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            self.on_repack(op)
 
     def _wgrad(self, op, x, dy):
         if self.on_ready is not None:
@@ -220,11 +237,14 @@ class ConvBlock:
             dy = dout
         if need_w:
             sink.conv(self.op, x, dy)
-        if not need_dx:
-            return None
-        _, wpkT = self.op.packs()
-        B, H, W, Cin = x.shape
-        return ops.conv_dgrad(self.kind, dy, wpkT, B, H, W, Cin)
+        dx = None
+        if need_dx:
+            _, wpkT = self.op.packs()
+            B, H, W, Cin = x.shape
+            dx = ops.conv_dgrad(self.kind, dy, wpkT, B, H, W, Cin)
+        if need_w:
+            sink.dgrad_done(self.op)
+        return dx
 
 
 class HeadBlock:
@@ -246,7 +266,9 @@ class HeadBlock:
         sink.conv(self.op, h, dy)
         _, wpkT = self.op.packs()
         B, H, W, C = h.shape
-        return ops.conv_dgrad(CONV3, dy, wpkT, B, H, W, C, flop_scale=self.op.flop_scale)
+        dx = ops.conv_dgrad(CONV3, dy, wpkT, B, H, W, C, flop_scale=self.op.flop_scale)
+        sink.dgrad_done(self.op)
+        return dx
 
 
 def _acc(a, b):
@@ -281,6 +303,12 @@ class GEngine:
 
     def params(self):
         return [p for p in self.net.parameters()]
+
+    def conv_ops(self):
+        ops_ = [b.op for b in self.ups1] + [h.op for h in self.heads]
+        for joint, res, up in self.stages:
+            ops_ += [joint.op, up.op] + [b.op for pair in res for b in pair]
+        return ops_
 
     # ------------------------------------------------------------------ forward
     def forward(self, z, emb, eps, training):
@@ -399,11 +427,14 @@ class StemBlock:
         dy = ops.lrelu_bwd(y, dout).view(1, 1, -1, self.op.Cout)
         if need_w:
             sink.conv(self.op, col, dy)
-        if not need_dimg:
-            return None
-        _, wpkT = self.op.packs()
-        dcol = ops.conv_dgrad(GEMM, dy, wpkT, 1, 1, col.shape[2], 64, flop_scale=self.op.flop_scale)
-        return ops.stem_col2im(dcol, B, S)
+        dimg = None
+        if need_dimg:
+            _, wpkT = self.op.packs()
+            dcol = ops.conv_dgrad(GEMM, dy, wpkT, 1, 1, col.shape[2], 64, flop_scale=self.op.flop_scale)
+            dimg = ops.stem_col2im(dcol, B, S)
+        if need_w:
+            sink.dgrad_done(self.op)
+        return dimg
 
 
 class DEngine:
@@ -423,6 +454,9 @@ class DEngine:
 
     def params(self):
         return [p for p in self.net.parameters()]
+
+    def conv_ops(self):
+        return [self.stem.op, self.joint.op] + [b.op for b in self.trunk]
 
     def forward(self, img, c, training, out_cond=None, out_uncond=None, groups=1):
         """groups > 1: img / c hold `groups` equal sub-batches that the reference runs as separate D passes (separate

@@ -158,6 +158,15 @@ class FusedTrainer:
             bucket.adam_range(o, n, lr)
             done.add(w)
 
+        def repack(op):
+            # the layer's master was just updated (ready) and its dgrad has been issued: refresh its bf16 operands now,
+            # on the side stream, instead of lazily on the critical path of the next forward
+            w = op.weight
+            if w in done:
+                w._sg2_version = getattr(w, "_sg2_version", 0) + 1
+                op.packs()
+                repacked.add(w)
+
         def finish():
             if self.all_reduce is not None:
                 self.all_reduce(bucket.grad[:bucket.head_n])
@@ -165,8 +174,12 @@ class FusedTrainer:
             for w in bucket.params:
                 if w not in done and bucket.range_of[w][0] >= bucket.head_n:
                     ready(w)
-            bucket.dirty()
+            for w in bucket.params:
+                if w not in repacked:
+                    w._sg2_version = getattr(w, "_sg2_version", 0) + 1
 
+        repacked = set()
+        ready.repack = repack
         return ready, finish
 
     def _bce(self, probs, targets, weights, loss_slot):
@@ -227,6 +240,7 @@ class FusedTrainer:
                 bucket.grad.zero_()                 # conv weight gradients accumulate straight into the bucket
                 ready, fin = self._layerwise(bucket, self.lr_d) if (self.batched_d and self.layerwise) else (None, None)
                 sink = GradSink(bucket.views, self._sW[i] if self.concurrent else None, prezeroed=True, on_ready=ready)
+                sink.on_repack = ready.repack if ready is not None else None
                 if self.batched_d:
                     # real | wrong | fake in ONE pass of 3B samples with per-sub-batch BatchNorm statistics: the same
                     # arithmetic as the reference's three passes (trainer.py:390-392), a third of the launches, and
@@ -281,6 +295,7 @@ class FusedTrainer:
         self.bG.grad.zero_()
         ready, fin = self._layerwise(self.bG, self.lr_g) if self.layerwise else (None, None)
         sinkG = GradSink(self.bG.views, self._sW[nD] if self.concurrent else None, prezeroed=True, on_ready=ready)
+        sinkG.on_repack = ready.repack if ready is not None else None
         self.G.backward(Tg, dimgs, dmu, dlogvar, sinkG)
         sinkG.finish()
         if fin is not None:
