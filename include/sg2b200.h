@@ -119,8 +119,11 @@ int sg2_linear_fwd(const float* x1, int K1, const float* x2, int K2, const float
                    int out_bf16, int M, int N, void* stream);
 int sg2_linear_bwd_w(const void* dy, int dy_bf16, const float* x1, int K1, const float* x2, int K2, float* dw,
                      float* dbias, int M, int N, int accumulate, void* stream);
-int sg2_linear_bwd_x(const void* dy, int dy_bf16, const float* w, float* dx /* [M][Kout], overwritten */, int M, int N,
-                     int K, int Kout, void* stream);
+/* dx = dy . w[:, :Kout]: two deterministic passes (per-slab partials in `scratch`, then their sum). */
+int sg2_linear_bwd_x_scratch_floats(int N, int Kout);
+int sg2_linear_bwd_x(const void* dy, int dy_bf16, const float* w, float* dx /* [M][Kout], overwritten */,
+                     float* scratch /* sg2_linear_bwd_x_scratch_floats(N, Kout) floats */, int M, int N, int K, int Kout,
+                     void* stream);
 /* CA_NET GLU + reparameterisation (model.py:183-195): fc [B][4E] -> mu, logvar, c = eps*exp(.5 logvar)+mu */
 int sg2_ca_glu_reparam_fwd(const float* fc, const float* eps, float* mu, float* logvar, float* c, int B, int E,
                            void* stream);

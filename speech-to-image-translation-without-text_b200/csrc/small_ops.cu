@@ -23,6 +23,7 @@ __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + __expf(-x))
 // warp walks `npw` output features, lanes stride K (coalesced weight rows read ONCE), 32 batch rows accumulate in
 // registers and one butterfly transpose-sum per feature leaves row m's result in lane m.
 constexpr int kLinKC = 256;
+constexpr int kLinF = 2;     // features per warp step in linear_fwd (they share the shared-memory reads of x)
 __device__ __forceinline__ float lin_x(const float* x1, int K1, const float* x2, int K2, int m, int k) {
   return k < K1 ? x1[(long long)m * K1 + k] : x2[(long long)m * K2 + (k - K1)];
 }
@@ -31,17 +32,20 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
                                                          int K2, const float* __restrict__ w,
                                                          const float* __restrict__ bias, void* __restrict__ out, int M,
                                                          int N, int npw) {
+  // each warp walks `npw` groups of kLinF features; the kLinF features of a group share every shared-memory read of x
   __shared__ float xs[32][kLinKC];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = K1 + K2;
   const int nchunks = (K + kLinKC - 1) / kLinKC;
-  const int nbase = (blockIdx.x * 8 + warp) * npw;
+  const int nbase = (blockIdx.x * 8 + warp) * npw * kLinF;
   for (int m0 = 0; m0 < M; m0 += 32) {
     for (int i = 0; i < npw; ++i) {
-      const int n = nbase + i;
-      float acc[32];
+      const int n = nbase + i * kLinF;
+      float acc[kLinF][32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+      for (int f = 0; f < kLinF; ++f)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[f][j] = 0.f;
       for (int c = 0; c < nchunks; ++c) {
         if (nchunks > 1 || i == 0) {  // a single chunk stays staged for all features of the block
           __syncthreads();
@@ -51,27 +55,34 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
           }
           __syncthreads();
         }
-        if (n < N) {
-          const int kend = min(kLinKC, K - c * kLinKC);
-          for (int kk = lane; kk < kend; kk += 32) {
-            const float wv = w[(long long)n * K + c * kLinKC + kk];
+        const int kend = min(kLinKC, K - c * kLinKC);
+        for (int kk = lane; kk < kend; kk += 32) {
+          float wv[kLinF];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = fmaf(wv, xs[j][kk], acc[j]);
+          for (int f = 0; f < kLinF; ++f) wv[f] = n + f < N ? w[(long long)(n + f) * K + c * kLinKC + kk] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float xv = xs[j][kk];
+#pragma unroll
+            for (int f = 0; f < kLinF; ++f) acc[f][j] = fmaf(wv[f], xv, acc[f][j]);
           }
         }
       }
-      const float s = warp_transpose_sum(acc, lane);  // lane m: sum over k of row m0 + m
-      const int m = m0 + lane;
-      if (n < N && m < M) {
-        const float v = s + (bias ? bias[n] : 0.f);
-        if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[(long long)m * N + n] = __float2bfloat16_rn(v);
-        else reinterpret_cast<float*>(out)[(long long)m * N + n] = v;
+#pragma unroll
+      for (int f = 0; f < kLinF; ++f) {
+        const float s = warp_transpose_sum(acc[f], lane);  // lane m: sum over k of row m0 + m
+        const int m = m0 + lane;
+        if (n + f < N && m < M) {
+          const float v = s + (bias ? bias[n + f] : 0.f);
+          if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[(long long)m * N + n + f] = __float2bfloat16_rn(v);
+          else reinterpret_cast<float*>(out)[(long long)m * N + n + f] = v;
+        }
       }
     }
   }
 }
 
-// dw[n][k] (+)= sum_m dy[m][n] * x(m,k);  dbias[n] (+)= sum_m dy[m][n].
+// dw[n][k] (+)= sum_m dy[m][n] * x(m,k);  dbias[n] (+)= sum_m dy[m][n].   M <= 32 per launch.
 // block = 256 consecutive k (grid.y = k slabs) x kLinNB features (grid.x): thread k keeps its activation column in
 // registers, the dy columns of the block sit in shared memory (broadcast reads), dw rows are written coalesced.
 constexpr int kLinNB = 64;
@@ -80,63 +91,67 @@ __global__ void __launch_bounds__(256) linear_bwd_w_kernel(const void* __restric
                                                            int K1, const float* __restrict__ x2, int K2,
                                                            float* __restrict__ dw, float* __restrict__ dbias, int M, int N,
                                                            int accumulate) {
-  __shared__ float ds[64][kLinNB];  // [m][n]
+  __shared__ float ds[kLinNB][32];  // [n][m]: one feature's batch column is one 128-byte row
   const int K = K1 + K2;
   const int n0 = blockIdx.x * kLinNB;
   const int k = blockIdx.y * 256 + threadIdx.x;
-  for (int e = threadIdx.x; e < M * kLinNB; e += 256) {
-    const int m = e / kLinNB, n = n0 + e % kLinNB;
+  for (int e = threadIdx.x; e < 32 * kLinNB; e += 256) {
+    const int m = e / kLinNB, j = e % kLinNB, n = n0 + j;
     float d = 0.f;
-    if (n < N)
+    if (n < N && m < M)
       d = DY_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy)[(long long)m * N + n])
                   : reinterpret_cast<const float*>(dy)[(long long)m * N + n];
-    ds[m][e % kLinNB] = d;
+    ds[j][m] = d;
   }
   __syncthreads();
   if (dbias && blockIdx.y == 0 && threadIdx.x < kLinNB && n0 + threadIdx.x < N) {
     float s = 0.f;
-    for (int m = 0; m < M; ++m) s += ds[m][threadIdx.x];
+    for (int m = 0; m < M; ++m) s += ds[threadIdx.x][m];
     if (accumulate) dbias[n0 + threadIdx.x] += s; else dbias[n0 + threadIdx.x] = s;
   }
   if (k >= K) return;
-  float xr[64];
+  float xr[32];
 #pragma unroll
-  for (int m = 0; m < 64; ++m) xr[m] = m < M ? lin_x(x1, K1, x2, K2, m, k) : 0.f;
+  for (int m = 0; m < 32; ++m) xr[m] = m < M ? lin_x(x1, K1, x2, K2, m, k) : 0.f;
   const int nend = min(kLinNB, N - n0);
   for (int j = 0; j < nend; ++j) {
     float acc = 0.f;
 #pragma unroll
-    for (int m = 0; m < 64; ++m)
-      if (m < M) acc = fmaf(ds[m][j], xr[m], acc);
+    for (int m4 = 0; m4 < 8; ++m4) {   // broadcast 128-bit reads of the feature's batch column
+      const float4 d4 = reinterpret_cast<const float4*>(ds[j])[m4];
+      acc = fmaf(d4.x, xr[4 * m4], acc);
+      acc = fmaf(d4.y, xr[4 * m4 + 1], acc);
+      acc = fmaf(d4.z, xr[4 * m4 + 2], acc);
+      acc = fmaf(d4.w, xr[4 * m4 + 3], acc);
+    }
     float* o = dw + (long long)(n0 + j) * K + k;
     if (accumulate) *o += acc; else *o = acc;
   }
 }
 
-// dx[m][k] = sum_n dy[m][n] * w[n][k] for k < Kout (only the leading Kout inputs need a gradient).
-// grid.x = feature slabs of kLinNB; thread = k; the slab's dy sits in shared memory, all batch rows accumulate in
-// registers while the weight rows are read once; fp32 atomics into a zeroed dx.
+// dx[m][k] = sum_n dy[m][n] * w[n][k] for k < Kout (only the leading Kout inputs need a gradient).   M <= 32 per launch.
+// Pass 1 (grid.x = feature slabs of kLinNB, thread = k): the slab's dy sits in shared memory, all batch rows accumulate
+// in registers while the weight rows are read once; the slab's partial [M][Kout] goes to scratch. Pass 2 sums the slabs
+// (deterministic, no atomics).
 template <bool DY_BF16>
 __global__ void __launch_bounds__(256) linear_bwd_x_kernel(const void* __restrict__ dy, const float* __restrict__ w,
-                                                           float* __restrict__ dx, int M, int N, int K, int Kout) {
-  constexpr int NBX = kLinNB;              // features per block
-  extern __shared__ float dsx[];           // [m][NBX]
-  float (*ds)[NBX] = reinterpret_cast<float (*)[NBX]>(dsx);
-  const int n0 = blockIdx.x * NBX;
-  for (int e = threadIdx.x; e < M * NBX; e += blockDim.x) {
-    const int m = e / NBX, n = n0 + e % NBX;
+                                                           float* __restrict__ part, int M, int N, int K, int Kout) {
+  __shared__ float ds[kLinNB][32];  // [n][m]
+  const int n0 = blockIdx.x * kLinNB;
+  for (int e = threadIdx.x; e < 32 * kLinNB; e += blockDim.x) {
+    const int m = e / kLinNB, j = e % kLinNB, n = n0 + j;
     float d = 0.f;
-    if (n < N)
+    if (n < N && m < M)
       d = DY_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy)[(long long)m * N + n])
                   : reinterpret_cast<const float*>(dy)[(long long)m * N + n];
-    ds[m][e % NBX] = d;
+    ds[j][m] = d;
   }
   __syncthreads();
-  const int nend = min(NBX, N - n0);
+  const int nend = min(kLinNB, N - n0);
   for (int k = threadIdx.x; k < Kout; k += blockDim.x) {
-    float acc[64];
+    float acc[32];
 #pragma unroll
-    for (int m = 0; m < 64; ++m) acc[m] = 0.f;
+    for (int m = 0; m < 32; ++m) acc[m] = 0.f;
     for (int j0 = 0; j0 < nend; j0 += 8) {      // 8 weight rows in flight per thread
       float wv[8];
 #pragma unroll
@@ -145,15 +160,37 @@ __global__ void __launch_bounds__(256) linear_bwd_x_kernel(const void* __restric
       for (int u = 0; u < 8; ++u) {
         if (j0 + u < nend) {
 #pragma unroll
-          for (int m = 0; m < 64; ++m)
-            if (m < M) acc[m] = fmaf(ds[m][j0 + u], wv[u], acc[m]);
+          for (int m4 = 0; m4 < 8; ++m4) {
+            const float4 d4 = reinterpret_cast<const float4*>(ds[j0 + u])[m4];
+            acc[4 * m4] = fmaf(d4.x, wv[u], acc[4 * m4]);
+            acc[4 * m4 + 1] = fmaf(d4.y, wv[u], acc[4 * m4 + 1]);
+            acc[4 * m4 + 2] = fmaf(d4.z, wv[u], acc[4 * m4 + 2]);
+            acc[4 * m4 + 3] = fmaf(d4.w, wv[u], acc[4 * m4 + 3]);
+          }
         }
       }
     }
+    float* o = part + ((long long)blockIdx.x * 32) * Kout + k;
 #pragma unroll
-    for (int m = 0; m < 64; ++m)
-      if (m < M) atomicAdd(&dx[(long long)m * Kout + k], acc[m]);
+    for (int m = 0; m < 32; ++m)
+      if (m < M) o[(long long)m * Kout] = acc[m];
   }
+}
+__global__ void linear_bwd_x_reduce_kernel(const float* __restrict__ part, float* __restrict__ dx, int nslabs, int M,
+                                           int Kout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (m, k)
+  if (i >= M * Kout) return;
+  const int m = i / Kout, k = i % Kout;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int b = 0;
+  for (; b + 3 < nslabs; b += 4) {
+    s0 += part[((long long)(b + 0) * 32 + m) * Kout + k];
+    s1 += part[((long long)(b + 1) * 32 + m) * Kout + k];
+    s2 += part[((long long)(b + 2) * 32 + m) * Kout + k];
+    s3 += part[((long long)(b + 3) * 32 + m) * Kout + k];
+  }
+  for (; b < nslabs; ++b) s0 += part[((long long)b * 32 + m) * Kout + k];
+  dx[i] = (s0 + s1) + (s2 + s3);
 }
 
 // ------------------------------------------------------------------------------------------ CA_NET tail
@@ -410,10 +447,10 @@ extern "C" {
 int sg2_linear_fwd(const float* x1, int K1, const float* x2, int K2, const float* w, const float* bias, void* out,
                    int out_bf16, int M, int N, void* stream) {
   if (M < 1 || M > 4096) SG2_FAIL(SG2_EINVAL, "linear_fwd: M=%d", M);
-  // features per warp: enough to amortise the activation staging, few enough to fill the SMs (8 warps per block)
-  int npw = N / (8 * 148 * 8);
+  // feature groups per warp: enough to amortise the activation staging, few enough to fill the SMs (8 warps per block)
+  int npw = N / (kLinF * 8 * 148 * 4);
   npw = npw < 1 ? 1 : (npw > 8 ? 8 : npw);
-  dim3 grid((N + 8 * npw - 1) / (8 * npw)), block(256);
+  dim3 grid((N + kLinF * 8 * npw - 1) / (kLinF * 8 * npw)), block(256);
   if (out_bf16)
     linear_fwd_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(x1, K1, x2, K2, w, bias, out, M, N, npw);
   else
@@ -425,8 +462,8 @@ int sg2_linear_bwd_w(const void* dy, int dy_bf16, const float* x1, int K1, const
                      float* dbias, int M, int N, int accumulate, void* stream) {
   const int K = K1 + K2;
   dim3 grid((N + kLinNB - 1) / kLinNB, (K + 255) / 256);
-  for (int m0 = 0; m0 < M; m0 += 64) {  // batch rows in slabs of 64 (the kernel keeps one activation column in registers)
-    const int mc = M - m0 < 64 ? M - m0 : 64;
+  for (int m0 = 0; m0 < M; m0 += 32) {  // batch rows in slabs of 32 (the kernel keeps one activation column in registers)
+    const int mc = M - m0 < 32 ? M - m0 : 32;
     const int acc = (accumulate || m0 > 0) ? 1 : 0;
     const float* x1o = x1 + (size_t)m0 * K1;
     const float* x2o = x2 ? x2 + (size_t)m0 * K2 : nullptr;
@@ -440,27 +477,25 @@ int sg2_linear_bwd_w(const void* dy, int dy_bf16, const float* x1, int K1, const
   SG2_LAUNCH_OK("linear_bwd_w");
 }
 
-int sg2_linear_bwd_x(const void* dy, int dy_bf16, const float* w, float* dx, int M, int N, int K, int Kout,
-                     void* stream) {
+int sg2_linear_bwd_x_scratch_floats(int N, int Kout) { return ((N + kLinNB - 1) / kLinNB) * 32 * Kout; }
+
+int sg2_linear_bwd_x(const void* dy, int dy_bf16, const float* w, float* dx, float* scratch, int M, int N, int K,
+                     int Kout, void* stream) {
   if (Kout > K) SG2_FAIL(SG2_EINVAL, "linear_bwd_x: Kout=%d", Kout);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(linear_bwd_x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 4 * kLinNB * 4);
-    cudaFuncSetAttribute(linear_bwd_x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 4 * kLinNB * 4);
-    attr = true;
-  }
-  cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)M * Kout, (cudaStream_t)stream);
-  if (e != cudaSuccess) SG2_FAIL((int)e, "linear_bwd_x memset: %s", cudaGetErrorString(e));
+  if (!scratch) SG2_FAIL(SG2_EINVAL, "linear_bwd_x: scratch of sg2_linear_bwd_x_scratch_floats(N, Kout) floats required");
   int threads = ((Kout + 31) / 32) * 32;
   threads = threads > 256 ? 256 : threads;
-  for (int m0 = 0; m0 < M; m0 += 64) {
-    const int mc = M - m0 < 64 ? M - m0 : 64;
+  const int nslabs = (N + kLinNB - 1) / kLinNB;
+  for (int m0 = 0; m0 < M; m0 += 32) {
+    const int mc = M - m0 < 32 ? M - m0 : 32;
     if (dy_bf16)
-      linear_bwd_x_kernel<true><<<(N + kLinNB - 1) / kLinNB, threads, mc * kLinNB * sizeof(float), (cudaStream_t)stream>>>(
-          reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)m0 * N, w, dx + (size_t)m0 * Kout, mc, N, K, Kout);
+      linear_bwd_x_kernel<true><<<nslabs, threads, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)m0 * N, w, scratch, mc, N, K, Kout);
     else
-      linear_bwd_x_kernel<false><<<(N + kLinNB - 1) / kLinNB, threads, mc * kLinNB * sizeof(float), (cudaStream_t)stream>>>(
-          reinterpret_cast<const float*>(dy) + (size_t)m0 * N, w, dx + (size_t)m0 * Kout, mc, N, K, Kout);
+      linear_bwd_x_kernel<false><<<nslabs, threads, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const float*>(dy) + (size_t)m0 * N, w, scratch, mc, N, K, Kout);
+    linear_bwd_x_reduce_kernel<<<(mc * Kout + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch, dx + (size_t)m0 * Kout,
+                                                                                          nslabs, mc, Kout);
   }
   SG2_LAUNCH_OK("linear_bwd_x");
 }

@@ -391,7 +391,9 @@ def linear_bwd_w(dy, x1, x2, dw, db, accumulate=False):
 def linear_bwd_x(dy, w, Kout):
     M, N = dy.shape
     dx = torch.empty((M, Kout), device=dy.device, dtype=torch.float32)
-    _call("sg2_linear_bwd_x", 2, _p(dy), int(dy.dtype == torch.bfloat16), _p(w), _p(dx), M, N, w.shape[1], Kout, _st())
+    scratch = torch.empty(_lib.lib().sg2_linear_bwd_x_scratch_floats(N, Kout), device=dy.device, dtype=torch.float32)
+    _call("sg2_linear_bwd_x", 2, _p(dy), int(dy.dtype == torch.bfloat16), _p(w), _p(dx), _p(scratch), M, N, w.shape[1],
+          Kout, _st())
     return dx
 
 
