@@ -384,6 +384,7 @@ static int launch_tile(const GatherDesc& d, cudaStream_t st) {
   if (rc) return rc;
   const int bn = pl.bn, bk = pl.bk;
   const int nt = d.ntaps / d.nmaps;
+  if (nt == 1 && bn == 64 && bk == 64) return launch_tile_t<64, 64, 1>(d, pl, st);   // 64 -> 64 GEMM tiles (D stems)
   if (nt != 4 && nt != 9) return 1;
   if (d.stats && d.stats_bg > 0 && (bn + 31) / 32 > 4) return 1;  // grouped statistics need the register-held sums
 #define SG2_CASE(BN_, BK_)                                                   \

@@ -771,31 +771,39 @@ __global__ void head_tanh_bwd_kernel(const float* __restrict__ dimg, const float
 }
 
 // D stem: conv4x4 s2 p1 on a 3-channel fp32 NCHW image == GEMM over im2col rows [P][64] (k = (kh*4+kw)*3 + c, 48 used)
-__global__ void stem_im2col_kernel(const float* __restrict__ img, uint4* __restrict__ col, int B, int S) {
-  const int So = S / 2;
-  const long long total = (long long)B * So * So * 8;  // 8 vectors of 8 bf16 per row
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i & 7);
-    const long long pix = i >> 3;
-    const int ox = (int)(pix % So);
-    const int oy = (int)((pix / So) % So);
-    const int b = (int)(pix / ((long long)So * So));
-    float f[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = v * 8 + j;
-      float val = 0.f;
-      if (k < 48) {
-        const int c = k % 3, t = k / 3, kh = t >> 2, kw = t & 3;
-        const int y = 2 * oy + kh - 1, x = 2 * ox + kw - 1;
-        if (y >= 0 && y < S && x >= 0 && x < S) val = img[(((long long)b * 3 + c) * S + y) * S + x];
-      }
-      f[j] = val;
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, uint4* __restrict__ col, int B,
+                                                          int S) {
+  // one block = one output row (b, oy): the 4 input rows x 3 channels it reads are staged in shared memory with
+  // coalesced loads (+1 zero column each side = the conv padding); every thread then emits 16-byte col vectors.
+  extern __shared__ float rows[];   // [3][4][S + 2]
+  const int So = S / 2, SP = S + 2;
+  for (int blk = blockIdx.x; blk < B * So; blk += gridDim.x) {
+    const int b = blk / So, oy = blk % So;
+    for (int e = threadIdx.x; e < 12 * SP; e += blockDim.x) {
+      const int xx = e % SP, rr = (e / SP) & 3, c = e / (4 * SP);
+      const int y = 2 * oy + rr - 1, x = xx - 1;
+      rows[e] = (y >= 0 && y < S && x >= 0 && x < S) ? img[(((long long)b * 3 + c) * S + y) * S + x] : 0.f;
     }
-    col[i] = pack8(f);
+    __syncthreads();
+    for (int e = threadIdx.x; e < So * 8; e += blockDim.x) {
+      const int v = e & 7, ox = e >> 3;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = v * 8 + j;
+        float val = 0.f;
+        if (k < 48) {
+          const int c = k % 3, t = k / 3, kh = t >> 2, kw = t & 3;
+          val = rows[(c * 4 + kh) * SP + 2 * ox + kw];
+        }
+        f[j] = val;
+      }
+      col[((long long)blk * So + ox) * 8 + v] = pack8(f);
+    }
+    __syncthreads();
   }
 }
+
 // dimg fp32 NCHW (=, not +=) from dcol [P][64] bf16 (gather form: no atomics)
 __global__ void stem_col2im_kernel(const __nv_bfloat16* __restrict__ dcol, float* __restrict__ dimg, int B, int S) {
   const int So = S / 2;
@@ -1086,8 +1094,9 @@ int sg2_head_tanh_bwd(const float* dimg, const float* img, void* dy, int B, int 
 
 int sg2_stem_im2col(const float* img, void* col, int B, int S, void* stream) {
   if (S % 2) EW_FAIL(SG2_EINVAL, "stem_im2col: odd image size");
-  stem_im2col_kernel<<<grid1d((long long)B * (S / 2) * (S / 2) * 8), 256, 0, (cudaStream_t)stream>>>(
-      img, (uint4*)col, B, S);
+  long long nblk = (long long)B * (S / 2);
+  if (nblk > 148 * 16) nblk = 148 * 16;
+  stem_im2col_kernel<<<(unsigned)nblk, 256, 12 * (S + 2) * sizeof(float), (cudaStream_t)stream>>>(img, (uint4*)col, B, S);
   return launch_ok("stem_im2col");
 }
 

@@ -413,13 +413,16 @@ class StemBlock:
         self.conv = conv
         self.op = ConvOperand(STEM, conv.weight, cin_pad=64)
 
-    def fwd(self, img):
+    def fwd(self, img, col=None):
+        """col: optional precomputed im2col rows of `img` (the G step reuses the fake third of the D update's)."""
         B, _, S, _ = img.shape
-        col = ops.stem_im2col(img)
+        if col is None:
+            col = ops.stem_im2col(img)
         wpk, _ = self.op.packs()
-        # LeakyReLU runs in the GEMM epilogue; backward only needs the sign, and sign(lrelu(y)) == sign(y)
-        out = ops.conv_fprop(GEMM, col, wpk, self.op.Cout, flop_scale=self.op.flop_scale, act=ACT_LRELU)
-        out = out.view(B, S // 2, S // 2, self.op.Cout)
+        # LeakyReLU runs in the GEMM epilogue; backward only needs the sign, and sign(lrelu(y)) == sign(y).
+        # The im2col rows are presented as a (B, S/2, S/2, 64) NHWC tensor: a 1x1 conv on the tile-resident kernel.
+        out = ops.conv_fprop(GEMM, col.view(B, S // 2, S // 2, 64), wpk, self.op.Cout, flop_scale=self.op.flop_scale,
+                             act=ACT_LRELU)
         return out, (col, out, B, S)
 
     def bwd(self, saved, dout, sink, need_dimg, need_w=True):
@@ -458,12 +461,12 @@ class DEngine:
     def conv_ops(self):
         return [self.stem.op, self.joint.op] + [b.op for b in self.trunk]
 
-    def forward(self, img, c, training, out_cond=None, out_uncond=None, groups=1):
+    def forward(self, img, c, training, out_cond=None, out_uncond=None, groups=1, stem_col=None):
         """groups > 1: img / c hold `groups` equal sub-batches that the reference runs as separate D passes (separate
         BatchNorm batches, trainer.py:390-392); everything else is per sample, so one pass over the concatenation
         gives the same result."""
         T = {"groups": groups}
-        x, T["stem"] = self.stem.fwd(img)
+        x, T["stem"] = self.stem.fwd(img, stem_col)
         T["trunk"] = []
         for blk in self.trunk:
             x, sv = blk.fwd(x, training, groups=groups)

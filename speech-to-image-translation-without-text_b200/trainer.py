@@ -254,7 +254,10 @@ class FusedTrainer:
                     dprobs = dprobs.view(2, 3 * B)
                     D.backward(T3, dprobs[0], dprobs[1], None, False, False, True, sink)
                     tapes = [T3]
+                    # the fake third of the batched pass's im2col rows is exactly what the G step's D pass needs
+                    fake_col = T3["stem"][0].view(3, -1, 64)[2].view(1, 1, -1, 64)
                 else:
+                    fake_col = None
                     tapes = []
                     probs = torch.empty(6, B, device=self.dev, dtype=torch.float32)
                     for k, img in enumerate((real[i], wrong[i], fake[i])):
@@ -274,7 +277,7 @@ class FusedTrainer:
                     bucket.adam(self.lr_d)
                 # ---------------- (3a) D_i's share of the G step, trainer.py:436-446 (updated D weights, live fake, mu)
                 probs = torch.empty(2, B, device=self.dev, dtype=torch.float32)
-                _, _, x_imm, T = D.forward(fake[i], mu, True, probs[0], probs[1])
+                _, _, x_imm, T = D.forward(fake[i], mu, True, probs[0], probs[1], stem_col=fake_col)
                 dprobs = self._bce(probs, (1, 1), (1, u), parts[i:i + 1])
                 dx_imm = None
                 if self.cal > 0:
