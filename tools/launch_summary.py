@@ -9,11 +9,10 @@ for row in csv.DictReader(lines):
         u = row["Metric Unit"]
         v = v / 1000 if u == "ns" else (v * 1000 if u == "ms" else v)
         rows.append((int(row["ID"]), re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", ""), v, row.get("Grid Size")))
-# step boundary = the G network's adam_ema launch (4 adam_ema launches per step, the last one closes the step)
-adam = [i for i, r in enumerate(rows) if "adam_ema_kernel" in r[1]]
-per_step = 4
-if len(adam) >= 2 * per_step:
-    it = rows[adam[-per_step - 1] + 1: adam[-1] + 1]
+# step boundary: ca_glu_reparam_fwd runs once per step, a handful of launches (arena fills, CA_NET fc) after its start
+marks = [i for i, r in enumerate(rows) if "ca_glu_reparam_fwd_kernel" in r[1]]
+if len(marks) >= 2:
+    it = rows[max(marks[-2], marks[-1] - 6) if False else marks[-1] - 6:]
 else:
     per = len(rows) // nsteps
     it = rows[-per:]
@@ -28,7 +27,7 @@ for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:40]:
     print(f"{t:10.1f} {100*t/tot:5.1f}% {n:5d}  {k[:100]}")
 fam = collections.defaultdict(float)
 for _, k, v, g in it:
-    f = "igemm (tcgen05 conv fprop/dgrad/wgrad)" if "igemm" in k else ("BN/act/elementwise (sg2)" if "sg2::" in k else "torch (fill/add/copy/rng)")
+    f = "igemm (tcgen05 conv fprop/dgrad/wgrad)" if ("igemm" in k or "tile_conv" in k or "tile_wgrad" in k) else ("BN/act/elementwise (sg2)" if "sg2::" in k else "torch (fill/add/copy/rng)")
     fam[f] += v
 for f, t in sorted(fam.items(), key=lambda x: -x[1]):
     print(f"family {f:45s} {t/1000:8.3f} ms {100*t/tot:5.1f}%")
