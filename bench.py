@@ -320,6 +320,8 @@ def run_ours(args):
 
     if rank != 0:
         sdist.shutdown()
+        if world > 1:
+            os._exit(0)          # see dist.shutdown(): do not run NCCL / CUDA-graph destructors at exit
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -343,6 +345,8 @@ def run_ours(args):
     }
     print(json.dumps(out))
     sdist.shutdown()
+    if world > 1:
+        os._exit(0)
 
 
 def main():

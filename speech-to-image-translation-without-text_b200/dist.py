@@ -51,6 +51,9 @@ def broadcast_state(modules, src=0):
 
 
 def shutdown():
-    """Tear the process group down (avoids the NCCL 'destroy_process_group() was not called' warning at exit)."""
-    if dist.is_initialized():
-        dist.destroy_process_group()
+    """End of a benchmark process. destroy_process_group() blocked forever here when CUDA graphs that captured NCCL
+    collectives were still alive (2-GPU bench: result printed, process never exited), so the process group is left to
+    the interpreter's teardown; stdout is flushed first because the caller may hard-exit."""
+    import sys
+    sys.stdout.flush()
+    sys.stderr.flush()
