@@ -88,7 +88,8 @@ def test_conv_fprop_dgrad_wgrad(kind, B, H, W, Ci, Co):
 
 # --------------------------------------------------------------------------------------------- BN + activations
 @pytest.mark.parametrize("act", [0, 1, 2])
-@pytest.mark.parametrize("P,C", [(24 * 64, 128), (1000, 32), (24, 4096), (96, 640)])
+# (70000, 64) is > 4 MB with a ragged last tile: the cp.async.bulk-staged variants; the others use register loads
+@pytest.mark.parametrize("P,C", [(24 * 64, 128), (1000, 32), (24, 4096), (96, 640), (70000, 64)])
 def test_bn_act_forward_backward(act, P, C):
     """BatchNorm(train) + {identity(+residual), GLU, LeakyReLU(0.2)} vs torch; outputs are bf16 -> rel err <= 4e-3;
     statistics and dgamma/dbeta are fp32 -> <= 1e-4 / 2e-3."""
@@ -279,3 +280,38 @@ def test_losses_and_adam():
         ops._call("sg2_adam_tick", 1, step.data_ptr(), bc.data_ptr(), 0.5, 0.999, ops._st())
         ops._call("sg2_adam_ema", 1, p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), avg.data_ptr(), n, 2e-4, 0.5, 0.999, 1e-8, bc.data_ptr(), 0.999, None, ops._st())
     assert _rel(p, pr.detach()) < 1e-6 and _rel(avg, avg_ref) < 1e-6
+
+
+@pytest.mark.parametrize("act", [1, 2])
+@pytest.mark.parametrize("P1,C", [(384, 256), (24000, 64)])
+def test_bn_groups_equal_separate_calls(act, P1, C):
+    """groups = 3 (the batched real / wrong / fake discriminator pass): statistics, outputs, dx of each sub-batch equal
+    those of three separate calls up to the fp32 atomic summation order of the statistics (mean / rstd rel <= 1e-6, a
+    bf16 output may flip by one ulp: rel <= 1e-3); running statistics see three momentum updates in order; dgamma /
+    dbeta are the sums over the groups (rel <= 1e-5)."""
+    from sg2b200 import ops
+    g = torch.Generator().manual_seed(P1 + C + act)
+    x = (torch.randn(3 * P1, C, generator=g) * 1.3 + 0.2).cuda().bfloat16()
+    Co = C // 2 if act == 1 else C
+    dout = torch.randn(3 * P1, Co, generator=g).cuda().bfloat16()
+    gamma = (torch.randn(C, generator=g) * 0.1 + 1).cuda()
+    beta = (torch.randn(C, generator=g) * 0.1).cuda()
+    rm3, rv3, nbt3 = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"), torch.zeros((), dtype=torch.long, device="cuda")
+    st3 = ops.bn_stats32(C, x.device, 3)
+    ops.bn_stats(x, st3, 3)
+    out3, mean3, rstd3 = ops.bn_act_fwd(x, gamma, beta, act, stats=st3, running=(rm3, rv3, nbt3), groups=3)
+    dg3, db3 = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    dx3 = ops.bn_act_bwd(x, dout, mean3, rstd3, gamma, beta, act, dg3, db3, False, groups=3)
+    rm, rv, nbt = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"), torch.zeros((), dtype=torch.long, device="cuda")
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    for k in range(3):
+        xs, ds = x[k * P1:(k + 1) * P1].contiguous(), dout[k * P1:(k + 1) * P1].contiguous()
+        st = ops.bn_stats32(C, x.device)
+        ops.bn_stats(xs, st)
+        o, m, r = ops.bn_act_fwd(xs, gamma, beta, act, stats=st, running=(rm, rv, nbt))
+        assert _rel(o.float(), out3[k * P1:(k + 1) * P1].float()) < 1e-3
+        assert _rel(m, mean3.view(3, C)[k]) < 1e-6 and _rel(r, rstd3.view(3, C)[k]) < 1e-6
+        dxk = ops.bn_act_bwd(xs, ds, m, r, gamma, beta, act, dg, db, k > 0)
+        assert _rel(dxk.float(), dx3[k * P1:(k + 1) * P1].float()) < 1e-3
+    assert _rel(rm3, rm) < 1e-6 and _rel(rv3, rv) < 1e-6 and int(nbt3) == int(nbt) == 3
+    assert _rel(dg3, dg) < 1e-5 and _rel(db3, db) < 1e-5
