@@ -33,9 +33,9 @@ struct Geo {
   int vc, cpb, rpb;
   dim3 grid, block;
 };
-static Geo make_geo(long long P, int C, int max_row_blocks) {
+static Geo make_geo(long long P, int C, int max_row_blocks, int width = 8) {
   Geo g;
-  g.vc = C / 8;
+  g.vc = C / width;
   g.cpb = g.vc < 256 ? g.vc : 256;
   // round cpb down to a power of two that divides vc? vc is a multiple of 4 for every layer here; keep generic:
   while (g.vc % g.cpb) --g.cpb;
@@ -313,66 +313,81 @@ __global__ void bn_eval_prepare_kernel(const float* rmean, const float* rvar, fl
 // ============================================================================================ BN apply (+act)
 enum { ACT_NONE = 0, ACT_GLU = 1, ACT_LRELU = 2 };
 
-// Row streaming for the large [P][C] tensors. With 16-byte register loads each thread keeps two or three loads in
-// flight and the 100+-register GLU kernels fit two blocks per SM: ~16 KB in flight per SM, ~2.5 TB/s. STAGED variants
-// instead pull row tiles of ~16 KB through a 4-deep shared-memory ring with cp.async.bulk (the TMA engine, one elected
-// thread issues, mbarrier completion), so ~100-190 KB per SM are in flight regardless of register use; the math then
-// reads its operands from shared memory. body(xs, ds, ri, rg): xs/ds = row-major tiles, ri = row inside them,
-// rg = row of the whole tensor (for the outputs).
-constexpr int kStStages = 4;
+// Row streaming for the [P][C] tensors. A thread owns one 4-channel column (8-byte vectors) of a few rows, so the
+// per-channel constants of the fused BN + activation math cost 16-40 registers and three 256-thread blocks fit an SM.
+// Large tensors take the STAGED path: row tiles of ~20 KB are pulled through a shared-memory ring with cp.async.bulk
+// (the TMA engine; one elected thread issues, mbarrier completion), so ~180 KB per SM are in flight regardless of
+// register use, and the math reads its operands from shared memory. body(xs, ds, ri, rg): xs/ds = row-major tiles,
+// ri = row inside them, rg = row of the whole tensor (for the outputs).
+constexpr int kBnW = 4;                       // channels per thread
+constexpr float kNegLog2e = -1.4426950408889634f;
+__device__ __forceinline__ void unpack4(const uint2& v, float (&f)[4]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+}
+__device__ __forceinline__ uint2 pack4(const float (&f)[4]) {
+  return make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
+}
+// 1 / (1 + 2^t): the sigmoid of x when t = -x * log2(e) (the scale is folded into the per-channel constants)
+__device__ __forceinline__ float sigmoid_from_t(float t, float& e) {
+  e = exp2f(t);
+  return __fdividef(1.f, 1.f + e);
+}
+
+constexpr int kStMaxStages = 4;
 template <bool WITH_D, typename F>
-__device__ __forceinline__ void staged_rows(const uint4* __restrict__ x, const uint4* __restrict__ d, long long P,
-                                            int vc_in, int vc_out, int R, int rl, int rpb, F&& body) {
+__device__ __forceinline__ void staged_rows(const uint2* __restrict__ x, const uint2* __restrict__ d, long long P,
+                                            int vc_in, int vc_out, int R, int stages, int rl, int rpb, F&& body) {
   extern __shared__ __align__(128) uint8_t st_smem[];
-  __shared__ uint64_t st_full[kStStages];
-  const int xv = R * vc_in, dv = WITH_D ? R * vc_out : 0;   // uint4 vectors per stage
+  __shared__ uint64_t st_full[kStMaxStages];
+  const int xv = R * vc_in, dv = WITH_D ? R * vc_out : 0;   // uint2 vectors per stage
   const long long tiles = (P + R - 1) / R;
   const int lane_id = blockIdx.y, nl = gridDim.y;
   const long long my_tiles = lane_id < tiles ? (tiles - lane_id + nl - 1) / nl : 0;
-  uint4* ring = reinterpret_cast<uint4*>(st_smem);
+  uint2* ring = reinterpret_cast<uint2*>(st_smem);
   auto issue = [&](long long i) {
     const long long t = lane_id + i * nl;
-    const int s = (int)(i % kStStages);
+    const int s = (int)(i % stages);
     const long long r0 = t * R;
     const int rows = (int)((P - r0) < R ? (P - r0) : R);
-    uint4* sx = ring + (size_t)s * (xv + dv);
-    mbar_expect_tx(&st_full[s], (uint32_t)rows * (uint32_t)(vc_in + (WITH_D ? vc_out : 0)) * 16u);
-    bulk_g2s(sx, x + r0 * vc_in, (uint32_t)rows * vc_in * 16u, &st_full[s]);
-    if (WITH_D) bulk_g2s(sx + xv, d + r0 * vc_out, (uint32_t)rows * vc_out * 16u, &st_full[s]);
+    uint2* sx = ring + (size_t)s * (xv + dv);
+    mbar_expect_tx(&st_full[s], (uint32_t)rows * (uint32_t)(vc_in + (WITH_D ? vc_out : 0)) * 8u);
+    bulk_g2s(sx, x + r0 * vc_in, (uint32_t)rows * vc_in * 8u, &st_full[s]);
+    if (WITH_D) bulk_g2s(sx + xv, d + r0 * vc_out, (uint32_t)rows * vc_out * 8u, &st_full[s]);
   };
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStStages; ++s) mbar_init(&st_full[s], 1);
+    for (int s = 0; s < stages; ++s) mbar_init(&st_full[s], 1);
     fence_barrier_init();
-    for (long long i = 0; i < my_tiles && i < kStStages; ++i) issue(i);
+    for (long long i = 0; i < my_tiles && i < stages; ++i) issue(i);
   }
   __syncthreads();
+  int s = 0;
+  uint32_t phase = 0;
   for (long long i = 0; i < my_tiles; ++i) {
-    const int s = (int)(i % kStStages);
-    mbar_wait(&st_full[s], (uint32_t)((i / kStStages) & 1));
+    mbar_wait(&st_full[s], phase);
     const long long r0 = (lane_id + i * nl) * (long long)R;
     const int rows = (int)((P - r0) < R ? (P - r0) : R);
-    const uint4* sx = ring + (size_t)s * (xv + dv);
+    const uint2* sx = ring + (size_t)s * (xv + dv);
     for (int r = rl; r < rows; r += rpb) body(sx, sx + xv, (long long)r, r0 + r);
     __syncthreads();
-    if (threadIdx.x == 0 && i + kStStages < my_tiles) issue(i + kStStages);
+    if (threadIdx.x == 0 && i + stages < my_tiles) issue(i + stages);
+    if (++s == stages) { s = 0; phase ^= 1u; }
   }
 }
 
 // out = act(bn(x)) (+ residual).  GLU: out[:, c] = bn(x)[:, c] * sigmoid(bn(x)[:, c + C/2]), out has C/2 channels.
 template <int ACT, bool STAGED>
-__global__ void bn_act_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ mean,
-                                  const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                  const float* __restrict__ beta, const uint4* __restrict__ residual,
-                                  uint4* __restrict__ out, long long P, int vc_in, int vc_out, int cpb, int rpb,
-                                  int has_bn, const float* __restrict__ stats, float eps, float momentum,
-                                  float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                  float* __restrict__ rmean, float* __restrict__ rvar, long long* __restrict__ nbt,
-                                  int tile_rows) {
+__global__ void __launch_bounds__(256, 3)
+bn_act_fwd_kernel(const uint2* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, const uint2* __restrict__ residual,
+                  uint2* __restrict__ out, long long P, int vc_in, int vc_out, int cpb, int rpb, int has_bn,
+                  const float* __restrict__ stats, float eps, float momentum, float* __restrict__ mean_out,
+                  float* __restrict__ rstd_out, float* __restrict__ rmean, float* __restrict__ rvar,
+                  long long* __restrict__ nbt, int tile_rows, int stages) {
   // stats != NULL: train mode — mean/rstd are derived here from the sums the conv epilogue accumulated; the first
   // row-block also saves them for backward and updates the running statistics (momentum, unbiased variance).
   const int col = blockIdx.x * cpb + threadIdx.x % cpb;  // output vector column
   const int rl = threadIdx.x / cpb;
-  const int C = vc_in * 8;
+  const int C = vc_in * kBnW;
   // blockIdx.z = statistics group (rows [z * P, (z + 1) * P)): each group of the batch is normalised on its own
   // statistics, exactly like separate nn.BatchNorm calls on the group's samples (train_Dnet's real / wrong / fake passes).
   const int gz = blockIdx.z, ngroups = gridDim.z;
@@ -400,78 +415,80 @@ __global__ void bn_act_fwd_kernel(const uint4* __restrict__ x, const float* __re
     rmean[c] = rm;
     rvar[c] = rv;
   };
-  float sc0[8], sh0[8], sc1[8], sh1[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = col * 8 + j;
-    if (has_bn) {
-      float m, r, var = 0.f;
-      if (stats) stat_mean_rstd(stats, C, c, invP, eps, m, r, var); else { m = mean[c]; r = rstd[c]; }
-      if (writer) {
-        mean_out[c] = m; rstd_out[c] = r;
-        update_running(c);
-      }
-      sc0[j] = gamma[c] * r;
-      sh0[j] = beta[c] - m * sc0[j];
-    } else {
-      sc0[j] = 1.f; sh0[j] = 0.f;
+  // per-channel scale / shift of channel c; `t_scale` folds the sigmoid's -log2(e) into the gate half
+  auto scale_shift = [&](int c, float t_scale, float& sc, float& sh) {
+    if (!has_bn) { sc = t_scale; sh = 0.f; return; }
+    float m, r, var = 0.f;
+    if (stats) stat_mean_rstd(stats, C, c, invP, eps, m, r, var); else { m = mean[c]; r = rstd[c]; }
+    if (writer) {
+      mean_out[c] = m; rstd_out[c] = r;
+      update_running(c);
     }
+    const float s = gamma[c] * r;
+    sc = s * t_scale;
+    sh = (beta[c] - m * s) * t_scale;
+  };
+  float sc0[kBnW], sh0[kBnW], sc1[kBnW], sh1[kBnW];
+#pragma unroll
+  for (int j = 0; j < kBnW; ++j) {
+    float a, b;
+    scale_shift(col * kBnW + j, 1.f, a, b);
+    sc0[j] = a; sh0[j] = b;
     if (ACT == ACT_GLU) {
-      const int c2 = c + vc_out * 8;
-      float m, r, var = 0.f;
-      if (stats) stat_mean_rstd(stats, C, c2, invP, eps, m, r, var); else { m = mean[c2]; r = rstd[c2]; }
-      if (writer) {
-        mean_out[c2] = m; rstd_out[c2] = r;
-        update_running(c2);
-      }
-      sc1[j] = gamma[c2] * r;
-      sh1[j] = beta[c2] - m * sc1[j];
+      scale_shift(col * kBnW + j + vc_out * kBnW, kNegLog2e, a, b);
+      sc1[j] = a; sh1[j] = b;
     }
   }
-  auto body = [&](const uint4* xs, const uint4* /*ds*/, long long ri, long long r) {
-    float a[8], o[8];
-    unpack8(xs[ri * vc_in + col], a);
+  auto body = [&](const uint2* xs, const uint2* /*ds*/, long long ri, long long r) {
+    float a[kBnW], o[kBnW];
+    unpack4(xs[ri * vc_in + col], a);
     if (ACT == ACT_GLU) {
-      float g[8];
-      unpack8(xs[ri * vc_in + col + vc_out], g);
+      float g[kBnW];
+      unpack4(xs[ri * vc_in + col + vc_out], g);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (a[j] * sc0[j] + sh0[j]) * sigmoidf_(g[j] * sc1[j] + sh1[j]);
+      for (int j = 0; j < kBnW; ++j) {
+        float e;
+        o[j] = fmaf(a[j], sc0[j], sh0[j]) * sigmoid_from_t(fmaf(g[j], sc1[j], sh1[j]), e);
+      }
     } else if (ACT == ACT_LRELU) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float z = a[j] * sc0[j] + sh0[j]; o[j] = z > 0.f ? z : 0.2f * z; }
+      for (int j = 0; j < kBnW; ++j) { const float z = fmaf(a[j], sc0[j], sh0[j]); o[j] = z > 0.f ? z : 0.2f * z; }
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = a[j] * sc0[j] + sh0[j];
+      for (int j = 0; j < kBnW; ++j) o[j] = fmaf(a[j], sc0[j], sh0[j]);
       if (residual) {
-        float rr[8];
-        unpack8(residual[r * vc_out + col], rr);
+        float rr[kBnW];
+        unpack4(residual[r * vc_out + col], rr);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += rr[j];
+        for (int j = 0; j < kBnW; ++j) o[j] += rr[j];
       }
     }
-    out[r * vc_out + col] = pack8(o);
+    out[r * vc_out + col] = pack4(o);
   };
   if (STAGED) {
-    staged_rows<false>(x, nullptr, P, vc_in, vc_out, tile_rows, rl, rpb, body);
+    staged_rows<false>(x, nullptr, P, vc_in, vc_out, tile_rows, stages, rl, rpb, body);
   } else {
     for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += (long long)gridDim.y * rpb) body(x, nullptr, r, r);
   }
 }
 
-// dz = d(bn output) for one output vector column. Returns dz (and for GLU the gate half's dz in dz2), xhat's.
+// dz = d(loss)/d(bn output) of one vector column (GLU: dz0 of the value half, dz1 of the gate half).
+// sc0/sh0 = BN scale / shift of the value half; sc1/sh1 = those of the gate half times -log2(e).
 template <int ACT>
-__device__ __forceinline__ void bn_act_dz(const float (&a)[8], const float (&g)[8], const float (&d)[8],
-                                          const float (&sc0)[8], const float (&sh0)[8], const float (&sc1)[8],
-                                          const float (&sh1)[8], float (&dz0)[8], float (&dz1)[8]) {
+__device__ __forceinline__ void bn_act_dz(const float (&a)[kBnW], const float (&g)[kBnW], const float (&d)[kBnW],
+                                          const float (&sc0)[kBnW], const float (&sh0)[kBnW],
+                                          const float (&sc1)[kBnW], const float (&sh1)[kBnW], float (&dz0)[kBnW],
+                                          float (&dz1)[kBnW]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < kBnW; ++j) {
     if (ACT == ACT_GLU) {
-      const float za = a[j] * sc0[j] + sh0[j];
-      const float s = sigmoidf_(g[j] * sc1[j] + sh1[j]);
+      const float za = fmaf(a[j], sc0[j], sh0[j]);
+      float e;
+      const float s = sigmoid_from_t(fmaf(g[j], sc1[j], sh1[j]), e);
       dz0[j] = d[j] * s;
-      dz1[j] = d[j] * za * s * (1.f - s);
+      dz1[j] = dz0[j] * za * (e * s);          // 1 - s = e * s
     } else if (ACT == ACT_LRELU) {
-      const float z = a[j] * sc0[j] + sh0[j];
+      const float z = fmaf(a[j], sc0[j], sh0[j]);
       dz0[j] = z > 0.f ? d[j] : 0.2f * d[j];
     } else {
       dz0[j] = d[j];
@@ -479,13 +496,14 @@ __device__ __forceinline__ void bn_act_dz(const float (&a)[8], const float (&g)[
   }
 }
 
-// pass 1: sums[0][c] = sum dz, sums[1][c] = sum dz * xhat   (per input channel c, fp64 atomics)
+// pass 1: sums[0][c] = sum dz, sums[1][c] = sum dz * xhat   (per input channel c, fp64 atomics).
+// The loop accumulates S = sum dz and T = sum dz * x; sum dz * xhat = rstd * (T - mean * S) is formed in fp64 per block.
 template <int ACT, bool STAGED>
-__global__ void bn_act_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dout,
-                                         const float* __restrict__ mean, const float* __restrict__ rstd,
-                                         const float* __restrict__ gamma, const float* __restrict__ beta, long long P,
-                                         int vc_in, int vc_out, int cpb, int rpb, double* __restrict__ sums, int C,
-                                         int tile_rows) {
+__global__ void __launch_bounds__(256, 3)
+bn_act_bwd_reduce_kernel(const uint2* __restrict__ x, const uint2* __restrict__ dout, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, long long P, int vc_in, int vc_out, int cpb, int rpb,
+                         double* __restrict__ sums, int C, int tile_rows, int stages) {
   x += (long long)blockIdx.z * P * vc_in;       // blockIdx.z = statistics group (see bn_act_fwd_kernel)
   dout += (long long)blockIdx.z * P * vc_out;
   mean += (long long)blockIdx.z * C;
@@ -493,41 +511,43 @@ __global__ void bn_act_bwd_reduce_kernel(const uint4* __restrict__ x, const uint
   sums += (long long)blockIdx.z * 2 * C;
   const int col = blockIdx.x * cpb + threadIdx.x % cpb;
   const int rl = threadIdx.x / cpb;
-  float sc0[8], sh0[8], sc1[8], sh1[8], m0[8], r0[8], m1[8], r1[8];
+  float sc0[kBnW], sh0[kBnW], sc1[kBnW], sh1[kBnW];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = col * 8 + j;
-    m0[j] = mean[c]; r0[j] = rstd[c];
-    sc0[j] = gamma[c] * r0[j]; sh0[j] = beta[c] - m0[j] * sc0[j];
+  for (int j = 0; j < kBnW; ++j) {
+    const int c = col * kBnW + j;
+    sc0[j] = gamma[c] * rstd[c]; sh0[j] = beta[c] - mean[c] * sc0[j];
     if (ACT == ACT_GLU) {
-      const int c2 = c + vc_out * 8;
-      m1[j] = mean[c2]; r1[j] = rstd[c2];
-      sc1[j] = gamma[c2] * r1[j]; sh1[j] = beta[c2] - m1[j] * sc1[j];
-    } else { m1[j] = r1[j] = sc1[j] = sh1[j] = 0.f; }
+      const int c2 = c + vc_out * kBnW;
+      const float s = gamma[c2] * rstd[c2];
+      sc1[j] = s * kNegLog2e; sh1[j] = (beta[c2] - mean[c2] * s) * kNegLog2e;
+    } else { sc1[j] = sh1[j] = 0.f; }
   }
-  float s0[8], t0[8], s1[8], t1[8];
+  float s0[kBnW], t0[kBnW], s1[kBnW], t1[kBnW];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s0[j] = t0[j] = s1[j] = t1[j] = 0.f;
-  auto body = [&](const uint4* xs, const uint4* ds, long long ri, long long /*r*/) {
-    float a[8], g[8], d[8], dz0[8], dz1[8];
-    unpack8(xs[ri * vc_in + col], a);
-    if (ACT == ACT_GLU) unpack8(xs[ri * vc_in + col + vc_out], g);
-    unpack8(ds[ri * vc_out + col], d);
+  for (int j = 0; j < kBnW; ++j) s0[j] = t0[j] = s1[j] = t1[j] = 0.f;
+  auto body = [&](const uint2* xs, const uint2* ds, long long ri, long long /*r*/) {
+    float a[kBnW], g[kBnW], d[kBnW], dz0[kBnW], dz1[kBnW];
+    unpack4(xs[ri * vc_in + col], a);
+    if (ACT == ACT_GLU) unpack4(xs[ri * vc_in + col + vc_out], g);
+    unpack4(ds[ri * vc_out + col], d);
     bn_act_dz<ACT>(a, g, d, sc0, sh0, sc1, sh1, dz0, dz1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s0[j] += dz0[j]; t0[j] += dz0[j] * (a[j] - m0[j]) * r0[j];
-      if (ACT == ACT_GLU) { s1[j] += dz1[j]; t1[j] += dz1[j] * (g[j] - m1[j]) * r1[j]; }
+    for (int j = 0; j < kBnW; ++j) {
+      s0[j] += dz0[j]; t0[j] = fmaf(dz0[j], a[j], t0[j]);
+      if (ACT == ACT_GLU) { s1[j] += dz1[j]; t1[j] = fmaf(dz1[j], g[j], t1[j]); }
     }
   };
   if (STAGED) {
-    staged_rows<true>(x, dout, P, vc_in, vc_out, tile_rows, rl, rpb, body);
+    staged_rows<true>(x, dout, P, vc_in, vc_out, tile_rows, stages, rl, rpb, body);
   } else {
     for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += (long long)gridDim.y * rpb) body(x, dout, r, r);
   }
-  __shared__ float sh[4][256][8];
+  // block reduction over the rpb row slots (the staged ring is idle by now: reuse it as the scratch)
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  __shared__ float sh_static[STAGED ? 1 : 4 * 256 * kBnW];
+  float (*sh)[256][kBnW] = reinterpret_cast<float (*)[256][kBnW]>(STAGED ? reinterpret_cast<float*>(st_smem) : sh_static);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < kBnW; ++j) {
     sh[0][threadIdx.x][j] = s0[j]; sh[1][threadIdx.x][j] = t0[j];
     if (ACT == ACT_GLU) { sh[2][threadIdx.x][j] = s1[j]; sh[3][threadIdx.x][j] = t1[j]; }
   }
@@ -535,32 +555,33 @@ __global__ void bn_act_bwd_reduce_kernel(const uint4* __restrict__ x, const uint
   if (rl == 0) {
     for (int k = 1; k < rpb; ++k)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < kBnW; ++j) {
         s0[j] += sh[0][threadIdx.x + k * cpb][j]; t0[j] += sh[1][threadIdx.x + k * cpb][j];
         if (ACT == ACT_GLU) { s1[j] += sh[2][threadIdx.x + k * cpb][j]; t1[j] += sh[3][threadIdx.x + k * cpb][j]; }
       }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = col * 8 + j;
+    for (int j = 0; j < kBnW; ++j) {
+      const int c = col * kBnW + j;
       atomicAdd(&sums[c], (double)s0[j]);
-      atomicAdd(&sums[C + c], (double)t0[j]);
+      atomicAdd(&sums[C + c], (double)rstd[c] * ((double)t0[j] - (double)mean[c] * (double)s0[j]));
       if (ACT == ACT_GLU) {
-        const int c2 = c + vc_out * 8;
+        const int c2 = c + vc_out * kBnW;
         atomicAdd(&sums[c2], (double)s1[j]);
-        atomicAdd(&sums[C + c2], (double)t1[j]);
+        atomicAdd(&sums[C + c2], (double)rstd[c2] * ((double)t1[j] - (double)mean[c2] * (double)s1[j]));
       }
     }
   }
 }
 
-// pass 2: dx = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat))
+// pass 2: dx = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat)) = sc * dz + nA * x + nB  with per-channel
+// nA = -sc * rstd * mean(dz * xhat), nB = -sc * mean(dz) - nA * mean.
 template <int ACT, bool STAGED>
-__global__ void bn_act_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dout,
-                                        const float* __restrict__ mean, const float* __restrict__ rstd,
-                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                        const double* __restrict__ sums, long long P, int vc_in, int vc_out, int cpb,
-                                        int rpb, uint4* __restrict__ dx, int C, float* __restrict__ dgamma,
-                                        float* __restrict__ dbeta, int accumulate, int tile_rows) {
+__global__ void __launch_bounds__(256, 3)
+bn_act_bwd_apply_kernel(const uint2* __restrict__ x, const uint2* __restrict__ dout, const float* __restrict__ mean,
+                        const float* __restrict__ rstd, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, const double* __restrict__ sums, long long P, int vc_in,
+                        int vc_out, int cpb, int rpb, uint2* __restrict__ dx, int C, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta, int accumulate, int tile_rows, int stages) {
   const int gz = blockIdx.z, ngroups = gridDim.z;   // statistics group (see bn_act_fwd_kernel)
   const double* sums_all = sums;
   x += (long long)gz * P * vc_in;
@@ -575,52 +596,51 @@ __global__ void bn_act_bwd_apply_kernel(const uint4* __restrict__ x, const uint4
   if (dgamma && gz == 0 && blockIdx.y == 0 && rl == 0) {   // dgamma = sum dz * xhat, dbeta = sum dz (over all groups)
     auto total = [&](int idx) {
       double t = 0.0;
+#pragma unroll 1
       for (int g = 0; g < ngroups; ++g) t += sums_all[(long long)g * 2 * C + idx];
       return (float)t;
     };
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = col * 8 + j;
+#pragma unroll 1
+    for (int j = 0; j < (ACT == ACT_GLU ? 2 * kBnW : kBnW); ++j) {
+      const int c = col * kBnW + (j % kBnW) + (j >= kBnW ? vc_out * kBnW : 0);
       const float db = total(c), dg = total(C + c);
       if (accumulate) { dgamma[c] += dg; dbeta[c] += db; } else { dgamma[c] = dg; dbeta[c] = db; }
-      if (ACT == ACT_GLU) {
-        const int c2 = c + vc_out * 8;
-        const float db2 = total(c2), dg2 = total(C + c2);
-        if (accumulate) { dgamma[c2] += dg2; dbeta[c2] += db2; } else { dgamma[c2] = dg2; dbeta[c2] = db2; }
-      }
     }
   }
-  float sc0[8], sh0[8], sc1[8], sh1[8], m0[8], r0[8], m1[8], r1[8], k0[8], k1[8], l0[8], l1[8];
+  float sc0[kBnW], sh0[kBnW], nA0[kBnW], nB0[kBnW], sc1[kBnW], sh1[kBnW], g1[kBnW], nA1[kBnW], nB1[kBnW];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = col * 8 + j;
-    m0[j] = mean[c]; r0[j] = rstd[c];
-    sc0[j] = gamma[c] * r0[j]; sh0[j] = beta[c] - m0[j] * sc0[j];
-    k0[j] = (float)sums[c] * invP; l0[j] = (float)sums[C + c] * invP;
+  for (int j = 0; j < kBnW; ++j) {
+    const int c = col * kBnW + j;
+    const float m = mean[c], r = rstd[c];
+    sc0[j] = gamma[c] * r; sh0[j] = beta[c] - m * sc0[j];
+    nA0[j] = -sc0[j] * r * ((float)sums[C + c] * invP);
+    nB0[j] = -sc0[j] * ((float)sums[c] * invP) - nA0[j] * m;
     if (ACT == ACT_GLU) {
-      const int c2 = c + vc_out * 8;
-      m1[j] = mean[c2]; r1[j] = rstd[c2];
-      sc1[j] = gamma[c2] * r1[j]; sh1[j] = beta[c2] - m1[j] * sc1[j];
-      k1[j] = (float)sums[c2] * invP; l1[j] = (float)sums[C + c2] * invP;
-    } else { m1[j] = r1[j] = sc1[j] = sh1[j] = k1[j] = l1[j] = 0.f; }
+      const int c2 = c + vc_out * kBnW;
+      const float m2 = mean[c2], r2 = rstd[c2];
+      g1[j] = gamma[c2] * r2;
+      sc1[j] = g1[j] * kNegLog2e; sh1[j] = (beta[c2] - m2 * g1[j]) * kNegLog2e;
+      nA1[j] = -g1[j] * r2 * ((float)sums[C + c2] * invP);
+      nB1[j] = -g1[j] * ((float)sums[c2] * invP) - nA1[j] * m2;
+    } else { sc1[j] = sh1[j] = g1[j] = nA1[j] = nB1[j] = 0.f; }
   }
-  auto body = [&](const uint4* xs, const uint4* ds, long long ri, long long r) {
-    float a[8], g[8], d[8], dz0[8], dz1[8], o[8];
-    unpack8(xs[ri * vc_in + col], a);
-    if (ACT == ACT_GLU) unpack8(xs[ri * vc_in + col + vc_out], g);
-    unpack8(ds[ri * vc_out + col], d);
+  auto body = [&](const uint2* xs, const uint2* ds, long long ri, long long r) {
+    float a[kBnW], g[kBnW], d[kBnW], dz0[kBnW], dz1[kBnW], o[kBnW];
+    unpack4(xs[ri * vc_in + col], a);
+    if (ACT == ACT_GLU) unpack4(xs[ri * vc_in + col + vc_out], g);
+    unpack4(ds[ri * vc_out + col], d);
     bn_act_dz<ACT>(a, g, d, sc0, sh0, sc1, sh1, dz0, dz1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = sc0[j] * (dz0[j] - k0[j] - (a[j] - m0[j]) * r0[j] * l0[j]);
-    dx[r * vc_in + col] = pack8(o);
+    for (int j = 0; j < kBnW; ++j) o[j] = fmaf(sc0[j], dz0[j], fmaf(nA0[j], a[j], nB0[j]));
+    dx[r * vc_in + col] = pack4(o);
     if (ACT == ACT_GLU) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = sc1[j] * (dz1[j] - k1[j] - (g[j] - m1[j]) * r1[j] * l1[j]);
-      dx[r * vc_in + col + vc_out] = pack8(o);
+      for (int j = 0; j < kBnW; ++j) o[j] = fmaf(g1[j], dz1[j], fmaf(nA1[j], g[j], nB1[j]));
+      dx[r * vc_in + col + vc_out] = pack4(o);
     }
   };
   if (STAGED) {
-    staged_rows<true>(x, dout, P, vc_in, vc_out, tile_rows, rl, rpb, body);
+    staged_rows<true>(x, dout, P, vc_in, vc_out, tile_rows, stages, rl, rpb, body);
   } else {
     for (long long r = (long long)blockIdx.y * rpb + rl; r < P; r += (long long)gridDim.y * rpb) body(x, dout, r, r);
   }
@@ -868,26 +888,35 @@ static inline unsigned grid1d(long long n, int threads = 256) {
 
 using namespace sg2;
 
-// Staged (cp.async.bulk) geometry for a [P][C] tensor: one block spans all columns; ~16 KB row tiles.
+// Staged (cp.async.bulk) geometry for a [P][C] tensor: one block spans all columns; row tiles of ~tile_kb KB
+// (x rows + dout rows), `stages` of them in flight per block, `blocks` blocks per SM.
 struct StagedGeo {
   bool ok;
-  int tile_rows;
+  int tile_rows, stages;
   unsigned lanes;
   size_t smem;
 };
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 static StagedGeo make_staged(const Geo& g, long long P, int vc_in, int vc_out, bool with_d) {
-  StagedGeo sg{false, 0, 0, 0};
-  static int on = [] {
-    const char* e = getenv("SG2_BN_STAGED");
-    return e ? atoi(e) : 1;
-  }();
-  if (!on || g.grid.x != 1 || P * vc_in * 16 < (4LL << 20)) return sg;   // small tensors are latency bound anyway
-  int k = 16384 / (g.rpb * vc_in * 16);
+  StagedGeo sg{false, 0, 0, 0, 0};
+  static const int on = env_int("SG2_BN_STAGED", 1);
+  static const int tile_kb = env_int("SG2_BN_TILE_KB", 20);
+  static const int stages = env_int("SG2_BN_STAGES", 3);
+  static const int blocks = env_int("SG2_BN_BLOCKS", 3);
+  const long long row_bytes = (long long)(vc_in + (with_d ? vc_out : 0)) * 8;
+  if (!on || g.grid.x != 1 || P * vc_in * 8 < (4LL << 20)) return sg;   // small tensors are latency bound anyway
+  int k = (int)((long long)tile_kb * 1024 / (g.rpb * row_bytes));
   if (k < 1) k = 1;
   sg.tile_rows = g.rpb * k;
+  sg.stages = stages < 2 ? 2 : (stages > kStMaxStages ? kStMaxStages : stages);
   const long long tiles = (P + sg.tile_rows - 1) / sg.tile_rows;
-  sg.lanes = (unsigned)(tiles < 296 ? tiles : 296);
-  sg.smem = (size_t)kStStages * sg.tile_rows * (vc_in + (with_d ? vc_out : 0)) * 16 + 128;
+  const long long want = 148LL * blocks;
+  sg.lanes = (unsigned)(tiles < want ? tiles : want);
+  sg.smem = (size_t)sg.stages * sg.tile_rows * row_bytes + 128;
+  if (sg.smem < 17 * 1024) sg.smem = 17 * 1024;   // the backward reduce reuses the ring as its 16 KB block scratch
   sg.ok = sg.smem <= 100 * 1024;
   return sg;
 }
@@ -971,12 +1000,12 @@ int sg2_bn_act_fwd(const void* x, const float* stats, float* mean, float* rstd, 
   if (Cout % 8) EW_FAIL(SG2_EINVAL, "bn_act_fwd: channels %% 8");
   if (groups < 1 || P % groups) EW_FAIL(SG2_EINVAL, "bn_act_fwd: %lld rows in %d groups", P, groups);
   P /= groups;
-  Geo g = make_geo(P, Cout, 148 * 4);
+  Geo g = make_geo(P, Cout, 148 * 6, kBnW);
   g.grid.z = groups;
   const int has_bn = (mean != nullptr);
   if (stats && !mean) EW_FAIL(SG2_EINVAL, "bn_act_fwd: stats given without mean/rstd outputs");
   cudaStream_t st = (cudaStream_t)stream;
-  const StagedGeo sg = make_staged(g, P, C / 8, Cout / 8, false);
+  const StagedGeo sg = make_staged(g, P, C / kBnW, Cout / kBnW, false);
   static bool attr = false;
   if (!attr) {
     staged_attr(bn_act_fwd_kernel<ACT_GLU, true>);
@@ -984,7 +1013,7 @@ int sg2_bn_act_fwd(const void* x, const float* stats, float* mean, float* rstd, 
     staged_attr(bn_act_fwd_kernel<ACT_NONE, true>);
     attr = true;
   }
-#define ARGS (const uint4*)x, mean, rstd, gamma, beta, (const uint4*)residual, (uint4*)out, P, C / 8, Cout / 8, g.cpb, g.rpb, has_bn, stats, eps, momentum, mean, rstd, running_mean, running_var, num_batches_tracked, sg.tile_rows
+#define ARGS (const uint2*)x, mean, rstd, gamma, beta, (const uint2*)residual, (uint2*)out, P, C / kBnW, Cout / kBnW, g.cpb, g.rpb, has_bn, stats, eps, momentum, mean, rstd, running_mean, running_var, num_batches_tracked, sg.tile_rows, sg.stages
   if (sg.ok) {
     dim3 grid(1, sg.lanes, groups);
     if (act == ACT_GLU) bn_act_fwd_kernel<ACT_GLU, true><<<grid, g.block, sg.smem, st>>>(ARGS);
@@ -1006,10 +1035,10 @@ int sg2_bn_act_bwd(const void* x, const void* dout, const float* mean, const flo
   if (Cout % 8) EW_FAIL(SG2_EINVAL, "bn_act_bwd: channels %% 8");
   if (groups < 1 || P % groups) EW_FAIL(SG2_EINVAL, "bn_act_bwd: %lld rows in %d groups", P, groups);
   P /= groups;
-  Geo g = make_geo(P, Cout, 148 * 4);
+  Geo g = make_geo(P, Cout, 148 * 6, kBnW);
   g.grid.z = groups;
   cudaStream_t st = (cudaStream_t)stream;
-  const StagedGeo sg = make_staged(g, P, C / 8, Cout / 8, true);
+  const StagedGeo sg = make_staged(g, P, C / kBnW, Cout / kBnW, true);
   static bool attr = false;
   if (!attr) {
     staged_attr(bn_act_bwd_reduce_kernel<ACT_GLU, true>);
@@ -1020,8 +1049,8 @@ int sg2_bn_act_bwd(const void* x, const void* dout, const float* mean, const flo
     staged_attr(bn_act_bwd_apply_kernel<ACT_NONE, true>);
     attr = true;
   }
-#define RARGS (const uint4*)x, (const uint4*)dout, mean, rstd, gamma, beta, P, C / 8, Cout / 8, g.cpb, g.rpb, sums, C, sg.tile_rows
-#define AARGS (const uint4*)x, (const uint4*)dout, mean, rstd, gamma, beta, sums, P, C / 8, Cout / 8, g.cpb, g.rpb, (uint4*)dx, C, dgamma, dbeta, accumulate, sg.tile_rows
+#define RARGS (const uint2*)x, (const uint2*)dout, mean, rstd, gamma, beta, P, C / kBnW, Cout / kBnW, g.cpb, g.rpb, sums, C, sg.tile_rows, sg.stages
+#define AARGS (const uint2*)x, (const uint2*)dout, mean, rstd, gamma, beta, sums, P, C / kBnW, Cout / kBnW, g.cpb, g.rpb, (uint2*)dx, C, dgamma, dbeta, accumulate, sg.tile_rows, sg.stages
 #define SG2_BWD(ACT_)                                                                       \
   if (sg.ok) {                                                                              \
     dim3 grid(1, sg.lanes, groups);                                                         \

@@ -11,8 +11,8 @@ for row in csv.DictReader(lines):
         rows.append((int(row["ID"]), re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", ""), v, row.get("Grid Size")))
 # step boundary: ca_glu_reparam_fwd runs once per step, a handful of launches (arena fills, CA_NET fc) after its start
 marks = [i for i, r in enumerate(rows) if "ca_glu_reparam_fwd_kernel" in r[1]]
-if len(marks) >= 2:
-    it = rows[max(marks[-2], marks[-1] - 6) if False else marks[-1] - 6:]
+if len(marks) >= 2:   # the last COMPLETE step: between the last two markers
+    it = rows[marks[-2] - 6:marks[-1] - 6]
 else:
     per = len(rows) // nsteps
     it = rows[-per:]
