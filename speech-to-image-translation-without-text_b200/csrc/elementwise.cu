@@ -900,29 +900,36 @@ static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
-static StagedGeo make_staged(const Geo& g, long long P, int vc_in, int vc_out, bool with_d) {
+static StagedGeo make_staged(const Geo& g, long long P, int groups, int vc_in, int vc_out, bool with_d) {
   StagedGeo sg{false, 0, 0, 0, 0};
   static const int on = env_int("SG2_BN_STAGED", 1);
-  static const int tile_kb = env_int("SG2_BN_TILE_KB", 20);
-  static const int stages = env_int("SG2_BN_STAGES", 3);
-  static const int blocks = env_int("SG2_BN_BLOCKS", 3);
+  static const int env_tile_kb = env_int("SG2_BN_TILE_KB", 0);
+  static const int env_stages = env_int("SG2_BN_STAGES", 0);
+  static const int env_blocks = env_int("SG2_BN_BLOCKS", 0);
   const long long row_bytes = (long long)(vc_in + (with_d ? vc_out : 0)) * 8;
-  if (!on || g.grid.x != 1 || P * vc_in * 8 < (4LL << 20)) return sg;   // small tensors are latency bound anyway
+  const long long x_bytes = P * groups * vc_in * 8;
+  if (!on || g.grid.x != 1 || x_bytes < (4LL << 20)) return sg;   // small tensors are latency bound anyway
+  // measured (tools/bench_bn.py): two blocks per SM with two 44 KB stages for the big tensors; the backward pair on
+  // tensors under 32 MB does better with one block per SM (half as many fp64 atomics at the end of the reduce pass)
+  const int blocks = env_blocks ? env_blocks : ((with_d && x_bytes < (32LL << 20)) ? 1 : 2);
+  const int tile_kb = env_tile_kb ? env_tile_kb : (blocks >= 2 ? 44 : 60);
+  const int stages = env_stages ? env_stages : (blocks >= 2 ? 2 : 3);
   int k = (int)((long long)tile_kb * 1024 / (g.rpb * row_bytes));
   if (k < 1) k = 1;
   sg.tile_rows = g.rpb * k;
   sg.stages = stages < 2 ? 2 : (stages > kStMaxStages ? kStMaxStages : stages);
   const long long tiles = (P + sg.tile_rows - 1) / sg.tile_rows;
-  const long long want = 148LL * blocks;
+  long long want = 148LL * blocks / groups;       // blockIdx.z = groups multiplies the grid
+  if (want < 1) want = 1;
   sg.lanes = (unsigned)(tiles < want ? tiles : want);
   sg.smem = (size_t)sg.stages * sg.tile_rows * row_bytes + 128;
   if (sg.smem < 17 * 1024) sg.smem = 17 * 1024;   // the backward reduce reuses the ring as its 16 KB block scratch
-  sg.ok = sg.smem <= 100 * 1024;
+  sg.ok = sg.smem <= (size_t)(blocks >= 2 ? 220 / blocks : 200) * 1024;
   return sg;
 }
 template <typename K>
 static void staged_attr(K kernel) {
-  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 extern "C" {
@@ -1005,7 +1012,7 @@ int sg2_bn_act_fwd(const void* x, const float* stats, float* mean, float* rstd, 
   const int has_bn = (mean != nullptr);
   if (stats && !mean) EW_FAIL(SG2_EINVAL, "bn_act_fwd: stats given without mean/rstd outputs");
   cudaStream_t st = (cudaStream_t)stream;
-  const StagedGeo sg = make_staged(g, P, C / kBnW, Cout / kBnW, false);
+  const StagedGeo sg = make_staged(g, P, groups, C / kBnW, Cout / kBnW, false);
   static bool attr = false;
   if (!attr) {
     staged_attr(bn_act_fwd_kernel<ACT_GLU, true>);
@@ -1038,7 +1045,7 @@ int sg2_bn_act_bwd(const void* x, const void* dout, const float* mean, const flo
   Geo g = make_geo(P, Cout, 148 * 6, kBnW);
   g.grid.z = groups;
   cudaStream_t st = (cudaStream_t)stream;
-  const StagedGeo sg = make_staged(g, P, C / kBnW, Cout / kBnW, true);
+  const StagedGeo sg = make_staged(g, P, groups, C / kBnW, Cout / kBnW, true);
   static bool attr = false;
   if (!attr) {
     staged_attr(bn_act_bwd_reduce_kernel<ACT_GLU, true>);
