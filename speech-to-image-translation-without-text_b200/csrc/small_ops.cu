@@ -246,14 +246,23 @@ __global__ void chw_to_hwc_bf16_kernel(const __nv_bfloat16* __restrict__ in, __n
 
 // ------------------------------------------------------------------------------------------ D logits
 // prob[b] = sigmoid(bias + sum_{p,c} x[b][p][c] * w[c][p]),  x NHWC bf16 [B][HW=16][C], w fp32 OIHW [1][C][4][4]
+// Each thread moves 8-channel (16-byte) vectors of x; w[c][p] of those channels comes through L1 (32 KB in all).
+__device__ __forceinline__ void lg_unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
 __global__ void logits_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                   const float* __restrict__ bias, float* __restrict__ prob, int HW, int C) {
   const int b = blockIdx.x;
-  const int n = HW * C;
+  const int n = HW * C, nv = n >> 3;
+  const uint4* xv = reinterpret_cast<const uint4*>(x + (long long)b * n);
   float acc = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int c = i % C, p = i / C;
-    acc += __bfloat162float(x[(long long)b * n + i]) * w[c * HW + p];
+  for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+    const int i = v << 3, p = i / C, c = i - p * C;
+    float f[8];
+    lg_unpack8(xv[v], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(f[j], w[(c + j) * HW + p], acc);
   }
   __shared__ float sh[32];
   acc = warp_sum(acc);
@@ -266,32 +275,47 @@ __global__ void logits_fwd_kernel(const __nv_bfloat16* __restrict__ x, const flo
   }
 }
 // dpre[b] = dprob[b] * p (1-p);  dx[b][p][c] (=|+=) dpre[b] * w[c][p];  dw[c][p] += sum_b dpre[b] x[b][p][c];  dbias += sum dpre
+// grid (vectors / 256, sample chunks of kLgChunk): a thread owns one 8-channel vector position for its chunk of samples.
+constexpr int kLgChunk = 8;
 __global__ void logits_bwd_kernel(const float* __restrict__ dprob, const float* __restrict__ prob,
                                   const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                   __nv_bfloat16* __restrict__ dx, int dx_accumulate, float* __restrict__ dw,
                                   float* __restrict__ dbias, int B, int HW, int C) {
-  const int n = HW * C;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int c = i % C, p = i / C;
-    const float wv = w[c * HW + p];
-    float gw = 0.f;
-    for (int b = 0; b < B; ++b) {
-      const float pr = prob[b];
-      const float dpre = dprob[b] * pr * (1.f - pr);
-      const long long o = (long long)b * n + i;
-      gw += dpre * __bfloat162float(x[o]);
-      if (dx) {
-        float v = dpre * wv;
-        if (dx_accumulate) v += __bfloat162float(dx[o]);
-        dx[o] = __float2bfloat16_rn(v);
-      }
-    }
-    if (dw) dw[c * HW + p] += gw;
-  }
-  if (dbias && blockIdx.x == 0 && threadIdx.x == 0) {
+  const int n = HW * C, nv = n >> 3;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b0 = blockIdx.y * kLgChunk, b1 = min(B, b0 + kLgChunk);
+  if (dbias && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     float s = 0.f;
     for (int b = 0; b < B; ++b) { const float pr = prob[b]; s += dprob[b] * pr * (1.f - pr); }
     dbias[0] += s;
+  }
+  if (v >= nv) return;
+  const int i = v << 3, p = i / C, c = i - p * C;
+  float wv[8], gw[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { wv[j] = w[(c + j) * HW + p]; gw[j] = 0.f; }
+  for (int b = b0; b < b1; ++b) {
+    const float pr = prob[b];
+    const float dpre = dprob[b] * pr * (1.f - pr);
+    const long long o = ((long long)b * n >> 3) + v;
+    float f[8];
+    lg_unpack8(reinterpret_cast<const uint4*>(x)[o], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gw[j] = fmaf(dpre, f[j], gw[j]);
+    if (dx) {
+      float d[8];
+      if (dx_accumulate) lg_unpack8(reinterpret_cast<const uint4*>(dx)[o], d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = dx_accumulate ? fmaf(dpre, wv[j], d[j]) : dpre * wv[j];
+      uint4 q;
+      q.x = pack_bf16x2(d[0], d[1]); q.y = pack_bf16x2(d[2], d[3]);
+      q.z = pack_bf16x2(d[4], d[5]); q.w = pack_bf16x2(d[6], d[7]);
+      reinterpret_cast<uint4*>(dx)[o] = q;
+    }
+  }
+  if (dw) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&dw[(c + j) * HW + p], gw[j]);
   }
 }
 
@@ -304,23 +328,61 @@ __global__ void adam_tick_kernel(int* __restrict__ step, float* __restrict__ bc,
   bc[0] = 1.f - powf(b1, (float)t);
   bc[1] = sqrtf(1.f - powf(b2, (float)t));
 }
-__global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                float* __restrict__ v, float* __restrict__ avg, long long n, float lr, float b1,
-                                float b2, float eps, const float* __restrict__ bc, float ema_decay,
-                                __nv_bfloat16* __restrict__ p_bf16) {
-  const float bc1 = bc[0], bc2_sqrt = bc[1];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i];
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    const float pi = p[i] - (lr / bc1) * (mi / denom);
-    p[i] = pi;
+__device__ __forceinline__ float adam_one(float pi, float gi, float& mi, float& vi, float b1, float b2, float eps,
+                                          float step, float inv_bc2_sqrt) {
+  mi = b1 * mi + (1.f - b1) * gi;
+  vi = b2 * vi + (1.f - b2) * gi * gi;
+  const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
+  return pi - step * (mi / denom);
+}
+// One Adam step (+ EMA of the parameters, + bf16 mirror) over a flat slice. The slice may start at any element of
+// the flat buckets: a scalar head brings every array to a 16-byte boundary (they all share the slice offset), the
+// body moves float4 vectors, a scalar tail finishes.
+__global__ void __launch_bounds__(256)
+adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                float* __restrict__ avg, long long n, float lr, float b1, float b2, float eps,
+                const float* __restrict__ bc, float ema_decay, __nv_bfloat16* __restrict__ p_bf16, int head) {
+  const float step = lr / bc[0], inv_bc2_sqrt = 1.f / bc[1];
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  auto scalar = [&](long long i) {
+    float mi = m[i], vi = v[i];
+    const float pi = adam_one(p[i], g[i], mi, vi, b1, b2, eps, step, inv_bc2_sqrt);
+    m[i] = mi; v[i] = vi; p[i] = pi;
     if (p_bf16) p_bf16[i] = __float2bfloat16_rn(pi);   // bf16 mirror = the conv operand pack of OHWI-stored weights
     if (avg) avg[i] = ema_decay * avg[i] + (1.f - ema_decay) * pi;
+  };
+  if (head < 0) {                                      // arrays not mutually aligned: all scalar
+    for (long long i = tid; i < n; i += nthreads) scalar(i);
+    return;
+  }
+  const long long h = head < n ? head : n;
+  const long long n4 = (n - h) >> 2;
+  if (tid < h) scalar(tid);
+  const long long tail0 = h + (n4 << 2);
+  if (tid < n - tail0) scalar(tail0 + tid);
+  float4* p4 = reinterpret_cast<float4*>(p + h);
+  const float4* g4 = reinterpret_cast<const float4*>(g + h);
+  float4* m4 = reinterpret_cast<float4*>(m + h);
+  float4* v4 = reinterpret_cast<float4*>(v + h);
+  float4* a4 = avg ? reinterpret_cast<float4*>(avg + h) : nullptr;
+  uint2* q4 = p_bf16 ? reinterpret_cast<uint2*>(p_bf16 + h) : nullptr;
+  for (long long i = tid; i < n4; i += nthreads) {
+    const float4 gi = g4[i], pi = p4[i];
+    float4 mi = m4[i], vi = v4[i], po;
+    po.x = adam_one(pi.x, gi.x, mi.x, vi.x, b1, b2, eps, step, inv_bc2_sqrt);
+    po.y = adam_one(pi.y, gi.y, mi.y, vi.y, b1, b2, eps, step, inv_bc2_sqrt);
+    po.z = adam_one(pi.z, gi.z, mi.z, vi.z, b1, b2, eps, step, inv_bc2_sqrt);
+    po.w = adam_one(pi.w, gi.w, mi.w, vi.w, b1, b2, eps, step, inv_bc2_sqrt);
+    m4[i] = mi; v4[i] = vi; p4[i] = po;
+    if (q4) q4[i] = make_uint2(pack_bf16x2(po.x, po.y), pack_bf16x2(po.z, po.w));
+    if (a4) {
+      float4 ai = a4[i];
+      const float w = 1.f - ema_decay;
+      ai.x = ema_decay * ai.x + w * po.x; ai.y = ema_decay * ai.y + w * po.y;
+      ai.z = ema_decay * ai.z + w * po.z; ai.w = ema_decay * ai.w + w * po.w;
+      a4[i] = ai;
+    }
   }
 }
 
@@ -521,14 +583,16 @@ int sg2_chw_hwc_bf16(const void* in, void* out, int B, int C, int HW, int to_hwc
 
 int sg2_logits_fwd(const void* x, const float* w, const float* bias, float* prob, int B, int HW, int C,
                    void* stream) {
+  if (C % 8) SG2_FAIL(SG2_EINVAL, "logits_fwd: C=%d not a multiple of 8", C);
   logits_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w, bias, prob, HW, C);
   SG2_LAUNCH_OK("logits_fwd");
 }
 
 int sg2_logits_bwd(const float* dprob, const float* prob, const void* x, const float* w, void* dx, int dx_accumulate,
                    float* dw, float* dbias, int B, int HW, int C, void* stream) {
-  const int n = HW * C;
-  logits_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+  if (C % 8) SG2_FAIL(SG2_EINVAL, "logits_bwd: C=%d not a multiple of 8", C);
+  const int nv = HW * C / 8;
+  logits_bwd_kernel<<<dim3((nv + 127) / 128, (B + kLgChunk - 1) / kLgChunk), 128, 0, (cudaStream_t)stream>>>(
       dprob, prob, (const __nv_bfloat16*)x, w, (__nv_bfloat16*)dx, dx_accumulate, dw, dbias, B, HW, C);
   SG2_LAUNCH_OK("logits_bwd");
 }
@@ -562,8 +626,15 @@ int sg2_adam_tick(int* step, float* bc, float beta1, float beta2, void* stream) 
 
 int sg2_adam_ema(float* p, const float* g, float* m, float* v, float* avg, long long n, float lr, float beta1,
                  float beta2, float eps, const float* bc, float ema_decay, void* p_bf16, void* stream) {
-  adam_ema_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, avg, n, lr, beta1, beta2, eps, bc,
-                                                              ema_decay, (__nv_bfloat16*)p_bf16);
+  // elements to the next 16-byte boundary; every array must agree (they are slices of identically laid out buckets)
+  auto mis = [](const void* q, int elem) { return (int)(((uintptr_t)q / elem) & 3); };
+  int head = (4 - mis(p, 4)) & 3;
+  const bool aligned = ((uintptr_t)p % 4 == 0) && mis(g, 4) == mis(p, 4) && mis(m, 4) == mis(p, 4) &&
+                       mis(v, 4) == mis(p, 4) && (!avg || mis(avg, 4) == mis(p, 4)) &&
+                       (!p_bf16 || ((uintptr_t)p_bf16 % 2 == 0 && mis(p_bf16, 2) == mis(p, 4)));
+  if (!aligned) head = -1;
+  adam_ema_kernel<<<grid1d((n + 3) / 4 + 8), 256, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, avg, n, lr, beta1, beta2, eps, bc, ema_decay, (__nv_bfloat16*)p_bf16, head);
   SG2_LAUNCH_OK("adam_ema");
 }
 
