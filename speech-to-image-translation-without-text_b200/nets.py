@@ -414,8 +414,9 @@ class StemBlock:
         self.op = ConvOperand(STEM, conv.weight, cin_pad=64)
 
     def fwd(self, img, col=None):
-        """col: optional precomputed im2col rows of `img` (the G step reuses the fake third of the D update's)."""
-        B, _, S, _ = img.shape
+        """col: optional precomputed im2col rows of `img` (the G step reuses the fake third of the D update's); `img`
+        may then be just the (B, S) pair."""
+        B, S = img if isinstance(img, tuple) else (img.shape[0], img.shape[2])
         if col is None:
             col = ops.stem_im2col(img)
         wpk, _ = self.op.packs()

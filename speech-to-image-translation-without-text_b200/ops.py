@@ -344,11 +344,16 @@ def head_tanh_bwd(dimg, img, CP):
     return dy
 
 
-def stem_im2col(img):
+def stem_im2col(img, out=None):
+    """(B,3,S,S) fp32 -> im2col rows (1,1,B*(S/2)^2,64) bf16 of the 4x4 s2 stem; `out`: a contiguous slice to fill."""
     B, _, S, _ = img.shape
-    col = torch.empty((1, 1, B * (S // 2) * (S // 2), 64), device=img.device, dtype=torch.bfloat16)
-    _call("sg2_stem_im2col", 1, _p(img), _p(col), B, S, _st())
-    return col
+    rows = B * (S // 2) * (S // 2)
+    if out is None:
+        out = torch.empty((1, 1, rows, 64), device=img.device, dtype=torch.bfloat16)
+    elif out.numel() != rows * 64 or not out.is_contiguous() or out.dtype != torch.bfloat16:
+        raise RuntimeError("sg2b200: stem_im2col: bad output slice")
+    _call("sg2_stem_im2col", 1, _p(img), _p(out), B, S, _st())
+    return out
 
 
 def stem_col2im(dcol, B, S):

@@ -235,6 +235,21 @@ class FusedTrainer:
         parts = torch.zeros(2 * nD, device=self.dev, dtype=torch.float32)    # per-D errG and cal (summed after the join)
         if eps is None:
             eps = torch.empty(B, self.G.E, device=self.dev, dtype=torch.float32).normal_()   # model.py:190-193
+        # Batched D update: the stem's im2col rows of real | wrong | fake live in one buffer per D; the real and wrong
+        # thirds do not depend on G, so each D stream fills them while the G forward runs on the main stream.
+        col3 = [None] * nD
+        if self.batched_d:
+            fork0 = torch.cuda.Event()
+            fork0.record(main)
+            for i in range(nD):
+                st = streams[i]
+                with torch.cuda.stream(st):
+                    if st is not main:
+                        st.wait_event(fork0)
+                    S = real[i].shape[2]
+                    col3[i] = torch.empty((3, B * (S // 2) * (S // 2), 64), device=self.dev, dtype=torch.bfloat16)
+                    ops.stem_im2col(real[i], out=col3[i][0])
+                    ops.stem_im2col(wrong[i], out=col3[i][1])
         fake, mu, logvar, Tg = self.G.forward(z, emb, eps, True)                             # trainer.py:544
         dmu = torch.empty_like(mu)
         dlogvar = torch.empty_like(logvar)
@@ -261,9 +276,10 @@ class FusedTrainer:
                     # real | wrong | fake in ONE pass of 3B samples with per-sub-batch BatchNorm statistics: the same
                     # arithmetic as the reference's three passes (trainer.py:390-392), a third of the launches, and
                     # three times the GEMM rows for D's latency- and weight-bound layers.
-                    imgs3 = torch.cat((real[i], wrong[i], fake[i]), 0)
+                    ops.stem_im2col(fake[i], out=col3[i][2])
                     probs = torch.empty(2, 3 * B, device=self.dev, dtype=torch.float32)
-                    _, _, _, T3 = D.forward(imgs3, mu3, True, probs[0], probs[1], groups=3)
+                    _, _, _, T3 = D.forward((3 * B, fake[i].shape[2]), mu3, True, probs[0], probs[1], groups=3,
+                                            stem_col=col3[i].view(1, 1, -1, 64))
                     # rows of probs.view(6, B): cond(real, wrong, fake), uncond(real, wrong, fake)
                     # targets: real -> 1,1 ; wrong -> cond 0, uncond 1 (trainer.py:400-401) ; fake -> 0,0
                     dprobs = self._bce(probs.view(6, B), (1, 0, 0, 1, 1, 0), (1, 1, 1, u, u, u), self.losses[i:i + 1])
