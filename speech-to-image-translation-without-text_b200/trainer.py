@@ -214,8 +214,13 @@ class FusedTrainer:
     # ------------------------------------------------------------------ the step
     def _streams(self):
         if getattr(self, "_sD", None) is None:
-            self._sD = [torch.cuda.Stream(device=self.dev) for _ in self.Ds]
-            self._sW = [torch.cuda.Stream(device=self.dev) for _ in range(len(self.Ds) + 1)]   # wgrad side streams
+            # the largest discriminator's update + G-step part is the longest branch of the step: its streams get the
+            # higher priority so that its kernels are not queued behind the smaller discriminators' (SG2_PRIO=0: off)
+            n = len(self.Ds)
+            hi = -1 if os.environ.get("SG2_PRIO", "1") != "0" else 0
+            prio = [hi if i == n - 1 and n > 1 else 0 for i in range(n)]
+            self._sD = [torch.cuda.Stream(device=self.dev, priority=prio[i]) for i in range(n)]
+            self._sW = [torch.cuda.Stream(device=self.dev, priority=(prio + [0])[i]) for i in range(n + 1)]  # wgrad side
         return self._sD
 
     def step(self, z, emb, real, wrong, labels, eps=None):
@@ -235,21 +240,30 @@ class FusedTrainer:
         parts = torch.zeros(2 * nD, device=self.dev, dtype=torch.float32)    # per-D errG and cal (summed after the join)
         if eps is None:
             eps = torch.empty(B, self.G.E, device=self.dev, dtype=torch.float32).normal_()   # model.py:190-193
-        # Batched D update: the stem's im2col rows of real | wrong | fake live in one buffer per D; the real and wrong
-        # thirds do not depend on G, so each D stream fills them while the G forward runs on the main stream.
+        # Work that does not depend on G runs on the D / side streams while the G forward occupies the main stream:
+        # clearing the flat gradient buckets (conv weight gradients accumulate straight into them) and, for the batched
+        # D update, the stem's im2col rows of real | wrong (one buffer per D; the fake third is filled after G).
         col3 = [None] * nD
-        if self.batched_d:
-            fork0 = torch.cuda.Event()
-            fork0.record(main)
-            for i in range(nD):
-                st = streams[i]
-                with torch.cuda.stream(st):
-                    if st is not main:
-                        st.wait_event(fork0)
+        fork0 = torch.cuda.Event()
+        fork0.record(main)
+        for i in range(nD):
+            st = streams[i]
+            with torch.cuda.stream(st):
+                if st is not main:
+                    st.wait_event(fork0)
+                self.bD[i].grad.zero_()
+                if self.batched_d:
                     S = real[i].shape[2]
                     col3[i] = torch.empty((3, B * (S // 2) * (S // 2), 64), device=self.dev, dtype=torch.bfloat16)
                     ops.stem_im2col(real[i], out=col3[i][0])
                     ops.stem_im2col(wrong[i], out=col3[i][1])
+        g_zeroed = None
+        if self.concurrent:
+            with torch.cuda.stream(self._sW[nD]):
+                self._sW[nD].wait_event(fork0)
+                self.bG.grad.zero_()
+                g_zeroed = torch.cuda.Event()
+                g_zeroed.record(self._sW[nD])
         fake, mu, logvar, Tg = self.G.forward(z, emb, eps, True)                             # trainer.py:544
         dmu = torch.empty_like(mu)
         dlogvar = torch.empty_like(logvar)
@@ -268,7 +282,6 @@ class FusedTrainer:
                     ops.arena_reset(self.dev)
                 # ---------------- (2) update D_i, trainer.py:375-427
                 bucket = self.bD[i]
-                bucket.grad.zero_()                 # conv weight gradients accumulate straight into the bucket
                 ready, fin = self._layerwise(bucket, self.lr_d) if (self.batched_d and self.layerwise) else (None, None)
                 sink = GradSink(bucket.views, self._sW[i] if self.concurrent else None, prezeroed=True, on_ready=ready)
                 sink.on_repack = ready.repack if ready is not None else None
@@ -327,7 +340,10 @@ class FusedTrainer:
         # ---------------- (3b) G backward + update, trainer.py:480-488
         for dc in dcs:
             dmu.add_(dc)                         # mu is not detached in train_Gnet (trainer.py:438)
-        self.bG.grad.zero_()
+        if g_zeroed is not None:
+            main.wait_event(g_zeroed)
+        else:
+            self.bG.grad.zero_()
         ready, fin = self._layerwise(self.bG, self.lr_g) if self.layerwise else (None, None)
         sinkG = GradSink(self.bG.views, self._sW[nD] if self.concurrent else None, prezeroed=True, on_ready=ready)
         sinkG.on_repack = ready.repack if ready is not None else None
