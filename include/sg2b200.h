@@ -65,13 +65,32 @@ int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad, int Cout, int Cin
  * epilogue from the TMEM accumulators (the BatchNorm batch statistics, consumed by sg2_bn_act_fwd). stats_groups > 1:
  * the batch is `stats_groups` equal sub-batches with separate statistics, stats [groups][2][Cout]; returns SG2_ENOFUSE
  * when a pixel tile of this shape would straddle two sub-batches (use sg2_bn_stats then).
- * act (fprop): 0, or SG2_ACT_LRELU applied in the epilogue (layers without BatchNorm: the D stems, model.py:383-384). */
+ * act (fprop): 0, or SG2_ACT_LRELU applied in the epilogue (layers without BatchNorm: the D stems, model.py:383-384).
+ * bias9 (fprop, CONV3x3, optional): fp32 [B][9][Cout] added to the accumulators before statistics / store; row
+ * (ry*3+rx) applies to the pixels of border class ry = {top row, interior, bottom row} x rx = {left, interior, right}
+ * (see sg2_joint_bias: the broadcast c_code channels of a jointConv folded into a per-sample bias). */
 int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mode, int B, int H, int W, int Cin,
-                   int Cout, int splitk, float* stats, int stats_groups, int act, void* stream);
+                   int Cout, int splitk, float* stats, int stats_groups, int act, const float* bias9, void* stream);
 int sg2_conv_dgrad(int kind, const void* dy, const void* wpkT, void* dx, int out_mode, int B, int H, int W, int Cin,
                    int Cout, int splitk, void* stream);
 int sg2_conv_wgrad(int kind, const void* x, const void* dy, float* dwpk, int B, int H, int W, int Cin, int Cout,
                    int splitk, void* stream);
+
+/* ---- jointConv with the broadcast c_code folded away (NEXT_STAGE_G, model.py:274-279) ---------------------------
+ * conv3x3(cat(c (x) 1, h)) = conv3x3_h(h) + bias9[b][border class][o]: the c_code channels are constant over the image,
+ * so their share is a per-sample bias that depends only on which taps fall inside the image (sg2_conv_fprop's bias9).
+ * w: the fp32 master of the FULL weight, element (o, e, tap) at w[o*so + e*se + tap*st]; the c_code channels are the
+ * first E input channels (model.py:277 puts c_code first).
+ *   sg2_joint_bias     : c [B][E] -> bias9 [B][9][Cout]
+ *   sg2_joint_tap_sums : dy [B][H][W][Cout] bf16 -> S [B][9 taps][Cout] = sum of dy over the pixels where the tap is
+ *                        inside the image (R: fp32 [B][9][Cout] ZEROED workspace). Two launches.
+ *   sg2_joint_c_bwd    : dw[o][e][tap] (=|+=) sum_b c[b][e] S[b][tap][o] (same strides as w; NULL to skip);
+ *                        dc[b][e] += sum_{o,tap} w[o][e][tap] S[b][tap][o] (NULL to skip). One launch each. */
+int sg2_joint_bias(const float* c, const float* w, long long so, long long se, long long st, float* bias9, int B, int E,
+                   int Cout, void* stream);
+int sg2_joint_tap_sums(const void* dy, float* R, float* S, int B, int H, int W, int Cout, void* stream);
+int sg2_joint_c_bwd(const float* S, const float* c, const float* w, long long so, long long se, long long st, float* dc,
+                    float* dw, int dw_accumulate, int B, int E, int Cout, void* stream);
 
 /* ---- BatchNorm (+ GLU / LeakyReLU(0.2) / residual) on [P pixels][C channels] bf16 ---------------------
  * nn.BatchNorm2d/1d train mode (model.py:137,147,158,161,218,361,372,387-394): batch mean, biased variance,

@@ -137,6 +137,7 @@ struct GatherDesc {
   float* stats;
   int stats_bg;  // images per statistics group (0: one)
   int act;  // epilogue activation (tile kernel only): 0 none, 2 LeakyReLU(0.2)
+  const float* bias9;  // [B][9][N] border-region bias (tile kernel only)
 };
 
 template <int BN, int BK>
@@ -286,6 +287,7 @@ static int plan_tile(const GatherDesc& d, TilePlan& pl) {
   p.stats = d.stats;
   p.stats_bg = d.stats_bg;
   p.act = d.act;
+  p.bias9 = d.bias9;
   {
     const char* e = getenv("SG2_TILE_DBG");
     p.dbg = e ? atoi(e) : 0;
@@ -411,6 +413,7 @@ static int launch_fprop(const GatherDesc& d, cudaStream_t st) {
     const int rc = launch_tile(d, st);
     if (rc != 1) return rc;
   }
+  if (d.bias9) SG2_FAIL(SG2_EINVAL, "conv_fprop: the region bias needs a tile-resident shape (Cin %d, N %d)", d.Cin, d.N);
 #define SG2_CASE(BN_, BK_) \
   if (bn == BN_ && bk == BK_) return launch_fprop_t<BN_, BK_>(d, st);
   SG2_CASE(256, 64) SG2_CASE(128, 64) SG2_CASE(64, 64) SG2_CASE(32, 64)
@@ -654,10 +657,13 @@ int sg2_version(void) { return 1; }
 const char* sg2_last_error(void) { return g_err; }
 
 int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mode, int B, int H, int W, int Cin,
-                   int Cout, int splitk, float* stats, int stats_groups, int act, void* stream) {
+                   int Cout, int splitk, float* stats, int stats_groups, int act, const float* bias9, void* stream) {
   GatherDesc d;
   memset(&d, 0, sizeof(d));
   d.stats = stats;
+  if (bias9 && (kind != SG2_CONV3x3 || out_mode != SG2_OUT_BF16 || splitk > 1 || (Cout % 4)))
+    SG2_FAIL(SG2_EINVAL, "conv_fprop: the region bias applies to a plain bf16 3x3 convolution");
+  d.bias9 = bias9;
   if (act != 0 && act != SG2_ACT_LRELU) SG2_FAIL(SG2_EINVAL, "conv_fprop: epilogue activation %d", act);
   if (act && (stats || out_mode != SG2_OUT_BF16 || splitk > 1)) SG2_FAIL(SG2_EINVAL, "conv_fprop: fused activation needs a plain bf16 epilogue");
   d.act = act;

@@ -319,6 +319,113 @@ __global__ void logits_bwd_kernel(const float* __restrict__ dprob, const float* 
   }
 }
 
+// ------------------------------------------------------------------------------------------ jointConv c_code folding
+// NEXT_STAGE_G.jointConv (model.py:274-279) convolves cat(c_code broadcast over the image, h). The c_code channels are
+// constant over the image, so their part of the 3x3 convolution is a per-sample bias that only depends on which taps
+// fall inside the image: 9 border classes (top / interior / bottom row) x (left / interior / right column).
+//   Wc[b][tap][o]   = sum_e W[o][e][tap] * c[b][e]
+//   bias9[b][r][o]  = sum over the taps valid in border class r of Wc[b][tap][o]
+// Backward needs S[b][tap][o] = sum of dy[b][y][x][o] over the pixels where tap is valid, then
+//   dW[o][e][tap] = sum_b c[b][e] * S[b][tap][o],   dc[b][e] += sum_{o,tap} W[o][e][tap] * S[b][tap][o].
+// W is addressed as w[o * so + e * se + tap * st] (OIHW or OHWI master; e runs over the first E input channels).
+__device__ __forceinline__ bool joint_tap_valid(int tap, int r) {
+  const int ky = tap / 3, kx = tap % 3, ry = r / 3, rx = r % 3;
+  return !(ry == 0 && ky == 0) && !(ry == 2 && ky == 2) && !(rx == 0 && kx == 0) && !(rx == 2 && kx == 2);
+}
+// grid (Cout, B), 288 threads: warp = tap
+__global__ void joint_bias_kernel(const float* __restrict__ c, const float* __restrict__ w, long long so, long long se,
+                                  long long st, float* __restrict__ bias9, int E, int Cout) {
+  const int o = blockIdx.x, b = blockIdx.y, tap = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float wc[9];
+  float acc = 0.f;
+  for (int e = lane; e < E; e += 32) acc = fmaf(w[o * so + e * se + tap * st], c[(long long)b * E + e], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) wc[tap] = acc;
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    const int r = threadIdx.x;
+    float v = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v += joint_tap_valid(t, r) ? wc[t] : 0.f;
+    bias9[((long long)b * 9 + r) * Cout + o] = v;
+  }
+}
+// R[b][r][o] += sums of dy over the pixels of border class r. grid (H, B): one image row per block (one row class);
+// 256 threads = 8-channel vectors x pixel slots.
+__global__ void __launch_bounds__(256)
+joint_region_sums_kernel(const uint4* __restrict__ dy, float* __restrict__ R, int H, int W, int Cout) {
+  const int y = blockIdx.x, b = blockIdx.y;
+  const int vc = Cout >> 3;                       // vectors per pixel
+  const int v = threadIdx.x % vc, slot = threadIdx.x / vc, nslot = blockDim.x / vc;
+  const int ry = y == 0 ? 0 : (y == H - 1 ? 2 : 1);
+  const uint4* row = dy + ((long long)b * H + y) * W * vc;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  float* Rb = R + ((long long)b * 9 + ry * 3) * Cout + v * 8;
+  if (slot < nslot) {
+    for (int x = slot; x < W; x += nslot) {
+      float f[8];
+      lg_unpack8(row[(long long)x * vc + v], f);
+      if (x == 0 || x == W - 1) {
+        float* dst = Rb + (x == 0 ? 0 : 2) * Cout;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dst + j, f[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+  }
+  __shared__ float sh[256][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (slot == 0) {
+    for (int k = 1; k < nslot; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += sh[k * vc + v][j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(Rb + Cout + j, acc[j]);
+  }
+}
+// S[b][tap][o] = sum over the border classes where tap is valid of R[b][r][o]
+__global__ void joint_tap_sums_kernel(const float* __restrict__ R, float* __restrict__ S, int B, int Cout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 9 * Cout) return;
+  const int o = i % Cout, tap = (i / Cout) % 9, b = i / (9 * Cout);
+  float v = 0.f;
+#pragma unroll
+  for (int r = 0; r < 9; ++r) v += joint_tap_valid(tap, r) ? R[((long long)b * 9 + r) * Cout + o] : 0.f;
+  S[i] = v;
+}
+// dW[o][e][tap] (=|+=) sum_b c[b][e] * S[b][tap][o].  grid (Cout, 9), threads over e.
+__global__ void joint_dw_kernel(const float* __restrict__ S, const float* __restrict__ c, float* __restrict__ dw,
+                                long long so, long long se, long long st, int accumulate, int B, int E, int Cout) {
+  const int o = blockIdx.x, tap = blockIdx.y;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(c[(long long)b * E + e], S[((long long)b * 9 + tap) * Cout + o], acc);
+    float* d = dw + o * so + e * se + tap * st;
+    *d = accumulate ? *d + acc : acc;
+  }
+}
+// dc[b][e] += sum_{o,tap} W[o][e][tap] * S[b][tap][o].  grid (B), threads over e; S[b] staged in shared memory.
+__global__ void joint_dc_kernel(const float* __restrict__ S, const float* __restrict__ w, long long so, long long se,
+                                long long st, float* __restrict__ dc, int E, int Cout) {
+  extern __shared__ float s_sb[];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) s_sb[i] = S[(long long)b * 9 * Cout + i];
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float acc = 0.f;
+    for (int o = 0; o < Cout; ++o)
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) acc = fmaf(w[o * so + e * se + tap * st], s_sb[tap * Cout + o], acc);
+    dc[(long long)b * E + e] += acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ Adam (+ EMA)
 // torch.optim.Adam semantics (no amsgrad, no weight decay): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
 // p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).  Optional EMA: avg = 0.999 avg + 0.001 p  (trainer.py:571-572).
@@ -617,6 +724,36 @@ int sg2_cal_loss(const float* x, const int* labels, int B, int F, float* ws /* 2
   cal_coeff_kernel<<<1, 256, 0, st>>>(ws, labels, B, F, loss, ws + (size_t)B * B);
   if (dx) cal_dx_kernel<<<grid1d((long long)B * F), 256, 0, st>>>(x, ws + (size_t)B * B, B, F, dx);
   SG2_LAUNCH_OK("cal_loss");
+}
+
+int sg2_joint_bias(const float* c, const float* w, long long so, long long se, long long st, float* bias9, int B, int E,
+                   int Cout, void* stream) {
+  joint_bias_kernel<<<dim3(Cout, B), 288, 0, (cudaStream_t)stream>>>(c, w, so, se, st, bias9, E, Cout);
+  SG2_LAUNCH_OK("joint_bias");
+}
+
+int sg2_joint_tap_sums(const void* dy, float* R, float* S, int B, int H, int W, int Cout, void* stream) {
+  if (Cout % 8 || Cout > 2048) SG2_FAIL(SG2_EINVAL, "joint_tap_sums: Cout=%d", Cout);
+  if (H < 2 || W < 2) SG2_FAIL(SG2_EINVAL, "joint_tap_sums: %dx%d image", H, W);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int vc = Cout / 8;
+  const int threads = vc >= 256 ? vc : (256 / vc) * vc;
+  joint_region_sums_kernel<<<dim3(H, B), threads, 0, st>>>((const uint4*)dy, R, H, W, Cout);
+  const int n = B * 9 * Cout;
+  joint_tap_sums_kernel<<<(n + 255) / 256, 256, 0, st>>>(R, S, B, Cout);
+  SG2_LAUNCH_OK("joint_tap_sums");
+}
+
+int sg2_joint_c_bwd(const float* S, const float* c, const float* w, long long so, long long se, long long st, float* dc,
+                    float* dw, int dw_accumulate, int B, int E, int Cout, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dw) joint_dw_kernel<<<dim3(Cout, 9), 128, 0, s>>>(S, c, dw, so, se, st, dw_accumulate, B, E, Cout);
+  if (dc) {
+    const size_t smem = (size_t)9 * Cout * sizeof(float);
+    if (smem > 48 * 1024) SG2_FAIL(SG2_EINVAL, "joint_c_bwd: Cout=%d", Cout);
+    joint_dc_kernel<<<B, 128, smem, s>>>(S, w, so, se, st, dc, E, Cout);
+  }
+  SG2_LAUNCH_OK("joint_c_bwd");
 }
 
 int sg2_adam_tick(int* step, float* bc, float beta1, float beta2, void* stream) {

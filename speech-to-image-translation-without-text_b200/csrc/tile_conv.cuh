@@ -54,6 +54,9 @@ struct TileParams {
   int b_resident;  // 1: all ntaps*kchunks weight tiles of this CTA's (group, n-tile) stay in SMEM for the whole kernel
   int na;          // halo stages (2..4): the producer runs na-1 (chunk, source) steps ahead of the MMA issuer
   int act;         // epilogue activation: 0 none, 2 LeakyReLU(0.2) (layers without BatchNorm)
+  // per-sample, per-border-region bias [B][9][N] added to the accumulators before statistics / store: the
+  // contribution of input channels that are constant over the image (the broadcast c_code of a jointConv)
+  const float* bias9;
   uint32_t magic_img, magic_x;  // ceil(2^32 / tiles_img), ceil(2^32 / tiles_x): division-free tile decoding
   long long* dbg_out;  // diagnostics: per-CTA wait-cycle counters (SG2_TILE_DBG & 64)
   int dbg;
@@ -444,6 +447,21 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
               for (int j = 16; j < 32; ++j) v[j] = 0u;
             }
             tmem_ld_wait();
+            if (p.bias9 != nullptr && valid) {
+              const int ry = y == 0 ? 0 : (y == p.Ho - 1 ? 2 : 1), rx = x == 0 ? 0 : (x == p.Wo - 1 ? 2 : 1);
+              const float4* bp =
+                  reinterpret_cast<const float4*>(p.bias9 + ((long long)(b * 9 + ry * 3 + rx) * p.N + n0 + c0));
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (c0 + 4 * j < BN) {
+                  const float4 t = __ldg(bp + j);
+                  v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + t.x);
+                  v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + t.y);
+                  v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + t.z);
+                  v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + t.w);
+                }
+              }
+            }
             if (p.act == 2) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {

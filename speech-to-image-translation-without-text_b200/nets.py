@@ -247,6 +247,124 @@ class ConvBlock:
         return dx
 
 
+class JointOperand:
+    """Operands of a generator jointConv (conv3x3 on cat(c_code broadcast, h), model.py:274-279) with the c_code
+    channels folded away: the tensor-core kernels only see the h part of the weight, [Cout][9][Ch]; the first E input
+    channels act through a per-sample bias (forward) and two small reductions (backward). Same interface as
+    ConvOperand, so GradSink / the per-layer optimiser treat it like any other conv weight."""
+    kind = CONV3
+
+    def __init__(self, weight, E):
+        self.weight = weight
+        self.E = E
+        self.Cout, self.CinFull = weight.shape[0], weight.shape[1]
+        self.Cin = self.CinFull - E
+        self.CoP, self.CiP = self.Cout, self.Cin
+        self.flop_scale = 1.0
+        self._key = None
+        self._full = ConvOperand(CONV3, weight)      # bf16 [Cout][9][CinFull] of the whole weight (mirror or pack)
+        self.wpk = self.wpkT = self.dwpk = None
+        self.cparts = []
+
+    def w_f32(self):
+        """(fp32 master, so, se, st): element (o, e, tap) of the full weight at flat[o*so + e*se + tap*st]."""
+        oh = getattr(self.weight, "_sg2_ohwi", None)
+        if oh is not None:
+            return oh, 9 * self.CinFull, 1, self.CinFull
+        return self.weight.detach(), 9 * self.CinFull, 9, 1
+
+    def packs(self):
+        w = self.weight
+        key = (w.data_ptr(), w._version, getattr(w, "_sg2_version", 0), w.device)
+        if key != self._key:
+            oh = getattr(w, "_sg2_ohwi", None)
+            if oh is not None:
+                if self._key is None or key[1] != self._key[1]:
+                    ops.f32_to_bf16(oh, out=w._sg2_wpk)      # torch-side write to the master: refresh the bf16 mirror
+                full = w._sg2_wpk
+            else:
+                full, _ = self._full.packs()
+            if self.wpk is None or self.wpk.device != w.device:
+                self.wpk = torch.empty((self.Cout, 9, self.Cin), device=w.device, dtype=torch.bfloat16)
+                self.wpkT = torch.empty((self.Cin, 9, self.Cout), device=w.device, dtype=torch.bfloat16)
+            self.wpk.copy_(full.view(self.Cout, 9, self.CinFull)[:, :, self.E:])
+            ops.pack_transpose(CONV3, self.wpk, self.wpkT, self.Cout, self.Cin)
+            self._key = key
+        return self.wpk, self.wpkT
+
+    def wgrad_begin(self, device, prezeroed=False):
+        shape = (self.Cout, 9, self.Cin)
+        if self.dwpk is None or self.dwpk.device != device:
+            self.dwpk = torch.empty(shape, device=device, dtype=torch.float32)
+        self.dwpk.zero_()
+        self._done_c = 0
+
+    def wgrad_add(self, x, dy):
+        ops.conv_wgrad(CONV3, x, dy, self.dwpk)
+
+    def wgrad_finish(self, out=None):
+        """h part: the packed accumulator goes into the [.., E:] channels of the gradient; c part: c^T S."""
+        w = self.weight
+        oh = getattr(w, "_sg2_ohwi", None)
+        if oh is not None:
+            g = w._sg2_dw.view(self.Cout, 9, self.CinFull)
+            g[:, :, self.E:].copy_(self.dwpk)
+            dst, strides = w._sg2_dw, (9 * self.CinFull, 1, self.CinFull)
+        else:
+            g = torch.empty_like(w, dtype=torch.float32) if out is None else out
+            g[:, self.E:].copy_(self.dwpk.view(self.Cout, 3, 3, self.Cin).permute(0, 3, 1, 2))
+            dst, strides = g, (9 * self.CinFull, 9, 1)
+        for k, (c, S) in enumerate(self.cparts):
+            ops.joint_c_bwd(S, c, (dst,) + strides, dw=dst, dw_accumulate=k > 0)
+        self.cparts = []
+        if oh is None:
+            return g
+        if out is not None:
+            return out
+        Co, Ci, kh, kw = w.shape
+        return w._sg2_dw.view(Co, kh, kw, Ci).permute(0, 3, 1, 2).contiguous()
+
+
+class JointBlock:
+    """jointConv of NEXT_STAGE_G: conv3x3(cat(c_code, h)) -> BatchNorm -> GLU without materialising the concatenation."""
+
+    def __init__(self, conv, bn, E):
+        self.conv, self.bn, self.act = conv, bn, ACT_GLU
+        self.op = JointOperand(conv.weight, E)
+
+    def fwd(self, c, h, training):
+        op, bn = self.op, self.bn
+        wpk, _ = op.packs()
+        bias9 = ops.joint_bias(c, op.w_f32(), op.Cout)
+        gamma, beta = bn.weight.detach(), bn.bias.detach()
+        if training:
+            st = ops.bn_stats32(op.Cout, h.device)
+            y, _ = ops.conv_fprop(CONV3, h, wpk, op.Cout, stats=st, bias9=bias9)
+            out, mean, rstd = ops.bn_act_fwd(y, gamma, beta, self.act, stats=st,
+                                             running=(bn.running_mean, bn.running_var, bn.num_batches_tracked))
+        else:
+            y = ops.conv_fprop(CONV3, h, wpk, op.Cout, bias9=bias9)
+            mean, rstd = ops.bn_eval_stats(bn.running_mean, bn.running_var)
+            out = ops.bn_act_fwd(y, gamma, beta, self.act, mean=mean, rstd=rstd)
+        return out, (h, y, mean, rstd, c)
+
+    def bwd(self, saved, dout, sink, dc):
+        """-> dh; dc (B, E) fp32 += the c_code gradient of this layer."""
+        h, y, mean, rstd, c = saved
+        op = self.op
+        (dg, acc), (db, _) = sink.slot(self.bn.weight), sink.slot(self.bn.bias)
+        dy = ops.bn_act_bwd(y, dout, mean, rstd, self.bn.weight.detach(), self.bn.bias.detach(), self.act, dg, db, acc)
+        S = ops.joint_tap_sums(dy)
+        ops.joint_c_bwd(S, c, op.w_f32(), dc=dc)
+        op.cparts.append((c, S))
+        sink.conv(op, h, dy)
+        _, wpkT = op.packs()
+        B, H, W, Ch = h.shape
+        dh = ops.conv_dgrad(CONV3, dy, wpkT, B, H, W, Ch)
+        sink.dgrad_done(op)
+        return dh
+
+
 class HeadBlock:
     """GET_IMAGE_G (model.py:287-298): conv3x3 C->3 + tanh; output NCHW fp32 image."""
     CP = 16
@@ -294,7 +412,7 @@ class GEngine:
         self.stages = []
         for s in range(2, self.branches + 1):
             hn = getattr(net, f"h_net{s}")
-            joint = ConvBlock(CONV3, hn.jointConv[0], hn.jointConv[1], ACT_GLU)
+            joint = JointBlock(hn.jointConv[0], hn.jointConv[1], self.E)
             res = [(ConvBlock(CONV3, r.block[0], r.block[1], ACT_GLU), ConvBlock(CONV3, r.block[3], r.block[4], ACT_NONE))
                    for r in hn.residual]
             up = ConvBlock(UPCONV, hn.upsample[1], hn.upsample[2], ACT_GLU)
@@ -343,8 +461,7 @@ class GEngine:
         T["heads"] = [hsv]
         T["stages"] = []
         for si, (joint, res, up) in enumerate(self.stages):
-            cat = ops.concat_c(c, x)
-            x, sj = joint.fwd(cat, training)
+            x, sj = joint.fwd(c, x, training)
             sres = []
             for (b0, b1) in res:
                 mid, s0 = b0.fwd(x, training)
@@ -385,8 +502,7 @@ class GEngine:
                 dmid = b1.bwd(s1, dx, grads)
                 dblk = b0.bwd(s0, dmid, grads)
                 dx = ops.add_bf16(dblk, dx)
-            dcat = joint.bwd(sj, dx, grads)
-            dx = ops.concat_c_bwd(dcat, self.E, dc)
+            dx = joint.bwd(sj, dx, grads, dc)
         for blk, sv in zip(reversed(self.ups1), reversed(T["ups1"])):
             dx = blk.bwd(sv, dx, grads)
         # INIT_STAGE_G fc: NHWC -> CHW feature order -> BN1d+GLU backward -> linear

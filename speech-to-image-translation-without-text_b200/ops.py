@@ -131,7 +131,7 @@ def _auto_split(m_rows, n_cols, k_blocks):
     return max(1, s)
 
 
-def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, groups=1, act=ACT_NONE):
+def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, groups=1, act=ACT_NONE, bias9=None):
     """x (B,H,W,Cin) bf16 -> y bf16 (B,Ho,Wo,Cout). With `stats` (fp32 [groups*2*Cout], zeroed) the per-channel sum /
     sum of squares of each of the `groups` sub-batches is accumulated too (in the conv epilogue, in the fp32->bf16 pass
     of a split-K layer, or by sg2_bn_stats when a pixel tile would straddle sub-batches); returns (y, True)."""
@@ -141,20 +141,21 @@ def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, grou
     taps = {CONV3: 9, UPCONV: 4, CONV4S2: 16, GEMM: 1}[kind]
     pgroups = 4 if kind == UPCONV else 1          # output parity groups (separate GEMMs)
     if splitk is None:
-        splitk = 1 if act else _auto_split(B * Ho * Wo // pgroups, Cout, taps * max(1, Cin // 64))
+        splitk = 1 if (act or bias9 is not None) else _auto_split(B * Ho * Wo // pgroups, Cout, taps * max(1, Cin // 64))
     if splitk > 1:
         y32 = torch.zeros((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
         _conv_call("sg2_conv_fprop", 2, fl, kind, _p(x), _p(wpk), _p(y32), OUT_F32_ATOMIC, B, H, W, Cin, Cout, splitk,
-                   None, 1, 0, _st())
+                   None, 1, 0, None, _st())
         if stats is None:
             return f32_to_bf16(y32)
         return f32_to_bf16_stats(y32, stats, groups), True
     y = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
     try:
         _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, 1, _p(stats),
-                   groups, act, _st())
+                   groups, act, _p(bias9), _st())
     except _lib.NoFuse:
-        _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, 1, None, 1, act, _st())
+        _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, 1, None, 1, act,
+                   _p(bias9), _st())
         bn_stats(y.view(-1, Cout), stats, groups)
     return y if stats is None else (y, True)
 
@@ -329,6 +330,31 @@ def concat_c_bwd(dcat, E, dc, want_dh=True):
     dh = torch.empty((B, H, W, Ch), device=dcat.device, dtype=torch.bfloat16) if want_dh else None
     _call("sg2_concat_c_bwd", 1, _p(dcat), _p(dh), _p(dc), B, H * W, E, Ch, _st())
     return dh
+
+
+# jointConv with the broadcast c_code folded into a per-sample border-class bias (see include/sg2b200.h).
+# wst = (w fp32 master of the full weight, so, se, st): element (o, e, tap) at w.flat[o*so + e*se + tap*st].
+def joint_bias(c, wst, Cout):
+    w, so, se, st = wst
+    B, E = c.shape
+    bias9 = torch.empty((B, 9, Cout), device=c.device, dtype=torch.float32)
+    _call("sg2_joint_bias", 1, _p(c), _p(w), so, se, st, _p(bias9), B, E, Cout, _st())
+    return bias9
+
+
+def joint_tap_sums(dy):
+    B, H, W, Cout = dy.shape
+    R = _arena(dy.device).take(B * 9 * Cout * 4, torch.float32)
+    S = torch.empty((B, 9, Cout), device=dy.device, dtype=torch.float32)
+    _call("sg2_joint_tap_sums", 2, _p(dy), _p(R), _p(S), B, H, W, Cout, _st())
+    return S
+
+
+def joint_c_bwd(S, c, wst, dc=None, dw=None, dw_accumulate=False):
+    w, so, se, st = wst
+    B, E = c.shape
+    _call("sg2_joint_c_bwd", (dc is not None) + (dw is not None), _p(S), _p(c), _p(w), so, se, st, _p(dc), _p(dw),
+          int(dw_accumulate), B, E, S.shape[2], _st())
 
 
 def head_tanh_fwd(y, B, H, W):

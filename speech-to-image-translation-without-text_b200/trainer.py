@@ -403,7 +403,9 @@ class CapturedStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = ops.launches()
-        with torch.cuda.graph(self.graph):
+        # the main branch (G forward, G backward) is on the step's critical path like the largest discriminator's
+        hi = -1 if os.environ.get("SG2_PRIO_MAIN", "1") != "0" else 0
+        with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(device=self.tr.dev, priority=hi)):
             self.losses = self._body()
         self.launches_per_step = ops.launches() - n0
         return self

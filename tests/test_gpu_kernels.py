@@ -149,6 +149,52 @@ def test_concat_c_and_backward():
     assert _rel(dc, dcat[..., :E].float().sum((1, 2))) < 1e-5
 
 
+@pytest.mark.parametrize("layout", ["oihw", "ohwi"])
+@pytest.mark.parametrize("B,H,W,E,Ch,Co", [(3, 16, 16, 128, 32, 64), (2, 24, 20, 128, 64, 128)])
+def test_joint_conv_c_code_folding(layout, B, H, W, E, Ch, Co):
+    """conv3x3(cat(c broadcast, h)) (model.py:274-279) with the c_code channels folded into a per-sample border-class
+    bias: forward vs F.conv2d on the concatenation (rel err <= 5e-3, bf16 h / weights), and the backward pieces
+    dc, dW[:, :E] (fp32 reductions, rel err <= 1e-4 against torch on the same bf16 dy) and dW[:, E:], dh (<= 5e-3)."""
+    from sg2b200 import ops
+    g = torch.Generator().manual_seed(7)
+    c = torch.randn(B, E, generator=g).cuda()
+    h = _bf(torch.randn(B, Ch, H, W, generator=g).cuda())
+    w = (torch.randn(Co, E + Ch, 3, 3, generator=g) / ((E + Ch) * 9) ** 0.5).cuda()
+    wb = w.clone()
+    wb[:, E:] = _bf(w[:, E:])                       # the kernels see the h part in bf16, the c part in fp32
+    cat = torch.cat((c[:, :, None, None].expand(B, E, H, W), h), 1)
+    ref = F.conv2d(cat, wb, padding=1)
+    if layout == "ohwi":
+        wm, so, se, st = w.permute(0, 2, 3, 1).contiguous(), 9 * (E + Ch), 1, E + Ch
+    else:
+        wm, so, se, st = w.contiguous(), 9 * (E + Ch), 9, 1
+    wst = (wm, so, se, st)
+    wpk = w[:, E:].permute(0, 2, 3, 1).reshape(Co, 9, Ch).contiguous().bfloat16()
+    x = h.permute(0, 2, 3, 1).contiguous().bfloat16()
+    bias9 = ops.joint_bias(c, wst, Co)
+    stats = torch.zeros(2 * Co, device="cuda")
+    y, _ = ops.conv_fprop(ops.CONV3, x, wpk, Co, stats=stats, bias9=bias9)
+    yf = y.float().permute(0, 3, 1, 2)
+    assert _rel(yf, ref) < 5e-3
+    assert _rel(stats[:Co], yf.sum((0, 2, 3))) < 1e-3          # statistics include the bias
+    # backward
+    dy = _bf(torch.randn(B, Co, H, W, generator=g).cuda())
+    cat_r = cat.clone().requires_grad_(True)
+    w_r = wb.clone().requires_grad_(True)
+    F.conv2d(cat_r, w_r, padding=1).backward(dy)
+    dyn = dy.permute(0, 2, 3, 1).contiguous().bfloat16()
+    S = ops.joint_tap_sums(dyn)
+    dc = torch.zeros(B, E, device="cuda")
+    dwm = torch.full_like(wm, float("nan"))
+    ops.joint_c_bwd(S, c, wst, dc=dc, dw=dwm)
+    dw_c = dwm.permute(0, 3, 1, 2)[:, :E] if layout == "ohwi" else dwm[:, :E]
+    assert _rel(dc, cat_r.grad[:, :E].sum((2, 3))) < 1e-4
+    assert _rel(dw_c, w_r.grad[:, :E]) < 1e-4
+    ops.joint_c_bwd(S, c, wst, dw=dwm, dw_accumulate=True)
+    dw_c = dwm.permute(0, 3, 1, 2)[:, :E] if layout == "ohwi" else dwm[:, :E]
+    assert _rel(dw_c, 2 * w_r.grad[:, :E]) < 1e-4
+
+
 def test_head_and_stem_layout_kernels():
     from sg2b200 import ops
     g = torch.Generator().manual_seed(2)

@@ -158,7 +158,7 @@ def run_case(kind, B, H, W, Ci, Co, splitk, reps):
     else:
         y = torch.full((B, Ho, Wo, Co), float("nan"), device=dev, dtype=torch.bfloat16)
         mode = 0
-    f = lambda: _lib.call("sg2_conv_fprop", kind, x_nhwc.data_ptr(), wpk.data_ptr(), y.data_ptr(), mode, B, H, W, Ci, Co, splitk, None, 1, 0, st)
+    f = lambda: _lib.call("sg2_conv_fprop", kind, x_nhwc.data_ptr(), wpk.data_ptr(), y.data_ptr(), mode, B, H, W, Ci, Co, splitk, None, 1, 0, None, st)
     f()
     torch.cuda.synchronize()
     res["checks"].append(err_report("fprop", y.permute(0, 3, 1, 2), y_ref.detach()))
