@@ -176,21 +176,30 @@ __global__ void __launch_bounds__(256) linear_bwd_x_kernel(const void* __restric
       if (m < M) o[(long long)m * Kout] = acc[m];
   }
 }
+// grid (ceil(Kout / 32), M), block (32, 8): the 8 thread rows split the slabs, then one shared-memory reduction
 __global__ void linear_bwd_x_reduce_kernel(const float* __restrict__ part, float* __restrict__ dx, int nslabs, int M,
                                            int Kout) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (m, k)
-  if (i >= M * Kout) return;
-  const int m = i / Kout, k = i % Kout;
+  const int k = blockIdx.x * 32 + threadIdx.x, m = blockIdx.y, g = threadIdx.y;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int b = 0;
-  for (; b + 3 < nslabs; b += 4) {
-    s0 += part[((long long)(b + 0) * 32 + m) * Kout + k];
-    s1 += part[((long long)(b + 1) * 32 + m) * Kout + k];
-    s2 += part[((long long)(b + 2) * 32 + m) * Kout + k];
-    s3 += part[((long long)(b + 3) * 32 + m) * Kout + k];
+  if (k < Kout) {
+    int b = g;
+    for (; b + 24 < nslabs; b += 32) {
+      s0 += part[((long long)(b + 0) * 32 + m) * Kout + k];
+      s1 += part[((long long)(b + 8) * 32 + m) * Kout + k];
+      s2 += part[((long long)(b + 16) * 32 + m) * Kout + k];
+      s3 += part[((long long)(b + 24) * 32 + m) * Kout + k];
+    }
+    for (; b < nslabs; b += 8) s0 += part[((long long)b * 32 + m) * Kout + k];
   }
-  for (; b < nslabs; ++b) s0 += part[((long long)b * 32 + m) * Kout + k];
-  dx[i] = (s0 + s1) + (s2 + s3);
+  __shared__ float sh[8][32];
+  sh[g][threadIdx.x] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (g == 0 && k < Kout) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += sh[j][threadIdx.x];
+    dx[(long long)m * Kout + k] = t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ CA_NET tail
@@ -363,19 +372,20 @@ joint_region_sums_kernel(const uint4* __restrict__ dy, float* __restrict__ R, in
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   float* Rb = R + ((long long)b * 9 + ry * 3) * Cout + v * 8;
-  if (slot < nslot) {
-    for (int x = slot; x < W; x += nslot) {
-      float f[8];
-      lg_unpack8(row[(long long)x * vc + v], f);
-      if (x == 0 || x == W - 1) {
-        float* dst = Rb + (x == 0 ? 0 : 2) * Cout;
+  // interior columns 1 .. W-2 (branch-free, loads pipelined); the two border columns go straight to their classes
+#pragma unroll 4
+  for (int x = 1 + slot; x < W - 1; x += nslot) {
+    float f[8];
+    lg_unpack8(row[(long long)x * vc + v], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(dst + j, f[j]);
-      } else {
+    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  }
+  if (slot < 2) {
+    float f[8];
+    lg_unpack8(row[(long long)(slot == 0 ? 0 : W - 1) * vc + v], f);
+    float* dst = Rb + (slot == 0 ? 0 : 2) * Cout;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += f[j];
-      }
-    }
+    for (int j = 0; j < 8; ++j) atomicAdd(dst + j, f[j]);
   }
   __shared__ float sh[256][8];
 #pragma unroll
@@ -410,19 +420,26 @@ __global__ void joint_dw_kernel(const float* __restrict__ S, const float* __rest
     *d = accumulate ? *d + acc : acc;
   }
 }
-// dc[b][e] += sum_{o,tap} W[o][e][tap] * S[b][tap][o].  grid (B), threads over e; S[b] staged in shared memory.
+// dc[b][e] += sum_{o,tap} W[o][e][tap] * S[b][tap][o].  grid (Cout / 8, 9 taps), threads over e: a thread reads its 8
+// weights once and walks the batch (S of the block's 8 output channels staged in shared memory; fp32 atomics on dc).
+constexpr int kJointMaxB = 128;
 __global__ void joint_dc_kernel(const float* __restrict__ S, const float* __restrict__ w, long long so, long long se,
-                                long long st, float* __restrict__ dc, int E, int Cout) {
-  extern __shared__ float s_sb[];
-  const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) s_sb[i] = S[(long long)b * 9 * Cout + i];
+                                long long st, float* __restrict__ dc, int B, int E, int Cout) {
+  __shared__ float ss[kJointMaxB][8];
+  const int o0 = blockIdx.x * 8, tap = blockIdx.y;
+  for (int i = threadIdx.x; i < B * 8; i += blockDim.x)
+    ss[i >> 3][i & 7] = S[((long long)(i >> 3) * 9 + tap) * Cout + o0 + (i & 7)];
   __syncthreads();
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    float acc = 0.f;
-    for (int o = 0; o < Cout; ++o)
+    float wv[8];
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) acc = fmaf(w[o * so + e * se + tap * st], s_sb[tap * Cout + o], acc);
-    dc[(long long)b * E + e] += acc;
+    for (int k = 0; k < 8; ++k) wv[k] = w[(o0 + k) * so + e * se + tap * st];
+    for (int b = 0; b < B; ++b) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc = fmaf(wv[k], ss[b][k], acc);
+      atomicAdd(&dc[(long long)b * E + e], acc);
+    }
   }
 }
 
@@ -545,7 +562,17 @@ __global__ void kl_loss_kernel(const float* __restrict__ mu, const float* __rest
 __global__ void cal_scores_kernel(const float* __restrict__ x, int B, int F, float* __restrict__ S) {
   const int i = blockIdx.x / B, j = blockIdx.x % B;
   float acc = 0.f;
-  for (int f = threadIdx.x; f < F; f += blockDim.x) acc += x[(long long)i * F + f] * x[(long long)j * F + f];
+  if ((F & 3) == 0) {
+    const float4* xi = reinterpret_cast<const float4*>(x + (long long)i * F);
+    const float4* xj = reinterpret_cast<const float4*>(x + (long long)j * F);
+#pragma unroll 4
+    for (int f = threadIdx.x; f < (F >> 2); f += blockDim.x) {
+      const float4 a = xi[f], b = xj[f];
+      acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    }
+  } else {
+    for (int f = threadIdx.x; f < F; f += blockDim.x) acc += x[(long long)i * F + f] * x[(long long)j * F + f];
+  }
   __shared__ float sh[32];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
@@ -663,8 +690,8 @@ int sg2_linear_bwd_x(const void* dy, int dy_bf16, const float* w, float* dx, flo
     else
       linear_bwd_x_kernel<false><<<nslabs, threads, 0, (cudaStream_t)stream>>>(
           reinterpret_cast<const float*>(dy) + (size_t)m0 * N, w, scratch, mc, N, K, Kout);
-    linear_bwd_x_reduce_kernel<<<(mc * Kout + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch, dx + (size_t)m0 * Kout,
-                                                                                          nslabs, mc, Kout);
+    linear_bwd_x_reduce_kernel<<<dim3((Kout + 31) / 32, mc), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        scratch, dx + (size_t)m0 * Kout, nslabs, mc, Kout);
   }
   SG2_LAUNCH_OK("linear_bwd_x");
 }
@@ -733,7 +760,7 @@ int sg2_joint_bias(const float* c, const float* w, long long so, long long se, l
 }
 
 int sg2_joint_tap_sums(const void* dy, float* R, float* S, int B, int H, int W, int Cout, void* stream) {
-  if (Cout % 8 || Cout > 2048) SG2_FAIL(SG2_EINVAL, "joint_tap_sums: Cout=%d", Cout);
+  if (Cout % 8 || Cout > 1024) SG2_FAIL(SG2_EINVAL, "joint_tap_sums: Cout=%d", Cout);
   if (H < 2 || W < 2) SG2_FAIL(SG2_EINVAL, "joint_tap_sums: %dx%d image", H, W);
   cudaStream_t st = (cudaStream_t)stream;
   const int vc = Cout / 8;
@@ -749,9 +776,8 @@ int sg2_joint_c_bwd(const float* S, const float* c, const float* w, long long so
   cudaStream_t s = (cudaStream_t)stream;
   if (dw) joint_dw_kernel<<<dim3(Cout, 9), 128, 0, s>>>(S, c, dw, so, se, st, dw_accumulate, B, E, Cout);
   if (dc) {
-    const size_t smem = (size_t)9 * Cout * sizeof(float);
-    if (smem > 48 * 1024) SG2_FAIL(SG2_EINVAL, "joint_c_bwd: Cout=%d", Cout);
-    joint_dc_kernel<<<B, 128, smem, s>>>(S, w, so, se, st, dc, E, Cout);
+    if (B > kJointMaxB || (Cout % 8)) SG2_FAIL(SG2_EINVAL, "joint_c_bwd: B=%d Cout=%d", B, Cout);
+    joint_dc_kernel<<<dim3(Cout / 8, 9), 128, 0, s>>>(S, w, so, se, st, dc, B, E, Cout);
   }
   SG2_LAUNCH_OK("joint_c_bwd");
 }

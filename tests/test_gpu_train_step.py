@@ -35,7 +35,7 @@ def _ostep(orc, b):
                          labels=b["labels"].tolist()))
 
 
-@pytest.mark.parametrize("branches,B", [(1, 8), (3, 6)])
+@pytest.mark.parametrize("branches,B", [(1, 8), (3, 6), (3, 24)])   # (3, 24) = BASELINE.json's configs[1]
 def test_fused_step_matches_oracle(branches, B):
     """Losses within 2e-2 relative (bf16 activations vs fp32 reference). Adam's first step moves every weight by
     lr * g/(|g| + eps) ~ +-lr, so after the update two implementations can differ by at most 2 lr per element (a

@@ -1,4 +1,7 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel totals for the LAST step."""
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel totals for the LAST complete step.
+
+    python tools/launch_summary.py launches.csv [nsteps] [step_rows_out.csv]
+"""
 import csv, collections, re, sys
 path, nsteps = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 2
 lines = [l for l in open(path) if not l.startswith("==")]
@@ -16,6 +19,13 @@ if len(marks) >= 2:   # the last COMPLETE step: between the last two markers
 else:
     per = len(rows) // nsteps
     it = rows[-per:]
+if len(sys.argv) > 3:          # dump the raw CSV rows of that step (header + rows) for profiles/
+    ids = {str(r[0]) for r in it}
+    with open(sys.argv[3], "w") as f:
+        f.write(lines[0])
+        for l in lines[1:]:
+            if l.split(",", 1)[0].strip('"') in ids:
+                f.write(l)
 tot = sum(r[2] for r in it)
 print(f"{len(rows)} launches total; last step: {len(it)} launches, {tot/1000:.3f} ms of kernel time (cold-cache, serialised)")
 agg = collections.defaultdict(lambda: [0, 0.0])
