@@ -71,8 +71,13 @@ int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad, int Cout, int Cin
  * (see sg2_joint_bias: the broadcast c_code channels of a jointConv folded into a per-sample bias). */
 int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mode, int B, int H, int W, int Cin,
                    int Cout, int splitk, float* stats, int stats_groups, int act, const float* bias9, void* stream);
+/* dgrad epilogue operand (optional): epi_src has the shape of dx (bf16). SG2_EPI_ADD: dx = dgrad + epi_src (the skip
+ * branch of a ResBlock's backward, model.py:166-169). SG2_EPI_LRELU_MASK: dx = dgrad * (epi_src > 0 ? 1 : 0.2), the
+ * backward of the LeakyReLU(0.2) that produced epi_src (D stems, model.py:383-384). Returns SG2_ENOFUSE for shapes that
+ * run on the gather kernel or split K (apply sg2_add_bf16 / sg2_lrelu_bwd afterwards instead). */
+enum { SG2_EPI_NONE = 0, SG2_EPI_ADD = 1, SG2_EPI_LRELU_MASK = 2 };
 int sg2_conv_dgrad(int kind, const void* dy, const void* wpkT, void* dx, int out_mode, int B, int H, int W, int Cin,
-                   int Cout, int splitk, void* stream);
+                   int Cout, int splitk, const void* epi_src, int epi_mode, void* stream);
 int sg2_conv_wgrad(int kind, const void* x, const void* dy, float* dwpk, int B, int H, int W, int Cin, int Cout,
                    int splitk, void* stream);
 

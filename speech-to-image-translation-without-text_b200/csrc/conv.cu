@@ -138,6 +138,8 @@ struct GatherDesc {
   int stats_bg;  // images per statistics group (0: one)
   int act;  // epilogue activation (tile kernel only): 0 none, 2 LeakyReLU(0.2)
   const float* bias9;  // [B][9][N] border-region bias (tile kernel only)
+  const void* epi_src;  // epilogue operand, layout of the output (tile kernel only)
+  int epi_mode;         // 0 none, SG2_EPI_ADD, SG2_EPI_LRELU_MASK
 };
 
 template <int BN, int BK>
@@ -288,6 +290,8 @@ static int plan_tile(const GatherDesc& d, TilePlan& pl) {
   p.stats_bg = d.stats_bg;
   p.act = d.act;
   p.bias9 = d.bias9;
+  p.epi_src = d.epi_src;
+  p.epi_mode = d.epi_mode;
   {
     const char* e = getenv("SG2_TILE_DBG");
     p.dbg = e ? atoi(e) : 0;
@@ -414,6 +418,7 @@ static int launch_fprop(const GatherDesc& d, cudaStream_t st) {
     if (rc != 1) return rc;
   }
   if (d.bias9) SG2_FAIL(SG2_EINVAL, "conv_fprop: the region bias needs a tile-resident shape (Cin %d, N %d)", d.Cin, d.N);
+  if (d.epi_mode) SG2_FAIL(SG2_ENOFUSE, "epilogue operand: this shape runs on the gather kernel (K %d, N %d)", d.Cin, d.N);
 #define SG2_CASE(BN_, BK_) \
   if (bn == BN_ && bk == BK_) return launch_fprop_t<BN_, BK_>(d, st);
   SG2_CASE(256, 64) SG2_CASE(128, 64) SG2_CASE(64, 64) SG2_CASE(32, 64)
@@ -748,9 +753,16 @@ int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mo
 }
 
 int sg2_conv_dgrad(int kind, const void* dy, const void* wpkT, void* dx, int out_mode, int B, int H, int W, int Cin,
-                   int Cout, int splitk, void* stream) {
+                   int Cout, int splitk, const void* epi_src, int epi_mode, void* stream) {
   GatherDesc d;
   memset(&d, 0, sizeof(d));
+  if (epi_mode != 0 && epi_mode != SG2_EPI_ADD && epi_mode != SG2_EPI_LRELU_MASK)
+    SG2_FAIL(SG2_EINVAL, "conv_dgrad: epilogue mode %d", epi_mode);
+  if (epi_mode && (!epi_src || (Cin % 8))) SG2_FAIL(SG2_EINVAL, "conv_dgrad: epilogue operand missing / Cin %% 8");
+  if (epi_mode && (out_mode != SG2_OUT_BF16 || splitk > 1))
+    SG2_FAIL(SG2_ENOFUSE, "conv_dgrad: the epilogue operand needs a plain bf16 epilogue");
+  d.epi_src = epi_src;
+  d.epi_mode = epi_mode;
   d.Cin = Cout;  // contraction runs over the forward output channels
   d.w = wpkT;
   d.N = Cin;

@@ -57,6 +57,10 @@ struct TileParams {
   // per-sample, per-border-region bias [B][9][N] added to the accumulators before statistics / store: the
   // contribution of input channels that are constant over the image (the broadcast c_code of a jointConv)
   const float* bias9;
+  // epilogue operand with the layout of the output tensor (bf16): epi_mode 1 adds it (residual gradient), 2 scales the
+  // result by LeakyReLU'(src) = (src > 0 ? 1 : 0.2) (backward of a LeakyReLU whose output is src)
+  const void* epi_src;
+  int epi_mode;
   uint32_t magic_img, magic_x;  // ceil(2^32 / tiles_img), ceil(2^32 / tiles_x): division-free tile decoding
   long long* dbg_out;  // diagnostics: per-CTA wait-cycle counters (SG2_TILE_DBG & 64)
   int dbg;
@@ -428,8 +432,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
             cur_grp = grp;
           }
         }
-        __nv_bfloat16* dst_row = reinterpret_cast<__nv_bfloat16*>(p.out) + p.out_off[g] + (long long)b * p.sb +
-                                 (long long)y * p.sy + (long long)x * p.sx + n0;
+        const long long row_off = p.out_off[g] + (long long)b * p.sb + (long long)y * p.sy + (long long)x * p.sx + n0;
+        __nv_bfloat16* dst_row = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off;
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t((acc * MT + m) * BN);
 #pragma unroll
         for (int ci = 0; ci < Cfg::kCPW; ++ci) {
@@ -459,6 +463,25 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
                   v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + t.y);
                   v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + t.z);
                   v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + t.w);
+                }
+              }
+            }
+            if (p.epi_mode != 0 && valid) {
+              const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.epi_src) + row_off + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (c0 + 8 * j < BN) {
+                  const uint4 sv = __ldg(sp + j);
+                  const uint32_t w4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float lo = bf16_lo(w4[k]), hi = bf16_hi(w4[k]);
+                    float a0 = __uint_as_float(v[8 * j + 2 * k]), a1 = __uint_as_float(v[8 * j + 2 * k + 1]);
+                    if (p.epi_mode == 1) { a0 += lo; a1 += hi; }
+                    else { a0 = lo > 0.f ? a0 : 0.2f * a0; a1 = hi > 0.f ? a1 : 0.2f * a1; }
+                    v[8 * j + 2 * k] = __float_as_uint(a0);
+                    v[8 * j + 2 * k + 1] = __float_as_uint(a1);
+                  }
                 }
               }
             }

@@ -221,7 +221,8 @@ class ConvBlock:
             out = ops.bn_act_fwd(y, gamma, beta, self.act, residual, mean=mean, rstd=rstd)
         return out, (x, y, mean, rstd)
 
-    def bwd(self, saved, dout, sink, need_dx=True, need_w=True, groups=1):
+    def bwd(self, saved, dout, sink, need_dx=True, need_w=True, groups=1, epi=None):
+        """epi = (src, ops.EPI_ADD | ops.EPI_LRELU_MASK): folded into the dgrad epilogue (see ops.conv_dgrad)."""
         x, y, mean, rstd = saved
         if self.bn is not None:
             if need_w:
@@ -241,7 +242,7 @@ class ConvBlock:
         if need_dx:
             _, wpkT = self.op.packs()
             B, H, W, Cin = x.shape
-            dx = ops.conv_dgrad(self.kind, dy, wpkT, B, H, W, Cin)
+            dx = ops.conv_dgrad(self.kind, dy, wpkT, B, H, W, Cin, epi=epi)
         if need_w:
             sink.dgrad_done(self.op)
         return dx
@@ -500,8 +501,7 @@ class GEngine:
             dx = up.bwd(su, dx, grads)
             for (b0, b1), (s0, s1) in zip(reversed(res), reversed(sres)):
                 dmid = b1.bwd(s1, dx, grads)
-                dblk = b0.bwd(s0, dmid, grads)
-                dx = ops.add_bf16(dblk, dx)
+                dx = b0.bwd(s0, dmid, grads, epi=(dx, ops.EPI_ADD))     # + the skip branch's gradient
             dx = joint.bwd(sj, dx, grads, dc)
         for blk, sv in zip(reversed(self.ups1), reversed(T["ups1"])):
             dx = blk.bwd(sv, dx, grads)
@@ -542,9 +542,10 @@ class StemBlock:
                              act=ACT_LRELU)
         return out, (col, out, B, S)
 
-    def bwd(self, saved, dout, sink, need_dimg, need_w=True):
+    def bwd(self, saved, dout, sink, need_dimg, need_w=True, masked=False):
+        """masked: dout already carries the LeakyReLU backward (folded into the producing dgrad's epilogue)."""
         col, y, B, S = saved
-        dy = ops.lrelu_bwd(y, dout).view(1, 1, -1, self.op.Cout)
+        dy = (dout if masked else ops.lrelu_bwd(y, dout)).view(1, 1, -1, self.op.Cout)
         if need_w:
             sink.conv(self.op, col, dy)
         dimg = None
@@ -633,7 +634,9 @@ class DEngine:
             dx = dxi if dx is None else ops.add_bf16(dx, dxi)
         if dx is None:
             raise RuntimeError("sg2b200: D backward without any output gradient")
-        for blk, sv in zip(reversed(self.trunk), reversed(T["trunk"])):
-            dx = blk.bwd(sv, dx, sink, need_w=need_w, groups=groups)
-        dimg = self.stem.bwd(T["stem"], dx, sink, need_dimg, need_w=need_w)
+        for li in range(len(self.trunk) - 1, -1, -1):
+            # the first trunk conv's dgrad also applies the stem's LeakyReLU backward (mask by the stem output)
+            epi = (T["stem"][1], ops.EPI_LRELU_MASK) if li == 0 else None
+            dx = self.trunk[li].bwd(T["trunk"][li], dx, sink, need_w=need_w, groups=groups, epi=epi)
+        dimg = self.stem.bwd(T["stem"], dx, sink, need_dimg, need_w=need_w, masked=True)
         return (sink.finish() if own else None), dimg, (dc if need_dc else None)

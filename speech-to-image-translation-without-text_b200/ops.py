@@ -160,8 +160,17 @@ def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, grou
     return y if stats is None else (y, True)
 
 
-def conv_dgrad(kind, dy, wpkT, B, H, W, Cin, splitk=None, flop_scale=1.0):
-    """dy (B,Ho,Wo,Cout) bf16 -> dx bf16 (B,H,W,Cin)."""
+EPI_ADD, EPI_LRELU_MASK = 1, 2
+
+
+def _epi_apply(dx, epi):
+    src, mode = epi
+    return add_bf16(dx, src) if mode == EPI_ADD else lrelu_bwd(src, dx)
+
+
+def conv_dgrad(kind, dy, wpkT, B, H, W, Cin, splitk=None, flop_scale=1.0, epi=None):
+    """dy (B,Ho,Wo,Cout) bf16 -> dx bf16 (B,H,W,Cin). epi = (src, EPI_ADD | EPI_LRELU_MASK): src (shape of dx) is added
+    to / masks the result, in the conv epilogue when the shape allows it, else by the separate kernel."""
     Cout = dy.shape[-1]
     fl = flop_scale * _conv_flops(kind, B, H, W, Cin, Cout)
     taps = {CONV3: 9, UPCONV: 16, CONV4S2: 4, GEMM: 1}[kind]
@@ -170,11 +179,20 @@ def conv_dgrad(kind, dy, wpkT, B, H, W, Cin, splitk=None, flop_scale=1.0):
         splitk = _auto_split(B * H * W // groups, Cin, taps * max(1, Cout // 64))
     if splitk > 1:
         dx32 = torch.zeros((B, H, W, Cin), device=dy.device, dtype=torch.float32)
-        _conv_call("sg2_conv_dgrad", 2, fl, kind, _p(dy), _p(wpkT), _p(dx32), OUT_F32_ATOMIC, B, H, W, Cin, Cout, splitk, _st())
-        return f32_to_bf16(dx32)
+        _conv_call("sg2_conv_dgrad", 2, fl, kind, _p(dy), _p(wpkT), _p(dx32), OUT_F32_ATOMIC, B, H, W, Cin, Cout, splitk,
+                   None, 0, _st())
+        dx = f32_to_bf16(dx32)
+        return dx if epi is None else _epi_apply(dx, epi)
     dx = torch.empty((B, H, W, Cin), device=dy.device, dtype=torch.bfloat16)
-    _conv_call("sg2_conv_dgrad", 1, fl, kind, _p(dy), _p(wpkT), _p(dx), OUT_BF16, B, H, W, Cin, Cout, 1, _st())
-    return dx
+    if epi is not None:
+        try:
+            _conv_call("sg2_conv_dgrad", 1, fl, kind, _p(dy), _p(wpkT), _p(dx), OUT_BF16, B, H, W, Cin, Cout, 1,
+                       _p(epi[0]), epi[1], _st())
+            return dx
+        except _lib.NoFuse:
+            pass
+    _conv_call("sg2_conv_dgrad", 1, fl, kind, _p(dy), _p(wpkT), _p(dx), OUT_BF16, B, H, W, Cin, Cout, 1, None, 0, _st())
+    return dx if epi is None else _epi_apply(dx, epi)
 
 
 def conv_wgrad(kind, x, dy, dwpk, splitk=None, flop_scale=1.0):

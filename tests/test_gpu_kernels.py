@@ -149,6 +149,35 @@ def test_concat_c_and_backward():
     assert _rel(dc, dcat[..., :E].float().sum((1, 2))) < 1e-5
 
 
+@pytest.mark.parametrize("kind,B,H,W,Ci,Co", [(0, 2, 32, 32, 32, 64), (2, 2, 32, 32, 64, 128), (0, 3, 4, 4, 128, 256)])
+def test_conv_dgrad_epilogue_operand(kind, B, H, W, Ci, Co):
+    """dgrad with a residual gradient added / a LeakyReLU mask applied in the epilogue (or, for shapes on the gather
+    kernel, by the separate kernel) equals dgrad followed by the separate kernel up to one bf16 rounding (2^-8)."""
+    from sg2b200 import ops
+    g = torch.Generator().manual_seed(5)
+    k = 3 if kind == 0 else 4
+    w = (torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5).cuda()
+    s1, s2 = ops.pack_shapes(kind, Co, Ci)
+    wpk = torch.empty(s1, device="cuda", dtype=torch.bfloat16)
+    wpkT = torch.empty(s2, device="cuda", dtype=torch.bfloat16)
+    ops.pack_weights(kind, w, wpk, wpkT, Co, Ci, Co, Ci)
+    Ho, Wo = (H, W) if kind == 0 else (H // 2, W // 2)
+    dy = torch.randn(B, Ho, Wo, Co, generator=g).cuda().bfloat16()
+    src = torch.randn(B, H, W, Ci, generator=g).cuda().bfloat16()
+    base = ops.conv_dgrad(kind, dy, wpkT, B, H, W, Ci).float()
+    n0 = ops.launches()
+    fused_add = ops.conv_dgrad(kind, dy, wpkT, B, H, W, Ci, epi=(src, ops.EPI_ADD)).float()
+    n1 = ops.launches()
+    fused_mask = ops.conv_dgrad(kind, dy, wpkT, B, H, W, Ci, epi=(src, ops.EPI_LRELU_MASK)).float()
+    # output grids >= 16 x 8 run on the tile-resident kernel: ONE launch; the 4 x 4 map falls back to conv + kernel
+    assert (n1 - n0 == 1) if H >= 16 else (n1 - n0 >= 2), n1 - n0
+    ref_add = base + src.float()
+    ref_mask = torch.where(src.float() > 0, base, 0.2 * base)
+    scale = base.abs() + src.float().abs() + 1e-2           # the sum may cancel: error relative to the operands
+    assert float(((fused_add - ref_add).abs() / scale).max()) < 2.0 ** -7
+    assert float(((fused_mask - ref_mask).abs() / (base.abs() + 1e-2)).max()) < 2.0 ** -7
+
+
 @pytest.mark.parametrize("layout", ["oihw", "ohwi"])
 @pytest.mark.parametrize("B,H,W,E,Ch,Co", [(3, 16, 16, 128, 32, 64), (2, 24, 20, 128, 64, 128)])
 def test_joint_conv_c_code_folding(layout, B, H, W, E, Ch, Co):

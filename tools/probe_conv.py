@@ -171,7 +171,7 @@ def run_case(kind, B, H, W, Ci, Co, splitk, reps):
         dx = torch.zeros(B, H, W, Ci, device=dev, dtype=torch.float32)
     else:
         dx = torch.full((B, H, W, Ci), float("nan"), device=dev, dtype=torch.bfloat16)
-    f = lambda: _lib.call("sg2_conv_dgrad", kind, dy_nhwc.data_ptr(), wpkT.data_ptr(), dx.data_ptr(), mode, B, H, W, Ci, Co, splitk, st)
+    f = lambda: _lib.call("sg2_conv_dgrad", kind, dy_nhwc.data_ptr(), wpkT.data_ptr(), dx.data_ptr(), mode, B, H, W, Ci, Co, splitk, None, 0, st)
     f()
     torch.cuda.synchronize()
     res["checks"].append(err_report("dgrad", dx.permute(0, 3, 1, 2), dx_ref))
