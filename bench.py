@@ -166,7 +166,8 @@ def run_ours(args):
     torch.manual_seed(1234)
     netG, netsD = utils.build_networks(cfg, dev)
     sdist.broadcast_state([netG] + netsD)
-    reducer = sdist.GradAllReducer() if world > 1 else None
+    # one NCCL communicator per network (3 discriminators + G): their reductions are independent branches of the step
+    reducer = sdist.GradAllReducer(channels=int(os.environ.get("SG2_COMMS", "4"))) if world > 1 else None
     tr = trainer.FusedTrainer(netG, netsD, cfg, all_reduce=reducer)
 
     n_host = 3

@@ -24,19 +24,34 @@ def init_from_env(backend=None):
 
 
 class GradAllReducer:
-    """callable(flat_grad): in-place mean over ranks. Mean of per-replica mean losses == the global-batch mean for
-    equal shards."""
+    """callable(flat_grad, chan=0): in-place mean over ranks. Mean of per-replica mean losses == the global-batch mean
+    for equal shards.
 
-    def __init__(self, group=None):
-        self.group = group
+    channels > 1 (NCCL only): one communicator per `chan` (the trainer passes the network's index). Collectives on ONE
+    communicator execute in host issue order, so with a single communicator the early, large gradient slices of the
+    biggest discriminator would queue behind the smaller networks' reductions, which are issued earlier by the host but
+    become ready later on the device; separate communicators let the networks' branches of the step reduce
+    independently. NCCL averages in the collective (ReduceOp.AVG); gloo sums and scales."""
+
+    def __init__(self, group=None, channels=1):
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bytes = 0
+        self.groups = [group]
+        self.avg = False
+        if self.world > 1 and dist.get_backend(group) == "nccl":
+            self.avg = True
+            if group is None and channels > 1:
+                self.groups += [dist.new_group(backend="nccl") for _ in range(channels - 1)]
 
-    def __call__(self, flat):
+    def __call__(self, flat, chan=0):
         if self.world == 1:
             return flat
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-        flat.mul_(1.0 / self.world)
+        g = self.groups[chan % len(self.groups)]
+        if self.avg:
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=g)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=g)
+            flat.mul_(1.0 / self.world)
         self.bytes += flat.numel() * flat.element_size()
         return flat
 

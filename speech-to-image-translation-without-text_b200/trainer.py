@@ -155,7 +155,7 @@ class FusedTrainer:
         self._tables = {}
 
     # ------------------------------------------------------------------ helpers
-    def _layerwise(self, bucket, lr):
+    def _layerwise(self, bucket, lr, chan=0):
         """-> (on_ready, finish): all-reduce + Adam of each conv weight as soon as its wgrad is done (on the wgrad side
         stream, overlapping the rest of backward), then the small parameters and any leftover in finish()."""
         bucket.adam_tick()
@@ -167,7 +167,7 @@ class FusedTrainer:
             if dp:
                 if o < bucket.small_n:
                     return                       # small layer: reduced + updated with the rest in finish()
-                self.all_reduce(bucket.grad[o:o + n])
+                self.all_reduce(bucket.grad[o:o + n], chan)
             bucket.adam_range(o, n, lr)
             done.add(w)
 
@@ -182,7 +182,7 @@ class FusedTrainer:
 
         def finish():
             if dp:
-                self.all_reduce(bucket.grad[:bucket.small_n])
+                self.all_reduce(bucket.grad[:bucket.small_n], chan)
                 bucket.adam_range(0, bucket.small_n, lr)
             else:
                 bucket.adam_range(0, bucket.head_n, lr)
@@ -282,7 +282,7 @@ class FusedTrainer:
                     ops.arena_reset(self.dev)
                 # ---------------- (2) update D_i, trainer.py:375-427
                 bucket = self.bD[i]
-                ready, fin = self._layerwise(bucket, self.lr_d) if (self.batched_d and self.layerwise) else (None, None)
+                ready, fin = self._layerwise(bucket, self.lr_d, i) if (self.batched_d and self.layerwise) else (None, None)
                 sink = GradSink(bucket.views, self._sW[i] if self.concurrent else None, prezeroed=True, on_ready=ready)
                 sink.on_repack = ready.repack if ready is not None else None
                 if self.batched_d:
@@ -318,7 +318,7 @@ class FusedTrainer:
                     fin()
                 else:
                     if self.all_reduce is not None:
-                        self.all_reduce(bucket.grad)
+                        self.all_reduce(bucket.grad, i)
                     bucket.adam(self.lr_d)
                 # ---------------- (3a) D_i's share of the G step, trainer.py:436-446 (updated D weights, live fake, mu)
                 probs = torch.empty(2, B, device=self.dev, dtype=torch.float32)
@@ -344,7 +344,7 @@ class FusedTrainer:
             main.wait_event(g_zeroed)
         else:
             self.bG.grad.zero_()
-        ready, fin = self._layerwise(self.bG, self.lr_g) if self.layerwise else (None, None)
+        ready, fin = self._layerwise(self.bG, self.lr_g, nD) if self.layerwise else (None, None)
         sinkG = GradSink(self.bG.views, self._sW[nD] if self.concurrent else None, prezeroed=True, on_ready=ready)
         sinkG.on_repack = ready.repack if ready is not None else None
         self.G.backward(Tg, dimgs, dmu, dlogvar, sinkG)
@@ -353,7 +353,7 @@ class FusedTrainer:
             fin()                                # + EMA avg = 0.999 avg + 0.001 p (trainer.py:571-572)
         else:
             if self.all_reduce is not None:
-                self.all_reduce(self.bG.grad)
+                self.all_reduce(self.bG.grad, nD)
             self.bG.adam(self.lr_g)
         # errG_total = sum_i errG_i + kl + sum_i cal_i (trainer.py:486)
         cal = self.losses[nD + 2:nD + 3]
