@@ -33,6 +33,12 @@ UNIT = "images/s"
 GF_PER_IMAGE_NECESSARY = 134.7   # conv+linear GFLOP per image of the necessary-work step
 
 
+
+def workload_name(branches, batch):
+    """The same string on both arms (the driver compares their `config`)."""
+    return (f"birds_3stages.yml {branches}-stage 256x256 train step (G + D64/D128/D256 fwd+bwd, Adam, EMA), "
+            f"batch {batch}/GPU")
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -144,7 +150,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"birds_3stages.yml {args.branches}-stage 256x256 train step, batch {args.batch}/GPU",
+        "config": {"workload": workload_name(args.branches, args.batch),
                    "device": "host CPU"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -335,7 +341,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": f"birds_3stages.yml {args.branches}-stage 256x256 train step (G + D64/D128/D256 fwd+bwd, Adam, EMA), batch {B}/GPU",
+        "config": {"workload": workload_name(args.branches, B),
                    "global_batch": world * B, "parallelism": f"dp{world}",
                    "launch": "eager" if cap is None else "CUDA graph replay (whole step)",
                    "l2": "inputs+activations per step (> 2 GB) exceed the 126 MB L2; no explicit flush"},
