@@ -78,6 +78,30 @@ def test_g_eval_mode_uses_running_stats():
     assert ok, msg
 
 
+def test_g_eval_synthesis_batch_256_equals_its_chunks():
+    """netG.eval() no_grad synthesis at batch 256 (the reference's evaluate(), trainer.py:681-803).
+    Eval-mode samples are independent, so the full-size batch must equal the concatenation of four 64-sample calls
+    (different tile / split-K schedules and atomic summation orders flip individual bf16 roundings, which then propagate
+    through up to 20 layers: measured 6e-3 at 256x256, bound 1.5e-2) — a size-independent check at a size the fp32
+    oracle is not run at; the first 16 samples are also compared with the oracle."""
+    cfg = Cfg(BRANCH_NUM=3)
+    net, sd, _, _, _, g = _g_case(cfg, 4, training=False)
+    gen = torch.Generator().manual_seed(9)
+    B = 256
+    z = torch.randn(B, cfg.Z_DIM, generator=gen).cuda()
+    emb = torch.randn(B, cfg.TEXT_DIM, generator=gen).cuda()
+    eps = torch.randn(B, cfg.EMBEDDING_DIM, generator=gen).cuda()
+    with torch.no_grad():
+        full, mu, _ = net(z, emb, eps=eps)
+        parts = [net(z[i:i + 64], emb[i:i + 64], eps=eps[i:i + 64])[0] for i in range(0, B, 64)]
+        oimgs, _, _ = g_forward(sd, z[:16], emb[:16], eps[:16], cfg, False)
+    assert [tuple(t.shape) for t in full] == [(B, 3, 64, 64), (B, 3, 128, 128), (B, 3, 256, 256)]
+    for lvl in range(3):
+        cat = torch.cat([p[lvl] for p in parts], 0)
+        assert rel(full[lvl], cat) < 1.5e-2, (lvl, rel(full[lvl], cat))
+        assert rel(full[lvl][:16], oimgs[lvl]) < FWD_TOL, (lvl, rel(full[lvl][:16], oimgs[lvl]))
+
+
 @pytest.mark.parametrize("which,B", [(0, 8), (1, 6), (2, 4)])
 def test_d_forward_backward(which, B):
     cfg = Cfg()
