@@ -363,7 +363,7 @@ class FusedTrainer:
 
 
 class CapturedStep:
-    """The whole train step (noise draw, G forward, 3 D updates, G update, Adam, EMA — ~1300 kernel launches) captured
+    """The whole train step (noise draw, G forward, 3 D updates, G update, Adam, EMA — ~650 kernel launches) captured
     once into a CUDA graph and replayed per step: the launch-bound inner loop costs one cudaGraphLaunch instead of
     ~20 ms of Python/ctypes/driver work. Inputs live in static device buffers (`load()` copies a batch in)."""
 
