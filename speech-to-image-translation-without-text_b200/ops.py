@@ -4,6 +4,7 @@ stream; every kernel launched here is one of ours. No CPU path: CPU tensors are 
 Layout convention: activations are NHWC bf16 torch tensors of shape (B, H, W, C) (or (P, C)).
 """
 import ctypes
+import os
 
 import torch
 
@@ -120,15 +121,28 @@ def _out_hw(kind, H, W):
     return H, W
 
 
-def _auto_split(m_rows, n_cols, k_blocks):
-    """Split-K factor for GEMMs whose 128 x BN output tiles cannot fill the 148 SMs."""
+def _auto_split(m_rows, n_cols, k_blocks, groups=1):
+    """Split-K factor for GEMMs whose 128 x BN output tiles cannot fill the 148 SMs.
+
+    One CTA per (tile, split): the launch runs in ceil(tiles * s / 148) waves and a CTA's time is its K range plus a fixed
+    part (prologue + epilogue; the fp32 red.global.add epilogue of a split CTA moves 4x the bytes of the bf16 store), both
+    in units of one 64-deep K block. The factor with the smallest waves x (K / s + fixed) wins, the smaller one on ties —
+    a factor that spills a few CTAs into a second wave costs a whole extra wave."""
     bn = n_cols if n_cols in (160, 192) else (
         256 if n_cols % 256 == 0 else (128 if n_cols % 128 == 0 else (64 if n_cols % 64 == 0 else 32)))
     tiles = -(-m_rows // 128) * max(1, n_cols // bn)
     if tiles >= 96 or k_blocks < 8:
         return 1
-    s = min(k_blocks // 8, -(-N_SM // tiles))      # >= 8 K blocks per CTA: fewer fp32 atomics per output
-    return max(1, s)
+    if os.environ.get("SG2_SPLIT_OLD", "0") == "1":
+        return max(1, min(k_blocks // 8, -(-N_SM // tiles)))
+    tiles *= groups                                   # output-parity groups are separate GEMMs of the same launch
+    best, best_cost = 1, None
+    for sp in range(1, max(1, min(k_blocks // 8, 32)) + 1):      # >= 8 K blocks per CTA: fewer fp32 atomics per output
+        waves = -(-tiles * sp // N_SM)
+        cost = waves * (k_blocks / sp + (6.0 if sp > 1 else 3.0))
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = sp, cost
+    return best
 
 
 def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, groups=1, act=ACT_NONE, bias9=None):
@@ -141,7 +155,7 @@ def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, grou
     taps = {CONV3: 9, UPCONV: 4, CONV4S2: 16, GEMM: 1}[kind]
     pgroups = 4 if kind == UPCONV else 1          # output parity groups (separate GEMMs)
     if splitk is None:
-        splitk = 1 if (act or bias9 is not None) else _auto_split(B * Ho * Wo // pgroups, Cout, taps * max(1, Cin // 64))
+        splitk = 1 if (act or bias9 is not None) else _auto_split(B * Ho * Wo // pgroups, Cout, taps * max(1, Cin // 64), pgroups)
     if splitk > 1:
         y32 = torch.zeros((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
         _conv_call("sg2_conv_fprop", 2, fl, kind, _p(x), _p(wpk), _p(y32), OUT_F32_ATOMIC, B, H, W, Cin, Cout, splitk,
@@ -176,7 +190,7 @@ def conv_dgrad(kind, dy, wpkT, B, H, W, Cin, splitk=None, flop_scale=1.0, epi=No
     taps = {CONV3: 9, UPCONV: 16, CONV4S2: 4, GEMM: 1}[kind]
     groups = 4 if kind == CONV4S2 else 1
     if splitk is None:
-        splitk = _auto_split(B * H * W // groups, Cin, taps * max(1, Cout // 64))
+        splitk = _auto_split(B * H * W // groups, Cin, taps * max(1, Cout // 64), groups)
     if splitk > 1:
         dx32 = torch.zeros((B, H, W, Cin), device=dy.device, dtype=torch.float32)
         _conv_call("sg2_conv_dgrad", 2, fl, kind, _p(dy), _p(wpkT), _p(dx32), OUT_F32_ATOMIC, B, H, W, Cin, Cout, splitk,
