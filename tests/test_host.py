@@ -89,3 +89,26 @@ def test_modules_reject_cpu_inputs():
             model.D_NET64()(torch.randn(2, 3, 64, 64), torch.randn(2, 128))
     finally:
         set_cfg(Cfg())
+
+
+def test_split_k_factor_fills_whole_waves():
+    """ops._auto_split (host logic, no kernel call): one CTA per (tile, split, parity group) on 148 SMs; the factor must
+    not spill a few CTAs into an extra wave (D256's 1024->2048 layer at 3B = 72 tiles: 2 x 72 = 144, not 3 x 72 = 216),
+    must count the output-parity groups of fused-upsample / stride-2-dgrad launches, and leaves full launches alone."""
+    from sg2b200 import ops
+    n_sm = ops.N_SM
+    assert ops._auto_split(72 * 16, 2048, 256) == 2            # 9 x 8 tiles
+    assert ops._auto_split(24 * 16, 2048, 256) == 6            # 3 x 8 tiles
+    assert ops._auto_split(24 * 16, 1024, 64, groups=4) == 3   # 3 x 4 tiles x 4 parity groups
+    assert ops._auto_split(72 * 64 * 64, 256, 32) == 1         # thousands of tiles
+    assert ops._auto_split(24 * 16, 512, 4) == 1               # too little K to split
+    for rows in (96, 384, 1152, 1536, 4608):
+        for n in (256, 512, 1024, 2048):
+            for kb in (16, 64, 144, 256, 288):
+                for groups in (1, 4):
+                    s = ops._auto_split(rows, n, kb, groups)
+                    tiles = -(-rows // 128) * (n // 256) * groups
+                    assert 1 <= s <= max(1, kb // 8)
+                    if s > 1:   # a split launch is a whole number of (nearly) full waves, or a single partial one
+                        waves = -(-tiles * s // n_sm)
+                        assert tiles * s > (waves - 1) * n_sm + n_sm // 2 or waves == 1, (rows, n, kb, groups, s)
