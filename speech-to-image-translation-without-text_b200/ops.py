@@ -219,7 +219,16 @@ def conv_wgrad(kind, x, dy, dwpk, splitk=None, flop_scale=1.0):
         ktiles = max(1, pix // 64)
         bn = 16 if Cin <= 16 else (32 if Cin <= 32 else (64 if Cin <= 64 else (128 if Cin <= 128 else 256)))
         ctas = -(-Cout // 128) * -(-Cin // bn) * JOBS[kind]
-        splitk = max(1, min(ktiles // 2 if ktiles >= 2 else 1, -(-2 * N_SM // ctas)))
+        smax = ktiles // 2 if ktiles >= 2 else 1
+        splitk = max(1, min(smax, -(-2 * N_SM // ctas)))
+        if os.environ.get("SG2_WGRAD_WAVES", "0") == "1":
+            # not measured yet (round 2 A/B): the wave accounting of _auto_split for the one-CTA-per-tap wgrad kernel
+            best, best_cost = 1, None
+            for sp in range(1, max(1, min(smax, 64)) + 1):
+                cost = -(-ctas * sp // N_SM) * (ktiles / sp + 4.0)
+                if best_cost is None or cost < best_cost - 1e-9:
+                    best, best_cost = sp, cost
+            splitk = best
     _conv_call("sg2_conv_wgrad", 1, fl, kind, _p(x), _p(dy), _p(dwpk), B, H, W, Cin, Cout, splitk, _st())
 
 
