@@ -61,7 +61,7 @@ int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad, int Cout, int Cin
  *   dgrad : dy (shape of y) -> dx [B][H][W][Cin]
  *   wgrad : dwpk[Cout][jobs][Cin] += dy^T (x) im2col(x)   (fp32, red.global.add)
  * out_mode: SG2_OUT_BF16 store, SG2_OUT_F32_ATOMIC (split-K accumulate into a zeroed fp32 buffer), SG2_OUT_F32_STORE.
- * stats (fprop, optional): fp32 [2][Cout], += per-channel sum and sum of squares of the bf16 outputs, computed in the
+ * stats (fprop, optional): fp64 [2][Cout], += per-channel sum and sum of squares of the bf16 outputs, computed in the
  * epilogue from the TMEM accumulators (the BatchNorm batch statistics, consumed by sg2_bn_act_fwd). stats_groups > 1:
  * the batch is `stats_groups` equal sub-batches with separate statistics, stats [groups][2][Cout]; returns SG2_ENOFUSE
  * when a pixel tile of this shape would straddle two sub-batches (use sg2_bn_stats then).
@@ -70,7 +70,7 @@ int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad, int Cout, int Cin
  * (ry*3+rx) applies to the pixels of border class ry = {top row, interior, bottom row} x rx = {left, interior, right}
  * (see sg2_joint_bias: the broadcast c_code channels of a jointConv folded into a per-sample bias). */
 int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mode, int B, int H, int W, int Cin,
-                   int Cout, int splitk, float* stats, int stats_groups, int act, const float* bias9, void* stream);
+                   int Cout, int splitk, double* stats, int stats_groups, int act, const float* bias9, void* stream);
 /* dgrad epilogue operand (optional): epi_src has the shape of dx (bf16). SG2_EPI_ADD: dx = dgrad + epi_src (the skip
  * branch of a ResBlock's backward, model.py:166-169). SG2_EPI_LRELU_MASK: dx = dgrad * (epi_src > 0 ? 1 : 0.2), the
  * backward of the LeakyReLU(0.2) that produced epi_src (D stems, model.py:383-384). Returns SG2_ENOFUSE for shapes that
@@ -78,8 +78,23 @@ int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mo
 enum { SG2_EPI_NONE = 0, SG2_EPI_ADD = 1, SG2_EPI_LRELU_MASK = 2 };
 int sg2_conv_dgrad(int kind, const void* dy, const void* wpkT, void* dx, int out_mode, int B, int H, int W, int Cin,
                    int Cout, int splitk, const void* epi_src, int epi_mode, void* stream);
+/* wgrad, deterministic mode (partials != NULL): every pixel split (gather kernel: `splitk` splits; tile kernel: its CTA
+ * lanes) STORES its partial result into its own slab partials[s][Cout][jobs][Cin]; sum them in slab order with
+ * sg2_reduce_slabs. sg2_conv_wgrad_slabs returns how many slabs this shape / splitk writes (>= 1; negative = error).
+ * partials == NULL: fp32 red.global.add straight into dwpk (faster for large weights with few splits, summation order
+ * not reproducible run to run). */
 int sg2_conv_wgrad(int kind, const void* x, const void* dy, float* dwpk, int B, int H, int W, int Cin, int Cout,
-                   int splitk, void* stream);
+                   int splitk, float* partials, void* stream);
+int sg2_conv_wgrad_slabs(int kind, int B, int H, int W, int Cin, int Cout, int splitk);
+/* dst[i] (=|+=) sum_s parts[s * slab + i], s in order (n, slab multiples of 4; 16-byte aligned pointers). */
+int sg2_reduce_slabs(const float* parts, int nslabs, long long n, long long slab, float* dst, int accumulate,
+                     void* stream);
+/* Split-K fprop / dgrad, deterministic mode: sg2_conv_fprop / sg2_conv_dgrad with SG2_OUT_F32_STORE and splitk > 1 store
+ * split s into slab s (y + s * B*Ho*Wo*Cout floats); this sums the slabs in order, applies the optional dgrad epilogue
+ * operand (SG2_EPI_*), rounds to bf16 [P][C] and (stats != NULL) accumulates the BatchNorm statistics of the rounded
+ * values. nsplit == 1: a plain fp32 -> bf16 conversion (+ statistics). */
+int sg2_splitk_finish(const float* parts, int nsplit, long long slab, void* y, long long P, int C, int groups,
+                      double* stats, const void* epi_src, int epi_mode, void* stream);
 
 /* ---- jointConv with the broadcast c_code folded away (NEXT_STAGE_G, model.py:274-279) ---------------------------
  * conv3x3(cat(c (x) 1, h)) = conv3x3_h(h) + bias9[b][border class][o]: the c_code channels are constant over the image,
@@ -88,32 +103,32 @@ int sg2_conv_wgrad(int kind, const void* x, const void* dy, float* dwpk, int B, 
  * first E input channels (model.py:277 puts c_code first).
  *   sg2_joint_bias     : c [B][E] -> bias9 [B][9][Cout]
  *   sg2_joint_tap_sums : dy [B][H][W][Cout] bf16 -> S [B][9 taps][Cout] = sum of dy over the pixels where the tap is
- *                        inside the image (R: fp32 [B][9][Cout] ZEROED workspace). Two launches.
+ *                        inside the image (R: fp64 [B][9][Cout] ZEROED workspace). Two launches.
  *   sg2_joint_c_bwd    : dw[o][e][tap] (=|+=) sum_b c[b][e] S[b][tap][o] (same strides as w; NULL to skip);
  *                        dc[b][e] += sum_{o,tap} w[o][e][tap] S[b][tap][o] (NULL to skip). One launch each. */
 int sg2_joint_bias(const float* c, const float* w, long long so, long long se, long long st, float* bias9, int B, int E,
                    int Cout, void* stream);
-int sg2_joint_tap_sums(const void* dy, float* R, float* S, int B, int H, int W, int Cout, void* stream);
+int sg2_joint_tap_sums(const void* dy, double* R, float* S, int B, int H, int W, int Cout, void* stream);
 int sg2_joint_c_bwd(const float* S, const float* c, const float* w, long long so, long long se, long long st, float* dc,
                     float* dw, int dw_accumulate, int B, int E, int Cout, void* stream);
 
 /* ---- BatchNorm (+ GLU / LeakyReLU(0.2) / residual) on [P pixels][C channels] bf16 ---------------------
  * nn.BatchNorm2d/1d train mode (model.py:137,147,158,161,218,361,372,387-394): batch mean, biased variance,
  * eps, momentum; running_var gets the unbiased variance; num_batches_tracked += 1.
- * stats: fp32 [2][C] per-channel sum / sum of squares, accumulated (+=) into a ZEROED workspace either by the conv
+ * stats: fp64 [2][C] per-channel sum / sum of squares, accumulated (+=) into a ZEROED workspace either by the conv
  * epilogue (sg2_conv_fprop), by sg2_f32_to_bf16_stats (split-K accumulators, fc outputs) or by sg2_bn_stats.
  * groups > 1: the P rows are `groups` consecutive equal slabs (sub-batches), each normalised on its OWN statistics
  * (stats [groups][2][C], mean/rstd [groups][C], sums [groups][2][C]) — the same arithmetic as `groups` separate
  * nn.BatchNorm calls (train_Dnet's real / wrong / fake passes, trainer.py:390-392); running statistics are updated
  * once per group in order, num_batches_tracked += groups, dgamma/dbeta sum over the groups. */
-int sg2_bn_stats(const void* x, long long P, int C, int groups, float* stats, void* stream);
-int sg2_f32_to_bf16_stats(const float* x, void* y, long long P, int C, int groups, float* stats, void* stream);
+int sg2_bn_stats(const void* x, long long P, int C, int groups, double* stats, void* stream);
+int sg2_f32_to_bf16_stats(const float* x, void* y, long long P, int C, int groups, double* stats, void* stream);
 int sg2_bn_eval_prepare(const float* running_mean, const float* running_var, float eps, float* mean, float* rstd,
                         int C, void* stream);
 /* out = act(bn(x)) (+ residual, ACT_NONE only). GLU (model.py:112-122) halves the channel count.
  * train: stats != NULL -> mean/rstd are derived in-kernel, written to mean/rstd (saved for backward) and the running
  * statistics are updated.  eval: stats == NULL, mean/rstd are inputs.  mean == NULL: no BatchNorm (D stem). */
-int sg2_bn_act_fwd(const void* x, const float* stats, float* mean, float* rstd, const float* gamma, const float* beta,
+int sg2_bn_act_fwd(const void* x, const double* stats, float* mean, float* rstd, const float* gamma, const float* beta,
                    const void* residual, void* out, long long P, int C, int groups, int act, float eps, float momentum,
                    float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
 /* dx (shape of x) from dout (shape of out); dgamma/dbeta (=|+=). sums: fp64 [2][C] ZEROED workspace. Two launches. */
@@ -156,8 +171,11 @@ int sg2_ca_glu_reparam_bwd(const float* fc, const float* eps, const float* dmu, 
 int sg2_chw_hwc_bf16(const void* in, void* out, int B, int C, int HW, int to_hwc, void* stream);
 /* D logits: conv k4 s4 C->1 + bias + sigmoid on a 4x4 map (model.py:414-422) */
 int sg2_logits_fwd(const void* x, const float* w, const float* bias, float* prob, int B, int HW, int C, void* stream);
+int sg2_logits_bwd_scratch_floats(int B, int HW, int C);
 int sg2_logits_bwd(const float* dprob, const float* prob, const void* x, const float* w, void* dx, int dx_accumulate,
-                   float* dw /* += */, float* dbias /* += */, int B, int HW, int C, void* stream);
+                   float* dw /* += */, float* dbias /* += */,
+                   float* dw_scratch /* sg2_logits_bwd_scratch_floats() floats when dw != NULL: per-sample-chunk partials */,
+                   int B, int HW, int C, void* stream);
 /* ---- losses (trainer.py:54-58, 298-311, 394-409, 439-446, 499) ---------------------------------------------
  * loss is a device scalar that the kernels ADD to (zero it first). probs/dprobs are contiguous [nvec][B]. */
 int sg2_gan_bce(const float* probs, const float* targets, const float* weights, int nvec, int B, float* loss,

@@ -37,9 +37,11 @@ class Cfg:
 BN_EPS, BN_MOM = 1e-5, 0.1
 
 # bf16 emulation: when EMULATE_BF16 is set, every tensor the CUDA path stores in bf16 (conv operands, conv outputs,
-# activation outputs) is rounded to bf16 here too, with a straight-through gradient. The arithmetic in between stays
-# fp32 (the tensor cores accumulate in fp32). Used by the GPU parity tests to separate "kernel computes the same
-# function" (tight tolerance vs the emulating oracle) from "bf16 storage vs the fp32 reference" (quantisation gap).
+# activation outputs) is rounded to bf16 here too, and so is the gradient that flows back through the same point (the
+# CUDA backward stores dy / dx of every layer in bf16). The arithmetic in between stays fp32 (the tensor cores
+# accumulate in fp32). Used by the GPU parity tests to separate "the kernels compute the same function" (tight
+# tolerance vs the emulating oracle) from "bf16 storage vs the fp32 reference" (quantisation gap, reported).
+# EMULATE_BF16 = "fwd": forward rounding only (straight-through gradients).
 EMULATE_BF16 = False
 
 
@@ -56,10 +58,24 @@ class emulate_bf16:
         EMULATE_BF16 = self.prev
 
 
+class _RoundBoth(torch.autograd.Function):
+    """bf16 rounding of a stored tensor; the gradient stored at the same point is rounded too."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
 def _q(t):
     if not EMULATE_BF16:
         return t
-    return t + (t.detach().bfloat16().float() - t.detach())
+    if EMULATE_BF16 == "fwd" or not t.requires_grad:
+        return t + (t.detach().bfloat16().float() - t.detach())
+    return _RoundBoth.apply(t)
 
 
 def _conv(x, w, **kw):
@@ -124,7 +140,15 @@ def g_forward(sd, z, emb, eps, cfg, training=True):
         p = f"h_net{stage}"
         s = h.size(2)
         cc = c.view(-1, cfg.EMBEDDING_DIM, 1, 1).repeat(1, 1, s, s)        # model.py:272-277
-        h = _block3x3_glu(torch.cat((_q(cc), h), 1), sd, p + ".jointConv", training)
+        if EMULATE_BF16:
+            # the CUDA path folds the broadcast c_code channels into an fp32 per-sample bias (fp32 c, fp32 master
+            # weights); only the h part goes through bf16 operands. Same function, different rounding points.
+            w = sd[p + ".jointConv.0.weight"]
+            e = cfg.EMBEDDING_DIM
+            y = _q(F.conv2d(_q(h), _q(w[:, e:]), padding=1) + F.conv2d(cc, w[:, :e], padding=1))
+            h = glu(_bn(y, sd, p + ".jointConv.1", training))
+        else:
+            h = _block3x3_glu(torch.cat((cc, h), 1), sd, p + ".jointConv", training)
         for r in range(cfg.R_NUM):
             h = _res_block(h, sd, f"{p}.residual.{r}", training)
         h = _up_block(h, sd, p + ".upsample", training)

@@ -1,6 +1,8 @@
 """The cfg keys the hot path reads, with the reference's defaults (StackGAN_v2/miscc/config.py:9-69 and
-cfg/birds_3stages.yml). When the reference's own `miscc.config.cfg` is importable (running under the reference's
-main.py) that object is used instead, so cfg/*.yml files keep working unchanged."""
+cfg/birds_3stages.yml). Under the reference's own main.py, `utils.install_as_reference_model()` binds the reference's
+`miscc.config.cfg` object instead (bind_reference_cfg), so cfg/*.yml files keep working unchanged. The binding is
+explicit: merely having `miscc.config` imported somewhere in the process (e.g. by the oracle's reference loader in the
+tests) does not change which cfg the sg2b200 modules read."""
 import sys
 from types import SimpleNamespace
 
@@ -18,9 +20,30 @@ def default_cfg():
 
 
 cfg = default_cfg()
+_bound = None          # explicit override (the reference's cfg object), see bind_reference_cfg()
+_use_reference = False
+
+
+def bind_reference_cfg(obj=None):
+    """Make G_NET() / D_NETxx() read `obj` (default: the reference's `miscc.config.cfg`, resolved lazily when a
+    network is constructed, because main.py imports miscc.config before it builds the networks). `unbind_cfg()` undoes it."""
+    global _bound, _use_reference
+    _bound = obj
+    _use_reference = obj is None
+
+
+def unbind_cfg():
+    global _bound, _use_reference
+    _bound, _use_reference = None, False
 
 
 def active_cfg():
-    """The reference's global cfg if its miscc.config is already imported, else ours."""
-    m = sys.modules.get("miscc.config")
-    return m.cfg if m is not None and hasattr(m, "cfg") else cfg
+    """The cfg the modules read: an explicitly bound object, the reference's global cfg after
+    install_as_reference_model(), else this package's own `cfg`."""
+    if _bound is not None:
+        return _bound
+    if _use_reference:
+        m = sys.modules.get("miscc.config")
+        if m is not None and hasattr(m, "cfg"):
+            return m.cfg
+    return cfg

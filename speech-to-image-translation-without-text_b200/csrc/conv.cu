@@ -95,6 +95,15 @@ static int make_w_map(CUtensorMap* m, const void* w, long long rows, long long K
   return 0;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device (context): remember it per device ordinal, not per process.
+static bool attr_needed(bool (&done)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 // Pipeline depth: as many stages as fit the per-CTA shared-memory budget (default 100 KB so that two CTAs
 // co-reside per SM and one's epilogue overlaps the other's main loop); SG2_SMEM_BUDGET_KB overrides.
 static int max_stages(int stage_bytes) {
@@ -134,7 +143,8 @@ struct GatherDesc {
   void* out;
   long long out_off[4], osx, osy, osb;
   int out_mode, splitk;
-  float* stats;
+  long long split_stride;  // elements between the split-K slabs of an OUT_F32_STORE output
+  double* stats;
   int stats_bg;  // images per statistics group (0: one)
   int act;  // epilogue activation (tile kernel only): 0 none, 2 LeakyReLU(0.2)
   const float* bias9;  // [B][9][N] border-region bias (tile kernel only)
@@ -159,7 +169,10 @@ static int launch_fprop_t(const GatherDesc& d, cudaStream_t st) {
   p.ngroups = d.ngroups;
   const int KB = p.ntaps * p.kchunks;
   p.splitk = d.splitk < 1 ? 1 : (d.splitk > KB ? KB : d.splitk);
-  if (p.splitk > 1 && d.out_mode != OUT_F32_ATOMIC) SG2_FAIL(SG2_EINVAL, "split-K needs SG2_OUT_F32_ATOMIC");
+  if (p.splitk > 1 && d.out_mode == OUT_BF16) SG2_FAIL(SG2_EINVAL, "split-K needs an fp32 output mode");
+  if (p.splitk != d.splitk && d.splitk > 1 && d.out_mode == OUT_F32_STORE)
+    SG2_FAIL(SG2_EINVAL, "split-K slabs: %d splits requested, only %d K blocks", d.splitk, KB);
+  p.split_stride = d.split_stride;
   p.tiles_x = (d.Wg + p.tw - 1) / p.tw;
   p.tiles_y = (d.Hg + p.th - 1) / p.th;
   p.tiles_b = (d.B + p.nb - 1) / p.nb;
@@ -184,12 +197,11 @@ static int launch_fprop_t(const GatherDesc& d, cudaStream_t st) {
   if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = Cfg::smem_bytes(stages);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};
+  if (attr_needed(attr_done)) {
     cudaError_t e = cudaFuncSetAttribute(igemm_fprop_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::smem_bytes(smax));
     if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(fprop<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
-    attr_done = true;
   }
   dim3 grid(p.tiles_x * p.tiles_y * p.tiles_b, d.N / BN, p.ngroups * p.splitk);
   igemm_fprop_kernel<BN, BK><<<grid, kNumThreads, smem, st>>>(p);
@@ -371,11 +383,10 @@ static int launch_tile_t(const GatherDesc& d, TilePlan& pl, cudaStream_t st) {
   for (int s = 0; s < d.nmaps; ++s)
     if ((rc = make_act_map(&p.tmA[s], d.a[s], BK, p.pitch, p.ph, 1))) return rc;
   if ((rc = make_w_map(&p.tmB, d.w, (long long)d.ngroups * d.N, (long long)d.ntaps * d.Cin, BK, BN))) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};
+  if (attr_needed(attr_done)) {
     cudaError_t e = cudaFuncSetAttribute(tile_conv_kernel<BN, BK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
     if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(tile_conv<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
-    attr_done = true;
   }
   tile_conv_kernel<BN, BK, NT><<<dim3(p.ngroups * p.n_tiles * p.lanes), kTileThreads, pl.smem, st>>>(p);
   cudaError_t e = cudaGetLastError();
@@ -442,6 +453,8 @@ struct WgradDesc {
   int Cout, Cin;
   float* dw;
   int splitk;
+  float* partials;  // deterministic mode: per-split / per-lane slabs (each laid out like dw), summed by the caller
+  int* slabs_out;   // plan only: receives the number of slabs this launch would write; nothing is launched
 };
 
 template <int BN, int CWA, int CWB>
@@ -451,6 +464,11 @@ static int launch_wgrad_t(const WgradDesc& d, cudaStream_t st) {
   memset(&p, 0, sizeof(p));
   int rc;
   if ((rc = pick_tile(d.Wg, d.Hg, kWgradBKP, &p.tw, &p.th, &p.nb))) return rc;
+  if (d.slabs_out) {
+    const int pt = ((d.Wg + p.tw - 1) / p.tw) * ((d.Hg + p.th - 1) / p.th) * ((d.B + p.nb - 1) / p.nb);
+    *d.slabs_out = d.splitk < 1 ? 1 : (d.splitk > pt ? pt : d.splitk);
+    return 0;
+  }
   for (int i = 0; i < d.namaps; ++i)
     if ((rc = make_act_map(&p.tmA[i], d.a[i], CWA, p.tw, p.th, p.nb))) return rc;
   for (int i = 0; i < d.nbmaps; ++i)
@@ -465,17 +483,18 @@ static int launch_wgrad_t(const WgradDesc& d, cudaStream_t st) {
   p.Cout = d.Cout;
   p.Cin = d.Cin;
   p.dw = d.dw;
+  p.partials = d.partials;
+  p.slab = (long long)d.Cout * d.njobs * d.Cin;
   const int smax = max_stages(Cfg::kStageBytes);
   int stages = smax;
   if (stages > PT / p.splitk + 1) stages = PT / p.splitk + 1;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};
+  if (attr_needed(attr_done)) {
     cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_kernel<BN, CWA, CWB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes(smax));
     if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
-    attr_done = true;
   }
   const int m_tiles = (d.Cout + kBlockM - 1) / kBlockM, n_tiles = (d.Cin + BN - 1) / BN;
   dim3 grid(m_tiles * n_tiles, d.njobs, p.splitk);
@@ -592,9 +611,15 @@ static int launch_tile_wgrad(const WgradDesc& d, cudaStream_t st) {
   if (lanes > pix_tiles) lanes = pix_tiles;
   if (lanes < 1) lanes = 1;
   p.lanes = lanes;
+  p.partials = d.partials;
+  p.slab = (long long)d.Cout * d.njobs * d.Cin;
   const int stage_bytes = (kBlockM / cwa) * p.a_chunk_bytes + p.b_chunks * p.b_chunk_bytes;
   int stages = (200 * 1024) / stage_bytes;
   if (stages < 2) return 1;
+  if (d.slabs_out) {
+    *d.slabs_out = lanes;
+    return 0;
+  }
   if (stages > 4) stages = 4;
   p.stages = stages;
   {
@@ -615,11 +640,10 @@ static int launch_tile_wgrad(const WgradDesc& d, cudaStream_t st) {
     if ((rc = make_act_map(&p.tmA[i], d.a[i], cwa, kTileW, kTileH, 1))) return rc;
   for (int i = 0; i < d.nbmaps; ++i)
     if ((rc = make_act_map(&p.tmB[i], d.b[i], cwb, p.pitch, p.ph, 1))) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};
+  if (attr_needed(attr_done)) {
     cudaError_t e = cudaFuncSetAttribute(tile_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
     if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(tile_wgrad): %s", cudaGetErrorString(e));
-    attr_done = true;
   }
   const size_t smem = size_t(stages) * stage_bytes + 1024 + 256;
   tile_wgrad_kernel<<<dim3(base * lanes), kNumThreads, smem, st>>>(p);
@@ -662,7 +686,7 @@ int sg2_version(void) { return 1; }
 const char* sg2_last_error(void) { return g_err; }
 
 int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mode, int B, int H, int W, int Cin,
-                   int Cout, int splitk, float* stats, int stats_groups, int act, const float* bias9, void* stream) {
+                   int Cout, int splitk, double* stats, int stats_groups, int act, const float* bias9, void* stream) {
   GatherDesc d;
   memset(&d, 0, sizeof(d));
   d.stats = stats;
@@ -749,6 +773,7 @@ int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mo
     default:
       SG2_FAIL(SG2_EINVAL, "unknown conv kind %d", kind);
   }
+  d.split_stride = (long long)B * d.Hg * d.Wg * d.ngroups * Cout;   // one dense output tensor per split-K slab
   return launch_fprop(d, (cudaStream_t)stream);
 }
 
@@ -838,13 +863,33 @@ int sg2_conv_dgrad(int kind, const void* dy, const void* wpkT, void* dx, int out
     default:
       SG2_FAIL(SG2_EINVAL, "unknown conv kind %d", kind);
   }
+  d.split_stride = (long long)B * H * W * Cin;
   return launch_fprop(d, (cudaStream_t)stream);
 }
 
+static int wgrad_entry(int kind, const void* x, const void* dy, float* dwpk, int B, int H, int W, int Cin, int Cout,
+                       int splitk, float* partials, int* slabs_out, void* stream);
+
 int sg2_conv_wgrad(int kind, const void* x, const void* dy, float* dwpk, int B, int H, int W, int Cin, int Cout,
-                   int splitk, void* stream) {
+                   int splitk, float* partials, void* stream) {
+  return wgrad_entry(kind, x, dy, dwpk, B, H, W, Cin, Cout, splitk, partials, nullptr, stream);
+}
+
+int sg2_conv_wgrad_slabs(int kind, int B, int H, int W, int Cin, int Cout, int splitk) {
+  int n = 0;
+  // the plan only looks at extents; any 16-byte aligned non-null pointers will do for the views
+  static const uintptr_t dummy = 4096;
+  const int rc = wgrad_entry(kind, (const void*)dummy, (const void*)dummy, (float*)dummy, B, H, W, Cin, Cout, splitk,
+                             nullptr, &n, nullptr);
+  return rc ? (rc < 0 ? rc : -rc) : n;
+}
+
+static int wgrad_entry(int kind, const void* x, const void* dy, float* dwpk, int B, int H, int W, int Cin, int Cout,
+                       int splitk, float* partials, int* slabs_out, void* stream) {
   WgradDesc d;
   memset(&d, 0, sizeof(d));
+  d.partials = partials;
+  d.slabs_out = slabs_out;
   d.B = B;
   d.Cout = Cout;
   d.Cin = Cin;

@@ -245,17 +245,21 @@ __global__ void unpack_wgrad_kernel(int kind, const float* __restrict__ dwpk, fl
 }
 
 // ============================================================================================ BN statistics
-// Per-channel sum / sum of squares of a [P][C] tensor into a ZEROED fp32 workspace stats[2][C] (fp32 atomics).
-// IN_F32: the input is a split-K fp32 accumulator; it is rounded to bf16 on the way (written to `y`) and the
-// statistics are those of the rounded values (what BatchNorm-apply reads back).
+// Per-channel sum / sum of squares of a [P][C] tensor into a ZEROED fp64 workspace stats[2][C]. Each block forms its
+// partial sums in a fixed order in fp32; blocks combine with fp64 atomics (order-independent beyond 2^-53).
+// IN_F32: the input is `nsplit` fp32 split-K slabs (slab s at xin + s * slab elements) that are summed in slab order,
+// optionally combined with an epilogue operand (epi_mode 1: += src, 2: *= LeakyReLU'(src)), rounded to bf16 (written
+// to `y`); the statistics (optional) are those of the rounded values (what BatchNorm-apply reads back).
 template <bool IN_F32>
 __global__ void bn_stats_kernel(const void* __restrict__ xin, uint4* __restrict__ y, long long P, int vc, int cpb,
-                                int rpb, float* __restrict__ stats, int C) {
+                                int rpb, double* __restrict__ stats, int C, int nsplit, long long slab,
+                                const uint4* __restrict__ epi_src, int epi_mode) {
   // blockIdx.z = statistics group: rows [z * P, (z + 1) * P) of the tensor, sums into stats[z][2][C]
   if (IN_F32) xin = reinterpret_cast<const float*>(xin) + (long long)blockIdx.z * P * C;
   else xin = reinterpret_cast<const uint4*>(xin) + (long long)blockIdx.z * P * vc;
   if (y) y += (long long)blockIdx.z * P * vc;
-  stats += (long long)blockIdx.z * 2 * C;
+  if (epi_src) epi_src += (long long)blockIdx.z * P * vc;
+  if (stats) stats += (long long)blockIdx.z * 2 * C;
   const int col = blockIdx.x * cpb + threadIdx.x % cpb;
   const int rl = threadIdx.x / cpb;
   float s[8], q[8];
@@ -266,8 +270,21 @@ __global__ void bn_stats_kernel(const void* __restrict__ xin, uint4* __restrict_
     float f[8];
     if (IN_F32) {
       const float4* x4 = reinterpret_cast<const float4*>(xin) + (r * vc + col) * 2;
-      const float4 lo = x4[0], hi = x4[1];
-      const float t[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      float4 lo = x4[0], hi = x4[1];
+      for (int sp = 1; sp < nsplit; ++sp) {
+        const float4* xs = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xin) + (long long)sp * slab) +
+                           (r * vc + col) * 2;
+        const float4 a = xs[0], b = xs[1];
+        lo.x += a.x; lo.y += a.y; lo.z += a.z; lo.w += a.w;
+        hi.x += b.x; hi.y += b.y; hi.z += b.z; hi.w += b.w;
+      }
+      float t[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      if (epi_mode) {
+        float e[8];
+        unpack8(epi_src[r * vc + col], e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = epi_mode == 1 ? t[j] + e[j] : (e[j] > 0.f ? t[j] : 0.2f * t[j]);
+      }
       const uint4 pk = pack8(t);
       y[r * vc + col] = pk;
       unpack8(pk, f);
@@ -277,6 +294,7 @@ __global__ void bn_stats_kernel(const void* __restrict__ xin, uint4* __restrict_
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
   }
+  if (!stats) return;
   __shared__ float sh[2][256][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sh[0][threadIdx.x][j] = s[j]; sh[1][threadIdx.x][j] = q[j]; }
@@ -287,17 +305,35 @@ __global__ void bn_stats_kernel(const void* __restrict__ xin, uint4* __restrict_
       for (int j = 0; j < 8; ++j) { s[j] += sh[0][threadIdx.x + k * cpb][j]; q[j] += sh[1][threadIdx.x + k * cpb][j]; }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&stats[col * 8 + j], s[j]);
-      atomicAdd(&stats[C + col * 8 + j], q[j]);
+      atomicAdd(&stats[col * 8 + j], (double)s[j]);
+      atomicAdd(&stats[C + col * 8 + j], (double)q[j]);
     }
   }
 }
 
+// dst[i] (=|+=) sum over the slabs, in slab order (deterministic counterpart of the red.global.add split reductions)
+__global__ void reduce_slabs_kernel(const float4* __restrict__ parts, int nslabs, long long n4, long long slab4,
+                                    float4* __restrict__ dst, int accumulate) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 a = parts[i];
+    for (int sp = 1; sp < nslabs; ++sp) {
+      const float4 b = parts[(long long)sp * slab4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (accumulate) {
+      const float4 d = dst[i];
+      a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
+    }
+    dst[i] = a;
+  }
+}
+
 // batch mean / rstd of channel c from the accumulated sums (biased variance, like nn.BatchNorm in train mode)
-__device__ __forceinline__ void stat_mean_rstd(const float* __restrict__ stats, int C, int c, double invP, float eps,
+__device__ __forceinline__ void stat_mean_rstd(const double* __restrict__ stats, int C, int c, double invP, float eps,
                                                float& m, float& r, float& var_out) {
-  const double mm = (double)stats[c] * invP;
-  double var = (double)stats[C + c] * invP - mm * mm;
+  const double mm = stats[c] * invP;
+  double var = stats[C + c] * invP - mm * mm;
   if (var < 0) var = 0;
   m = (float)mm;
   r = (float)(1.0 / sqrt(var + (double)eps));
@@ -380,7 +416,7 @@ __global__ void __launch_bounds__(256, 3)
 bn_act_fwd_kernel(const uint2* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
                   const float* __restrict__ gamma, const float* __restrict__ beta, const uint2* __restrict__ residual,
                   uint2* __restrict__ out, long long P, int vc_in, int vc_out, int cpb, int rpb, int has_bn,
-                  const float* __restrict__ stats, float eps, float momentum, float* __restrict__ mean_out,
+                  const double* __restrict__ stats, float eps, float momentum, float* __restrict__ mean_out,
                   float* __restrict__ rstd_out, float* __restrict__ rmean, float* __restrict__ rvar,
                   long long* __restrict__ nbt, int tile_rows, int stages) {
   // stats != NULL: train mode — mean/rstd are derived here from the sums the conv epilogue accumulated; the first
@@ -394,7 +430,7 @@ bn_act_fwd_kernel(const uint2* __restrict__ x, const float* __restrict__ mean, c
   x += (long long)gz * P * vc_in;
   out += (long long)gz * P * vc_out;
   if (residual) residual += (long long)gz * P * vc_out;
-  const float* stats_all = stats;
+  const double* stats_all = stats;
   if (stats) stats += (long long)gz * 2 * C;
   if (mean) { mean += (long long)gz * C; rstd += (long long)gz * C; }
   if (mean_out) { mean_out += (long long)gz * C; rstd_out += (long long)gz * C; }
@@ -931,6 +967,14 @@ template <typename K>
 static void staged_attr(K kernel) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
+// the attribute is per device: remember it per device ordinal
+static bool attr_needed(bool (&done)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
 
 extern "C" {
 
@@ -973,24 +1017,43 @@ int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad, int Cout, int Cin
   return launch_ok("unpack_wgrad");
 }
 
-int sg2_bn_stats(const void* x, long long P, int C, int groups, float* stats, void* stream) {
+int sg2_bn_stats(const void* x, long long P, int C, int groups, double* stats, void* stream) {
   if (C % 8) EW_FAIL(SG2_EINVAL, "bn_stats: C %% 8");
   if (groups < 1 || P % groups) EW_FAIL(SG2_EINVAL, "bn_stats: %lld rows in %d groups", P, groups);
   P /= groups;
   Geo g = make_geo(P, C, 148 * 4);
   g.grid.z = groups;
-  bn_stats_kernel<false><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(x, nullptr, P, g.vc, g.cpb, g.rpb, stats, C);
+  bn_stats_kernel<false><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(x, nullptr, P, g.vc, g.cpb, g.rpb, stats, C, 1,
+                                                                       0, nullptr, 0);
   return launch_ok("bn_stats");
 }
 
-int sg2_f32_to_bf16_stats(const float* x, void* y, long long P, int C, int groups, float* stats, void* stream) {
-  if (C % 8) EW_FAIL(SG2_EINVAL, "f32_to_bf16_stats: C %% 8");
-  if (groups < 1 || P % groups) EW_FAIL(SG2_EINVAL, "f32_to_bf16_stats: %lld rows in %d groups", P, groups);
+int sg2_f32_to_bf16_stats(const float* x, void* y, long long P, int C, int groups, double* stats, void* stream) {
+  return sg2_splitk_finish(x, 1, 0, y, P, C, groups, stats, nullptr, 0, stream);
+}
+
+int sg2_splitk_finish(const float* parts, int nsplit, long long slab, void* y, long long P, int C, int groups,
+                      double* stats, const void* epi_src, int epi_mode, void* stream) {
+  if (C % 8) EW_FAIL(SG2_EINVAL, "splitk_finish: C %% 8");
+  if (groups < 1 || P % groups) EW_FAIL(SG2_EINVAL, "splitk_finish: %lld rows in %d groups", P, groups);
+  if (nsplit < 1 || (nsplit > 1 && slab < P * C)) EW_FAIL(SG2_EINVAL, "splitk_finish: %d slabs of %lld elements", nsplit, slab);
+  if (epi_mode != 0 && epi_mode != SG2_EPI_ADD && epi_mode != SG2_EPI_LRELU_MASK) EW_FAIL(SG2_EINVAL, "splitk_finish: epilogue mode %d", epi_mode);
+  if (epi_mode && !epi_src) EW_FAIL(SG2_EINVAL, "splitk_finish: epilogue operand missing");
   P /= groups;
   Geo g = make_geo(P, C, 148 * 4);
   g.grid.z = groups;
-  bn_stats_kernel<true><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(x, (uint4*)y, P, g.vc, g.cpb, g.rpb, stats, C);
-  return launch_ok("f32_to_bf16_stats");
+  bn_stats_kernel<true><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(parts, (uint4*)y, P, g.vc, g.cpb, g.rpb, stats, C,
+                                                                      nsplit, slab, (const uint4*)epi_src, epi_mode);
+  return launch_ok("splitk_finish");
+}
+
+int sg2_reduce_slabs(const float* parts, int nslabs, long long n, long long slab, float* dst, int accumulate,
+                     void* stream) {
+  if (nslabs < 1 || (n % 4) || (slab % 4)) EW_FAIL(SG2_EINVAL, "reduce_slabs: %d slabs, n %lld, slab %lld", nslabs, n, slab);
+  if ((reinterpret_cast<uintptr_t>(parts) | reinterpret_cast<uintptr_t>(dst)) & 15) EW_FAIL(SG2_EINVAL, "reduce_slabs: 16-byte alignment");
+  reduce_slabs_kernel<<<grid1d(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)parts, nslabs, n / 4, slab / 4,
+                                                                       (float4*)dst, accumulate);
+  return launch_ok("reduce_slabs");
 }
 
 int sg2_bn_eval_prepare(const float* running_mean, const float* running_var, float eps, float* mean, float* rstd,
@@ -1000,7 +1063,7 @@ int sg2_bn_eval_prepare(const float* running_mean, const float* running_var, flo
   return launch_ok("bn_eval_prepare");
 }
 
-int sg2_bn_act_fwd(const void* x, const float* stats, float* mean, float* rstd, const float* gamma, const float* beta,
+int sg2_bn_act_fwd(const void* x, const double* stats, float* mean, float* rstd, const float* gamma, const float* beta,
                    const void* residual, void* out, long long P, int C, int groups, int act, float eps, float momentum,
                    float* running_mean, float* running_var, long long* num_batches_tracked, void* stream) {
   const int Cout = act == ACT_GLU ? C / 2 : C;
@@ -1013,12 +1076,11 @@ int sg2_bn_act_fwd(const void* x, const float* stats, float* mean, float* rstd, 
   if (stats && !mean) EW_FAIL(SG2_EINVAL, "bn_act_fwd: stats given without mean/rstd outputs");
   cudaStream_t st = (cudaStream_t)stream;
   const StagedGeo sg = make_staged(g, P, groups, C / kBnW, Cout / kBnW, false);
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  if (attr_needed(attr)) {
     staged_attr(bn_act_fwd_kernel<ACT_GLU, true>);
     staged_attr(bn_act_fwd_kernel<ACT_LRELU, true>);
     staged_attr(bn_act_fwd_kernel<ACT_NONE, true>);
-    attr = true;
   }
 #define ARGS (const uint2*)x, mean, rstd, gamma, beta, (const uint2*)residual, (uint2*)out, P, C / kBnW, Cout / kBnW, g.cpb, g.rpb, has_bn, stats, eps, momentum, mean, rstd, running_mean, running_var, num_batches_tracked, sg.tile_rows, sg.stages
   if (sg.ok) {
@@ -1046,15 +1108,14 @@ int sg2_bn_act_bwd(const void* x, const void* dout, const float* mean, const flo
   g.grid.z = groups;
   cudaStream_t st = (cudaStream_t)stream;
   const StagedGeo sg = make_staged(g, P, groups, C / kBnW, Cout / kBnW, true);
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  if (attr_needed(attr)) {
     staged_attr(bn_act_bwd_reduce_kernel<ACT_GLU, true>);
     staged_attr(bn_act_bwd_reduce_kernel<ACT_LRELU, true>);
     staged_attr(bn_act_bwd_reduce_kernel<ACT_NONE, true>);
     staged_attr(bn_act_bwd_apply_kernel<ACT_GLU, true>);
     staged_attr(bn_act_bwd_apply_kernel<ACT_LRELU, true>);
     staged_attr(bn_act_bwd_apply_kernel<ACT_NONE, true>);
-    attr = true;
   }
 #define RARGS (const uint2*)x, (const uint2*)dout, mean, rstd, gamma, beta, P, C / kBnW, Cout / kBnW, g.cpb, g.rpb, sums, C, sg.tile_rows, sg.stages
 #define AARGS (const uint2*)x, (const uint2*)dout, mean, rstd, gamma, beta, sums, P, C / kBnW, Cout / kBnW, g.cpb, g.rpb, (uint2*)dx, C, dgamma, dbeta, accumulate, sg.tile_rows, sg.stages

@@ -40,9 +40,11 @@ struct FpropParams {
   void* out;
   int out_mode;
   int stages;
-  float* stats;  // optional [groups][2][N] fp32: per-channel sum / sum of squares of the (bf16-rounded) outputs, += (BN statistics)
+  double* stats;  // optional [groups][2][N] fp64: per-channel sum / sum of squares of the (bf16-rounded) outputs, += (BN statistics)
   int stats_bg;  // images per statistics group (0: one group); a tile never straddles groups (checked on the host)
   int act;       // epilogue activation: 0 none, 2 LeakyReLU(0.2) (layers without BatchNorm: the D stems)
+  long long split_stride;  // OUT_F32_STORE with split-K: split s stores its partial tile into slab s (out + s * split_stride);
+                           // the slabs are summed in split order by sg2_splitk_finish (deterministic, no atomics)
 };
 
 template <int BN, int BK>
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
   uint64_t* empty = full + S;
   uint64_t* tmem_full = empty + S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  __shared__ float s_stats[2 * (BN < 32 ? 32 : BN)];
+  __shared__ float s_stats[4 * 2 * (BN < 32 ? 32 : BN)];   // [TMEM lane quarter][2][SN]: one writer warp per slot
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -164,14 +166,11 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
     const int bi = row / (p.tw * p.th);
     const int x = x0 + xi, y = y0 + yi, b = b0 + bi;
     const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
-    const long long off = p.out_off[g] + (long long)b * p.sb + (long long)y * p.sy + (long long)x * p.sx + n0;
+    const long long off = p.out_off[g] + (long long)b * p.sb + (long long)y * p.sy + (long long)x * p.sx + n0 +
+                          (p.out_mode == OUT_F32_STORE ? (long long)split * p.split_stride : 0);
     const bool do_stats = (p.stats != nullptr) && (p.out_mode == OUT_BF16);
     const int et = threadIdx.x - 64;  // 0..127 within the epilogue warps
     constexpr int SN = BN < 32 ? 32 : BN;
-    if (do_stats) {
-      for (int i = et; i < 2 * SN; i += 128) s_stats[i] = 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
@@ -180,6 +179,10 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
       uint32_t v[32];
       tmem_ld_32x32(taddr + c0, v);
       tmem_ld_wait();
+      if (nkb <= 0) {   // no K block in this split: the accumulator was never written
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
       if (p.act == 2) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -199,8 +202,8 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
         const float cs = warp_transpose_sum(a, lane);
         const float cq = warp_transpose_sum(qq, lane);
         if (c0 + lane < BN) {
-          atomicAdd(&s_stats[c0 + lane], cs);
-          atomicAdd(&s_stats[SN + c0 + lane], cq);
+          s_stats[q * 2 * SN + c0 + lane] = cs;
+          s_stats[q * 2 * SN + SN + c0 + lane] = cq;
         }
       }
       if (valid) {
@@ -233,10 +236,16 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
     }
     if (do_stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      float* st = p.stats + (p.stats_bg > 0 ? (long long)(b0 / p.stats_bg) * 2 * p.N : 0);
+      double* st = p.stats + (p.stats_bg > 0 ? (long long)(b0 / p.stats_bg) * 2 * p.N : 0);
       for (int i = et; i < BN; i += 128) {
-        atomicAdd(&st[n0 + i], s_stats[i]);
-        atomicAdd(&st[p.N + n0 + i], s_stats[SN + i]);
+        float cs = 0.f, cq = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          cs += s_stats[qq * 2 * SN + i];
+          cq += s_stats[qq * 2 * SN + SN + i];
+        }
+        atomicAdd(&st[n0 + i], (double)cs);
+        atomicAdd(&st[p.N + n0 + i], (double)cq);
       }
     }
     tc_fence_before();
@@ -264,6 +273,10 @@ struct WgradParams {
   int Cout, Cin;
   float* dw;  // [Cout][njobs][Cin]
   int stages;
+  // deterministic mode: split s STORES its partial tile into slab s (partials + s * slab elements, each slab laid out
+  // like dw); the caller sums the slabs in order (sg2_reduce_slabs). NULL: red.global.add into dw.
+  float* partials;
+  long long slab;
 };
 
 constexpr int kWgradBKP = 64;  // pixels per K block
@@ -386,7 +399,8 @@ __global__ void __launch_bounds__(kNumThreads) igemm_wgrad_kernel(const __grid_c
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
     const bool valid = m < p.Cout;
-    float* rowp = p.dw + ((long long)m * p.njobs + job) * p.Cin + n0;
+    const bool slabs = p.partials != nullptr;
+    float* rowp = (slabs ? p.partials + (long long)split * p.slab : p.dw) + ((long long)m * p.njobs + job) * p.Cin + n0;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
@@ -395,7 +409,19 @@ __global__ void __launch_bounds__(kNumThreads) igemm_wgrad_kernel(const __grid_c
       uint32_t v[32];
       tmem_ld_32x32(taddr + c0, v);
       tmem_ld_wait();
-      if (valid && nkb > 0) {
+      if (slabs) {
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n0 + c0 + j < p.Cin) {
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3]));
+              if (nkb <= 0) o = make_float4(0.f, 0.f, 0.f, 0.f);
+              *reinterpret_cast<float4*>(rowp + c0 + j) = o;
+            }
+          }
+        }
+      } else if (valid && nkb > 0) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           if (n0 + c0 + j < p.Cin) {

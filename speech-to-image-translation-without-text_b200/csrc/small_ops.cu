@@ -283,12 +283,12 @@ __global__ void logits_fwd_kernel(const __nv_bfloat16* __restrict__ x, const flo
     if (threadIdx.x == 0) prob[b] = sigm(v + bias[0]);
   }
 }
-// dpre[b] = dprob[b] * p (1-p);  dx[b][p][c] (=|+=) dpre[b] * w[c][p];  dw[c][p] += sum_b dpre[b] x[b][p][c];  dbias += sum dpre
+// dpre[b] = dprob[b] * p (1-p);  dx[b][p][c] (=|+=) dpre[b] * w[c][p];  dw_parts[chunk][c][p] = sum_{b in chunk} dpre[b] x[b][p][c];  dbias += sum dpre
 // grid (vectors / 256, sample chunks of kLgChunk): a thread owns one 8-channel vector position for its chunk of samples.
 constexpr int kLgChunk = 8;
 __global__ void logits_bwd_kernel(const float* __restrict__ dprob, const float* __restrict__ prob,
                                   const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
-                                  __nv_bfloat16* __restrict__ dx, int dx_accumulate, float* __restrict__ dw,
+                                  __nv_bfloat16* __restrict__ dx, int dx_accumulate, float* __restrict__ dw_parts,
                                   float* __restrict__ dbias, int B, int HW, int C) {
   const int n = HW * C, nv = n >> 3;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -322,9 +322,10 @@ __global__ void logits_bwd_kernel(const float* __restrict__ dprob, const float* 
       reinterpret_cast<uint4*>(dx)[o] = q;
     }
   }
-  if (dw) {
+  if (dw_parts) {   // this sample chunk's partial, summed over the chunks in order by sg2_reduce_slabs (no atomics)
+    float* dst = dw_parts + (long long)blockIdx.y * n;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&dw[(c + j) * HW + p], gw[j]);
+    for (int j = 0; j < 8; ++j) dst[(c + j) * HW + p] = gw[j];
   }
 }
 
@@ -362,7 +363,7 @@ __global__ void joint_bias_kernel(const float* __restrict__ c, const float* __re
 // R[b][r][o] += sums of dy over the pixels of border class r. grid (H, B): one image row per block (one row class);
 // 256 threads = 8-channel vectors x pixel slots.
 __global__ void __launch_bounds__(256)
-joint_region_sums_kernel(const uint4* __restrict__ dy, float* __restrict__ R, int H, int W, int Cout) {
+joint_region_sums_kernel(const uint4* __restrict__ dy, double* __restrict__ R, int H, int W, int Cout) {
   const int y = blockIdx.x, b = blockIdx.y;
   const int vc = Cout >> 3;                       // vectors per pixel
   const int v = threadIdx.x % vc, slot = threadIdx.x / vc, nslot = blockDim.x / vc;
@@ -371,7 +372,7 @@ joint_region_sums_kernel(const uint4* __restrict__ dy, float* __restrict__ R, in
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  float* Rb = R + ((long long)b * 9 + ry * 3) * Cout + v * 8;
+  double* Rb = R + ((long long)b * 9 + ry * 3) * Cout + v * 8;   // fp64 atomics: the sum does not depend on block order
   // interior columns 1 .. W-2 (branch-free, loads pipelined); the two border columns go straight to their classes
 #pragma unroll 4
   for (int x = 1 + slot; x < W - 1; x += nslot) {
@@ -383,9 +384,9 @@ joint_region_sums_kernel(const uint4* __restrict__ dy, float* __restrict__ R, in
   if (slot < 2) {
     float f[8];
     lg_unpack8(row[(long long)(slot == 0 ? 0 : W - 1) * vc + v], f);
-    float* dst = Rb + (slot == 0 ? 0 : 2) * Cout;
+    double* dst = Rb + (slot == 0 ? 0 : 2) * Cout;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(dst + j, f[j]);
+    for (int j = 0; j < 8; ++j) atomicAdd(dst + j, (double)f[j]);
   }
   __shared__ float sh[256][8];
 #pragma unroll
@@ -396,18 +397,18 @@ joint_region_sums_kernel(const uint4* __restrict__ dy, float* __restrict__ R, in
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += sh[k * vc + v][j];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(Rb + Cout + j, acc[j]);
+    for (int j = 0; j < 8; ++j) atomicAdd(Rb + Cout + j, (double)acc[j]);
   }
 }
 // S[b][tap][o] = sum over the border classes where tap is valid of R[b][r][o]
-__global__ void joint_tap_sums_kernel(const float* __restrict__ R, float* __restrict__ S, int B, int Cout) {
+__global__ void joint_tap_sums_kernel(const double* __restrict__ R, float* __restrict__ S, int B, int Cout) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * 9 * Cout) return;
   const int o = i % Cout, tap = (i / Cout) % 9, b = i / (9 * Cout);
-  float v = 0.f;
+  double v = 0.0;
 #pragma unroll
-  for (int r = 0; r < 9; ++r) v += joint_tap_valid(tap, r) ? R[((long long)b * 9 + r) * Cout + o] : 0.f;
-  S[i] = v;
+  for (int r = 0; r < 9; ++r) v += joint_tap_valid(tap, r) ? R[((long long)b * 9 + r) * Cout + o] : 0.0;
+  S[i] = (float)v;
 }
 // dW[o][e][tap] (=|+=) sum_b c[b][e] * S[b][tap][o].  grid (Cout, 9), threads over e.
 __global__ void joint_dw_kernel(const float* __restrict__ S, const float* __restrict__ c, float* __restrict__ dw,
@@ -420,26 +421,40 @@ __global__ void joint_dw_kernel(const float* __restrict__ S, const float* __rest
     *d = accumulate ? *d + acc : acc;
   }
 }
-// dc[b][e] += sum_{o,tap} W[o][e][tap] * S[b][tap][o].  grid (Cout / 8, 9 taps), threads over e: a thread reads its 8
-// weights once and walks the batch (S of the block's 8 output channels staged in shared memory; fp32 atomics on dc).
-constexpr int kJointMaxB = 128;
-__global__ void joint_dc_kernel(const float* __restrict__ S, const float* __restrict__ w, long long so, long long se,
-                                long long st, float* __restrict__ dc, int B, int E, int Cout) {
-  __shared__ float ss[kJointMaxB][8];
-  const int o0 = blockIdx.x * 8, tap = blockIdx.y;
-  for (int i = threadIdx.x; i < B * 8; i += blockDim.x)
-    ss[i >> 3][i & 7] = S[((long long)(i >> 3) * 9 + tap) * Cout + o0 + (i & 7)];
+// dc[b][e] += sum_{o,tap} W[o][e][tap] * S[b][tap][o].  grid (B), 1024 threads = 8 K-slices x up to 128 channels e:
+// slice k walks the (o, tap) pairs k, k+8, ... (fixed order), the 8 slice sums are combined in slice order through
+// shared memory — deterministic, no atomics. S[b] is staged in shared memory (9 * Cout floats).
+constexpr int kJointSlices = 8;
+__global__ void __launch_bounds__(1024)
+joint_dc_kernel(const float* __restrict__ S, const float* __restrict__ w, long long so, long long se, long long st,
+                float* __restrict__ dc, int E, int Cout) {
+  extern __shared__ float jsm[];            // [9 * Cout] S of this sample, then [kJointSlices][ept] partials
+  const int b = blockIdx.x;
+  const int K = 9 * Cout;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) jsm[i] = S[(long long)b * K + i];   // index = tap * Cout + o
   __syncthreads();
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    float wv[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) wv[k] = w[(o0 + k) * so + e * se + tap * st];
-    for (int b = 0; b < B; ++b) {
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc = fmaf(wv[k], ss[b][k], acc);
-      atomicAdd(&dc[(long long)b * E + e], acc);
+  const int ept = blockDim.x / kJointSlices;   // channels handled per pass
+  const int el = threadIdx.x % ept, ks = threadIdx.x / ept;
+  float* part = jsm + K;
+  for (int e0 = 0; e0 < E; e0 += ept) {
+    const int e = e0 + el;
+    float acc = 0.f;
+    if (e < E) {
+#pragma unroll 4
+      for (int k = ks; k < K; k += kJointSlices) {
+        const int tap = k / Cout, o = k - tap * Cout;
+        acc = fmaf(w[o * so + e * se + tap * st], jsm[k], acc);
+      }
     }
+    part[ks * ept + el] = acc;
+    __syncthreads();
+    if (ks == 0 && e < E) {
+      float t = part[el];
+#pragma unroll
+      for (int k2 = 1; k2 < kJointSlices; ++k2) t += part[k2 * ept + el];
+      dc[(long long)b * E + e] += t;
+    }
+    __syncthreads();
   }
 }
 
@@ -588,8 +603,8 @@ __global__ void cal_coeff_kernel(const float* __restrict__ S, const int* __restr
                                  float* __restrict__ loss, float* __restrict__ G) {
   __shared__ float s_all, s_pair;
   __shared__ int n_pair;
-  if (threadIdx.x == 0) { s_all = 0.f; s_pair = 0.f; n_pair = 0; }
-  __syncthreads();
+  __shared__ float sh_a[32], sh_p[32];
+  __shared__ int sh_n[32];
   float a = 0.f, pr = 0.f;
   int np = 0;
   for (int i = threadIdx.x; i < B * B; i += blockDim.x) {
@@ -598,9 +613,19 @@ __global__ void cal_coeff_kernel(const float* __restrict__ S, const int* __restr
     a += v;
     if (r != c && labels[r] == labels[c]) { pr += v; ++np; }
   }
-  atomicAdd(&s_all, a);
-  atomicAdd(&s_pair, pr);
-  atomicAdd(&n_pair, np);
+  // ordered block reduction (shuffle tree per warp, then the warps in index order): no atomics, reproducible
+  a = warp_sum(a);
+  pr = warp_sum(pr);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) np += __shfl_xor_sync(0xffffffffu, np, o);
+  if ((threadIdx.x & 31) == 0) { sh_a[threadIdx.x >> 5] = a; sh_p[threadIdx.x >> 5] = pr; sh_n[threadIdx.x >> 5] = np; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ta = 0.f, tp = 0.f;
+    int tn = 0;
+    for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) { ta += sh_a[wi]; tp += sh_p[wi]; tn += sh_n[wi]; }
+    s_all = ta; s_pair = tp; n_pair = tn;
+  }
   __syncthreads();
   const float l = (n_pair > 0) ? (s_all / (float)(B * B) - s_pair / (float)n_pair) : 0.f;
   const bool active = (n_pair > 0) && (l > 0.f);
@@ -722,13 +747,21 @@ int sg2_logits_fwd(const void* x, const float* w, const float* bias, float* prob
   SG2_LAUNCH_OK("logits_fwd");
 }
 
+int sg2_logits_bwd_scratch_floats(int B, int HW, int C) { return ((B + kLgChunk - 1) / kLgChunk) * HW * C; }
+
 int sg2_logits_bwd(const float* dprob, const float* prob, const void* x, const float* w, void* dx, int dx_accumulate,
-                   float* dw, float* dbias, int B, int HW, int C, void* stream) {
+                   float* dw, float* dbias, float* dw_scratch, int B, int HW, int C, void* stream) {
   if (C % 8) SG2_FAIL(SG2_EINVAL, "logits_bwd: C=%d not a multiple of 8", C);
+  if (dw && !dw_scratch) SG2_FAIL(SG2_EINVAL, "logits_bwd: dw needs sg2_logits_bwd_scratch_floats() floats of scratch");
   const int nv = HW * C / 8;
-  logits_bwd_kernel<<<dim3((nv + 127) / 128, (B + kLgChunk - 1) / kLgChunk), 128, 0, (cudaStream_t)stream>>>(
-      dprob, prob, (const __nv_bfloat16*)x, w, (__nv_bfloat16*)dx, dx_accumulate, dw, dbias, B, HW, C);
-  SG2_LAUNCH_OK("logits_bwd");
+  const int chunks = (B + kLgChunk - 1) / kLgChunk;
+  logits_bwd_kernel<<<dim3((nv + 127) / 128, chunks), 128, 0, (cudaStream_t)stream>>>(
+      dprob, prob, (const __nv_bfloat16*)x, w, (__nv_bfloat16*)dx, dx_accumulate, dw ? dw_scratch : nullptr, dbias, B, HW, C);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) SG2_FAIL((int)e, "logits_bwd launch: %s", cudaGetErrorString(e));
+  // dw += the chunk partials in chunk order
+  if (dw) return sg2_reduce_slabs(dw_scratch, chunks, (long long)HW * C, (long long)HW * C, dw, 1, stream);
+  return 0;
 }
 
 int sg2_gan_bce(const float* probs, const float* targets, const float* weights, int nvec, int B, float* loss,
@@ -759,7 +792,7 @@ int sg2_joint_bias(const float* c, const float* w, long long so, long long se, l
   SG2_LAUNCH_OK("joint_bias");
 }
 
-int sg2_joint_tap_sums(const void* dy, float* R, float* S, int B, int H, int W, int Cout, void* stream) {
+int sg2_joint_tap_sums(const void* dy, double* R, float* S, int B, int H, int W, int Cout, void* stream) {
   if (Cout % 8 || Cout > 1024) SG2_FAIL(SG2_EINVAL, "joint_tap_sums: Cout=%d", Cout);
   if (H < 2 || W < 2) SG2_FAIL(SG2_EINVAL, "joint_tap_sums: %dx%d image", H, W);
   cudaStream_t st = (cudaStream_t)stream;
@@ -776,8 +809,10 @@ int sg2_joint_c_bwd(const float* S, const float* c, const float* w, long long so
   cudaStream_t s = (cudaStream_t)stream;
   if (dw) joint_dw_kernel<<<dim3(Cout, 9), 128, 0, s>>>(S, c, dw, so, se, st, dw_accumulate, B, E, Cout);
   if (dc) {
-    if (B > kJointMaxB || (Cout % 8)) SG2_FAIL(SG2_EINVAL, "joint_c_bwd: B=%d Cout=%d", B, Cout);
-    joint_dc_kernel<<<dim3(Cout / 8, 9), 128, 0, s>>>(S, w, so, se, st, dc, B, E, Cout);
+    const int ept = E >= 128 ? 128 : (E >= 64 ? 64 : 32);
+    const size_t smem = (size_t)(9 * Cout + kJointSlices * ept) * sizeof(float);
+    if (smem > 48 * 1024) SG2_FAIL(SG2_EINVAL, "joint_c_bwd: Cout=%d too large", Cout);
+    joint_dc_kernel<<<B, kJointSlices * ept, smem, s>>>(S, w, so, se, st, dc, E, Cout);
   }
   SG2_LAUNCH_OK("joint_c_bwd");
 }

@@ -46,7 +46,9 @@ struct TileParams {
   int Wo, Ho, N;
   long long out_off[4], sb, sy, sx;
   void* out;
-  float* stats;    // optional [groups][2][N] fp32 (+=): per-channel sum / sum of squares of the bf16-rounded outputs
+  double* stats;   // optional [groups][2][N] fp64 (+=): per-channel sum / sum of squares of the bf16-rounded outputs.
+                   // Per-CTA partial sums are formed in a fixed order in fp32; the cross-CTA accumulation is an fp64
+                   // atomic, whose result does not depend on the arrival order beyond 2^-53 (run-to-run reproducible)
   int stats_bg;    // images per statistics group (0: the whole batch is one group)
   int stages;      // weight ring depth (ring mode), in stages of `tps` taps
   int tps;         // taps per weight stage (divides the taps of every source)
@@ -240,7 +242,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
   sm.b_full = bars + 12;   // [16]
   sm.b_empty = bars + 28;  // [16]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
-  __shared__ float s_stats[Cfg::kRegStats ? 2 : 2 * Cfg::kSN];
+  // wide tiles (BN > 128): per-TMEM-lane-quarter partial sums, each slot written by exactly one warp (no atomics)
+  __shared__ float s_stats[Cfg::kRegStats ? 2 : 4 * 2 * Cfg::kSN];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -384,7 +387,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
         for (int j = 0; j < 32; ++j) acc_s[ci][j] = acc_q[ci][j] = 0.f;
     } else {
       if (do_stats) {
-        for (int i = et; i < 2 * Cfg::kSN; i += 256) s_stats[i] = 0.f;
+        for (int i = et; i < 4 * 2 * Cfg::kSN; i += 256) s_stats[i] = 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
     int cur_grp = -1;
     auto flush_stats = [&](int grp) {
       if constexpr (Cfg::kRegStats) {
-        float* st = p.stats + (long long)grp * 2 * p.N;
+        double* st = p.stats + (long long)grp * 2 * p.N;
 #pragma unroll
         for (int ci = 0; ci < Cfg::kCPW; ++ci) {
           const int c0 = (half + 2 * ci) * 32;
@@ -400,8 +403,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
             const float cs = warp_transpose_sum(acc_s[ci], lane);
             const float cq = warp_transpose_sum(acc_q[ci], lane);
             if (c0 + lane < BN) {
-              atomicAdd(&st[n0 + c0 + lane], cs);
-              atomicAdd(&st[p.N + n0 + c0 + lane], cq);
+              atomicAdd(&st[n0 + c0 + lane], (double)cs);
+              atomicAdd(&st[p.N + n0 + c0 + lane], (double)cq);
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc_s[ci][j] = acc_q[ci][j] = 0.f;
@@ -513,9 +516,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
                 }
                 const float cs = warp_transpose_sum(a, lane);
                 const float cq = warp_transpose_sum(qq, lane);
-                if (c0 + lane < BN) {
-                  atomicAdd(&s_stats[c0 + lane], cs);
-                  atomicAdd(&s_stats[Cfg::kSN + c0 + lane], cq);
+                if (c0 + lane < BN) {   // this warp is the only writer of quarter q's slots of its column blocks
+                  s_stats[q * 2 * Cfg::kSN + c0 + lane] += cs;
+                  s_stats[q * 2 * Cfg::kSN + Cfg::kSN + c0 + lane] += cq;
                 }
               }
             }
@@ -555,8 +558,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
       } else {
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int i = et; i < BN; i += 256) {
-          atomicAdd(&p.stats[n0 + i], s_stats[i]);
-          atomicAdd(&p.stats[p.N + n0 + i], s_stats[Cfg::kSN + i]);
+          float cs = 0.f, cq = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            cs += s_stats[qq * 2 * Cfg::kSN + i];
+            cq += s_stats[qq * 2 * Cfg::kSN + Cfg::kSN + i];
+          }
+          atomicAdd(&p.stats[n0 + i], (double)cs);
+          atomicAdd(&p.stats[p.N + n0 + i], (double)cq);
         }
       }
     }

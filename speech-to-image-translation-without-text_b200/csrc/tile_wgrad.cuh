@@ -38,6 +38,8 @@ struct TileWgradParams {
   int Cout, Cin;
   float* dw;
   int stages;
+  float* partials;  // deterministic mode: CTA lane l STORES its 128 x (taps x BN) tile into slab l (partials + l * slab,
+  long long slab;   // laid out like dw); the caller sums the `lanes` slabs in order. NULL: red.global.add into dw
   int merge3;  // 1: the three taps of a filter row run as ONE MMA of N = 3 * bn: the x operand's chunk stride (LBO) is one
                //    pixel, so chunk j is the window shifted by j pixels; needs bn == cwb and taps ordered (row, col)
 };
@@ -172,12 +174,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) tile_wgrad_kernel(const __grid
     // ================================================================= epilogue (once per CTA)
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
-    const bool valid = m < p.Cout && my_tiles > 0;
+    const bool slabs = p.partials != nullptr;
+    const bool valid = m < p.Cout && (my_tiles > 0 || slabs);
+    float* const base = slabs ? p.partials + (long long)my_lane * p.slab : p.dw;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
     for (int t = 0; t < ntap; ++t) {
-      float* rowp = p.dw + ((long long)m * p.njobs + p.tap_job[g][tap0 + t]) * p.Cin + n0;
+      float* rowp = base + ((long long)m * p.njobs + p.tap_job[g][tap0 + t]) * p.Cin + n0;
 #pragma unroll 1
       for (int c0 = 0; c0 < p.bn; c0 += 32) {
         uint32_t v[32];
@@ -192,7 +196,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) tile_wgrad_kernel(const __grid
           for (int j = 16; j < 32; ++j) v[j] = 0u;
         }
         tmem_ld_wait();
-        if (valid) {
+        if (valid && slabs) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (c0 + j < p.bn) {
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3]));
+              if (my_tiles <= 0) o = make_float4(0.f, 0.f, 0.f, 0.f);
+              *reinterpret_cast<float4*>(rowp + c0 + j) = o;
+            }
+          }
+        } else if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             if (c0 + j < p.bn) {

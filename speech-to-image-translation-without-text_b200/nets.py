@@ -26,6 +26,11 @@ class ConvOperand:
         self.CiP = cin_pad or self.Cin
         self._key = None
         self.wpk = self.wpkT = self.dwpk = None
+        # Module-API mode: the reference writes weights through `p.data` (load_params' EMA swap for snapshot images and
+        # save_model, trainer.py:78-80,256,592-601; weights_init), which bumps no version counter. Those forwards all run
+        # under torch.no_grad(), so with auto_refresh a no_grad forward always re-packs and leaves the cache invalid for
+        # the next (training) forward. The fused trainer owns its weights and switches this off.
+        self.auto_refresh = True
         # algorithmic / executed FLOP ratio of the padded operand (image heads pad 3 -> 32, stems pad 48 -> 64)
         self.flop_scale = (self.Cout * self.Cin) / float(self.CoP * self.CiP)
 
@@ -40,48 +45,60 @@ class ConvOperand:
         return (self._ohwi() is not None and self.kind in (CONV3, CONV4S2) and self.CoP == self.Cout
                 and self.CiP == self.Cin and self.Cout % 8 == 0 and self.Cin % 8 == 0)
 
+    def _pack_key(self):
+        """(cache key, force): force = re-pack regardless of the key and do not cache (see auto_refresh)."""
+        w = self.weight
+        # _sg2_version: bumped by FlatBucket.adam(), whose kernel updates the weights behind torch's back, and by
+        # utils.load_params / invalidate_packs for writes through `.data`
+        key = (w.data_ptr(), w._version, getattr(w, "_sg2_version", 0), w.device)
+        return key, (self.auto_refresh and not torch.is_grad_enabled())
+
     def packs(self):
         w = self.weight
-        # _sg2_version: bumped by FlatBucket.adam(), whose kernel updates the weights behind torch's back
-        key = (w.data_ptr(), w._version, getattr(w, "_sg2_version", 0), w.device)
+        key, force = self._pack_key()
         oh = self._ohwi()
         if self._direct():
-            if key != self._key:
-                if self._key is None or key[1] != self._key[1]:
+            if force or key != self._key:
+                if force or self._key is None or key[1] != self._key[1] or getattr(w, "_sg2_mirror_stale", False):
                     ops.f32_to_bf16(oh, out=w._sg2_wpk)      # torch-side write to the master: refresh the bf16 mirror
+                    w._sg2_mirror_stale = False
                 self.wpk = w._sg2_wpk
                 if self.wpkT is None or self.wpkT.device != w.device:
                     _, s2 = ops.pack_shapes(self.kind, self.CoP, self.CiP)
                     self.wpkT = torch.empty(s2, device=w.device, dtype=torch.bfloat16)
                 ops.pack_transpose(self.kind, self.wpk, self.wpkT, self.Cout, self.Cin)
-                self._key = key
+                self._key = None if force else key
             return self.wpk, self.wpkT
-        if key != self._key:
+        if force or key != self._key:
             s1, s2 = ops.pack_shapes(GEMM if self.kind == STEM else self.kind, self.CoP, self.CiP)
             if self.wpk is None or self.wpk.device != w.device:
                 self.wpk = torch.empty(s1, device=w.device, dtype=torch.bfloat16)
                 self.wpkT = torch.empty(s2, device=w.device, dtype=torch.bfloat16)
             ops.pack_weights(self.kind, w.detach() if oh is None else oh, self.wpk, self.wpkT, self.Cout, self.Cin,
                              self.CoP, self.CiP, ohwi=oh is not None)
-            self._key = key
+            self._key = None if force else key
         return self.wpk, self.wpkT
 
     def wgrad_begin(self, device, prezeroed=False):
         """prezeroed: the caller cleared the whole flat gradient bucket (direct accumulation needs no fill here)."""
+        self._first = True      # reproducible mode: the first pass writes the accumulator, no clearing needed
         if self._direct():
             self.dwpk = self.weight._sg2_dw
-            if not prezeroed:
+            if not prezeroed and not ops.DETERMINISTIC:
                 self.dwpk.zero_()
             return
         k = GEMM if self.kind == STEM else self.kind
         shape = (self.CoP, ops.JOBS[k], self.CiP)
         if self.dwpk is None or self.dwpk.device != device or self.dwpk.shape != shape:
             self.dwpk = torch.empty(shape, device=device, dtype=torch.float32)
-        self.dwpk.zero_()
+        if not ops.DETERMINISTIC:
+            self.dwpk.zero_()
 
     def wgrad_add(self, x, dy):
-        """dwpk += dy^T im2col(x) (tcgen05 wgrad kernel, fp32 red.global.add)."""
-        ops.conv_wgrad(GEMM if self.kind == STEM else self.kind, x, dy, self.dwpk, flop_scale=self.flop_scale)
+        """dwpk (=|+=) dy^T im2col(x) (tcgen05 wgrad kernel; ordered slab reduction, or fp32 red.global.add)."""
+        ops.conv_wgrad(GEMM if self.kind == STEM else self.kind, x, dy, self.dwpk, flop_scale=self.flop_scale,
+                       first=self._first)
+        self._first = False
 
     def wgrad_finish(self, out=None):
         """packed fp32 accumulator -> fp32 gradient in the master's layout (written into `out` if given)."""
@@ -266,6 +283,9 @@ class JointOperand:
         self._full = ConvOperand(CONV3, weight)      # bf16 [Cout][9][CinFull] of the whole weight (mirror or pack)
         self.wpk = self.wpkT = self.dwpk = None
         self.cparts = []
+        self.auto_refresh = True                      # see ConvOperand
+
+    _pack_key = ConvOperand._pack_key
 
     def w_f32(self):
         """(fp32 master, so, se, st): element (o, e, tap) of the full weight at flat[o*so + e*se + tap*st]."""
@@ -276,32 +296,36 @@ class JointOperand:
 
     def packs(self):
         w = self.weight
-        key = (w.data_ptr(), w._version, getattr(w, "_sg2_version", 0), w.device)
-        if key != self._key:
+        key, force = self._pack_key()
+        if force or key != self._key:
             oh = getattr(w, "_sg2_ohwi", None)
             if oh is not None:
-                if self._key is None or key[1] != self._key[1]:
+                if force or self._key is None or key[1] != self._key[1] or getattr(w, "_sg2_mirror_stale", False):
                     ops.f32_to_bf16(oh, out=w._sg2_wpk)      # torch-side write to the master: refresh the bf16 mirror
+                    w._sg2_mirror_stale = False
                 full = w._sg2_wpk
             else:
+                self._full.auto_refresh = self.auto_refresh
                 full, _ = self._full.packs()
             if self.wpk is None or self.wpk.device != w.device:
                 self.wpk = torch.empty((self.Cout, 9, self.Cin), device=w.device, dtype=torch.bfloat16)
                 self.wpkT = torch.empty((self.Cin, 9, self.Cout), device=w.device, dtype=torch.bfloat16)
             self.wpk.copy_(full.view(self.Cout, 9, self.CinFull)[:, :, self.E:])
             ops.pack_transpose(CONV3, self.wpk, self.wpkT, self.Cout, self.Cin)
-            self._key = key
+            self._key = None if force else key
         return self.wpk, self.wpkT
 
     def wgrad_begin(self, device, prezeroed=False):
         shape = (self.Cout, 9, self.Cin)
         if self.dwpk is None or self.dwpk.device != device:
             self.dwpk = torch.empty(shape, device=device, dtype=torch.float32)
-        self.dwpk.zero_()
-        self._done_c = 0
+        if not ops.DETERMINISTIC:
+            self.dwpk.zero_()
+        self._first = True
 
     def wgrad_add(self, x, dy):
-        ops.conv_wgrad(CONV3, x, dy, self.dwpk)
+        ops.conv_wgrad(CONV3, x, dy, self.dwpk, first=self._first)
+        self._first = False
 
     def wgrad_finish(self, out=None):
         """h part: the packed accumulator goes into the [.., E:] channels of the gradient; c part: c^T S."""
@@ -358,6 +382,9 @@ class JointBlock:
         S = ops.joint_tap_sums(dy)
         ops.joint_c_bwd(S, c, op.w_f32(), dc=dc)
         op.cparts.append((c, S))
+        # S (and c) are read again by wgrad_finish() on the wgrad side stream after this function has returned: keep
+        # them allocated until GradSink.finish() so the main stream's allocator cannot hand the memory out in between
+        sink.keep.append((c, S))
         sink.conv(op, h, dy)
         _, wpkT = op.packs()
         B, H, W, Ch = h.shape
@@ -422,6 +449,10 @@ class GEngine:
 
     def params(self):
         return [p for p in self.net.parameters()]
+
+    def set_auto_refresh(self, flag):
+        for op in self.conv_ops():
+            op.auto_refresh = flag
 
     def conv_ops(self):
         ops_ = [b.op for b in self.ups1] + [h.op for h in self.heads]
@@ -575,6 +606,10 @@ class DEngine:
 
     def params(self):
         return [p for p in self.net.parameters()]
+
+    def set_auto_refresh(self, flag):
+        for op in self.conv_ops():
+            op.auto_refresh = flag
 
     def conv_ops(self):
         return [self.stem.op, self.joint.op] + [b.op for b in self.trunk]

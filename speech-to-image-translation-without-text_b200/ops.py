@@ -18,6 +18,12 @@ N_SM = 148
 
 _launches = 0   # kernels of ours launched through this module (bench.py reports it as gpu_launches)
 
+# Reproducible reductions (default): split-K convolutions store per-split slabs that one pass sums in split order, weight
+# gradients store per-split / per-CTA-lane slabs summed in order, every remaining cross-block sum (BatchNorm statistics,
+# tap sums) is an fp64 atomic over per-block partials formed in a fixed order. SG2_DETERMINISTIC=0 switches the split-K
+# and wgrad reductions back to fp32 red.global.add into a zeroed buffer (order not reproducible run to run).
+DETERMINISTIC = os.environ.get("SG2_DETERMINISTIC", "1") != "0"
+
 
 def launches():
     return _launches
@@ -40,6 +46,13 @@ def _p(t):
     if _prof is not None:
         _prof["keep"].append(t)      # recorded launches are replayed later: their operands must stay allocated
     return t.data_ptr()
+
+
+def _p64(t):
+    """Device pointer of an fp64 workspace (BatchNorm sums, tap sums)."""
+    if t is not None and t.dtype != torch.float64:
+        raise RuntimeError("sg2b200: this workspace is fp64 (torch.float64)")
+    return _p(t)
 
 
 def _call(name, n_launch, *args):
@@ -157,6 +170,12 @@ def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, grou
     if splitk is None:
         splitk = 1 if (act or bias9 is not None) else _auto_split(B * Ho * Wo // pgroups, Cout, taps * max(1, Cin // 64), pgroups)
     if splitk > 1:
+        if DETERMINISTIC:
+            y32 = torch.empty((splitk, B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
+            _conv_call("sg2_conv_fprop", 2, fl, kind, _p(x), _p(wpk), _p(y32), OUT_F32_STORE, B, H, W, Cin, Cout, splitk,
+                       None, 1, 0, None, _st())
+            y = splitk_finish(y32, splitk, (B, Ho, Wo, Cout), stats, groups)
+            return y if stats is None else (y, True)
         y32 = torch.zeros((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
         _conv_call("sg2_conv_fprop", 2, fl, kind, _p(x), _p(wpk), _p(y32), OUT_F32_ATOMIC, B, H, W, Cin, Cout, splitk,
                    None, 1, 0, None, _st())
@@ -165,7 +184,7 @@ def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, grou
         return f32_to_bf16_stats(y32, stats, groups), True
     y = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
     try:
-        _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, 1, _p(stats),
+        _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, 1, _p64(stats),
                    groups, act, _p(bias9), _st())
     except _lib.NoFuse:
         _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, 1, None, 1, act,
@@ -192,6 +211,11 @@ def conv_dgrad(kind, dy, wpkT, B, H, W, Cin, splitk=None, flop_scale=1.0, epi=No
     if splitk is None:
         splitk = _auto_split(B * H * W // groups, Cin, taps * max(1, Cout // 64), groups)
     if splitk > 1:
+        if DETERMINISTIC:
+            dx32 = torch.empty((splitk, B, H, W, Cin), device=dy.device, dtype=torch.float32)
+            _conv_call("sg2_conv_dgrad", 2, fl, kind, _p(dy), _p(wpkT), _p(dx32), OUT_F32_STORE, B, H, W, Cin, Cout, splitk,
+                       None, 0, _st())
+            return splitk_finish(dx32, splitk, (B, H, W, Cin), None, 1, epi)      # + the epilogue operand, same pass
         dx32 = torch.zeros((B, H, W, Cin), device=dy.device, dtype=torch.float32)
         _conv_call("sg2_conv_dgrad", 2, fl, kind, _p(dy), _p(wpkT), _p(dx32), OUT_F32_ATOMIC, B, H, W, Cin, Cout, splitk,
                    None, 0, _st())
@@ -209,8 +233,8 @@ def conv_dgrad(kind, dy, wpkT, B, H, W, Cin, splitk=None, flop_scale=1.0, epi=No
     return dx if epi is None else _epi_apply(dx, epi)
 
 
-def conv_wgrad(kind, x, dy, dwpk, splitk=None, flop_scale=1.0):
-    """dwpk (Cout, jobs, Cin) fp32 += dy^T im2col(x)."""
+def conv_wgrad(kind, x, dy, dwpk, splitk=None, flop_scale=1.0, first=False):
+    """dwpk (Cout, jobs, Cin) fp32 += dy^T im2col(x).  first: dwpk holds nothing yet (write instead of accumulate)."""
     B, H, W, Cin = x.shape
     Cout = dy.shape[-1]
     fl = flop_scale * _conv_flops(kind, B, H, W, Cin, Cout)
@@ -229,7 +253,37 @@ def conv_wgrad(kind, x, dy, dwpk, splitk=None, flop_scale=1.0):
                 if best_cost is None or cost < best_cost - 1e-9:
                     best, best_cost = sp, cost
             splitk = best
-    _conv_call("sg2_conv_wgrad", 1, fl, kind, _p(x), _p(dy), _p(dwpk), B, H, W, Cin, Cout, splitk, _st())
+    if not DETERMINISTIC:
+        _conv_call("sg2_conv_wgrad", 1, fl, kind, _p(x), _p(dy), _p(dwpk), B, H, W, Cin, Cout, splitk, None, _st())
+        return
+    n = dwpk.numel()
+    if splitk > 1 and n * 4 >= (16 << 20):
+        splitk = max(1, min(splitk, (64 << 20) // (n * 4)))       # bound the slab traffic of large weights
+    slabs = _lib.lib().sg2_conv_wgrad_slabs(kind, B, H, W, Cin, Cout, splitk)
+    if slabs < 1:
+        _lib.check(slabs if slabs < 0 else -1, "sg2_conv_wgrad_slabs")
+    if slabs == 1 and first:
+        # one slab and nothing to add to: the kernel stores straight into the accumulator
+        _conv_call("sg2_conv_wgrad", 1, fl, kind, _p(x), _p(dy), _p(dwpk), B, H, W, Cin, Cout, splitk, _p(dwpk), _st())
+        return
+    parts = torch.empty((slabs, n), device=dwpk.device, dtype=torch.float32)
+    _conv_call("sg2_conv_wgrad", 1, fl, kind, _p(x), _p(dy), _p(dwpk), B, H, W, Cin, Cout, splitk, _p(parts), _st())
+    reduce_slabs(parts, slabs, n, dwpk, accumulate=not first)
+
+
+def reduce_slabs(parts, nslabs, n, dst, accumulate):
+    """dst (=|+=) the sum of the slabs, in slab order."""
+    _call("sg2_reduce_slabs", 1, _p(parts), nslabs, n, n, _p(dst), int(accumulate), _st())
+
+
+def splitk_finish(parts, nsplit, shape, stats=None, groups=1, epi=None):
+    """(nsplit, *shape) fp32 split-K slabs -> bf16 tensor of `shape`: slabs summed in order (+ epilogue operand, + BN stats)."""
+    C = shape[-1]
+    y = torch.empty(shape, device=parts.device, dtype=torch.bfloat16)
+    n = y.numel()
+    _call("sg2_splitk_finish", 1, _p(parts), nsplit, n, _p(y), n // C, C, groups, _p64(stats),
+          _p(epi[0]) if epi is not None else None, epi[1] if epi is not None else 0, _st())
+    return y
 
 
 # ------------------------------------------------------------------------------------------ BN / activations
@@ -279,20 +333,20 @@ def arena_reset(device):
 
 
 def bn_stats32(C, device, groups=1):
-    """Zeroed fp32 [groups][2][C] slot for the per-channel sum / sum of squares (filled by a conv epilogue or bn_stats)."""
-    return _arena(device).take(groups * 2 * C * 4, torch.float32)
+    """Zeroed fp64 [groups][2][C] slot for the per-channel sum / sum of squares (filled by a conv epilogue or bn_stats)."""
+    return _arena(device).take(groups * 2 * C * 8, torch.float64)
 
 
 def bn_stats(x2d, stats, groups=1):
     P, C = x2d.shape
-    _call("sg2_bn_stats", 1, _p(x2d), P, C, groups, _p(stats), _st())
+    _call("sg2_bn_stats", 1, _p(x2d), P, C, groups, _p64(stats), _st())
 
 
 def f32_to_bf16_stats(x32, stats, groups=1):
     """fp32 [..., C] -> bf16 copy, and += per-channel sums of the rounded values into `stats`."""
     C = x32.shape[-1]
     y = torch.empty(x32.shape, device=x32.device, dtype=torch.bfloat16)
-    _call("sg2_f32_to_bf16_stats", 1, _p(x32), _p(y), x32.numel() // C, C, groups, _p(stats), _st())
+    _call("sg2_f32_to_bf16_stats", 1, _p(x32), _p(y), x32.numel() // C, C, groups, _p64(stats), _st())
     return y
 
 
@@ -321,7 +375,7 @@ def bn_act_fwd(x, gamma, beta, act, residual=None, stats=None, mean=None, rstd=N
         mr = torch.empty(2, groups * C, device=x.device, dtype=torch.float32)
         mean, rstd = mr[0], mr[1]
     rm, rv, nbt = running if (running is not None and stats is not None) else (None, None, None)
-    _call("sg2_bn_act_fwd", 1, _p(x), _p(stats), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(out), P, C,
+    _call("sg2_bn_act_fwd", 1, _p(x), _p64(stats), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(out), P, C,
           groups, act, BN_EPS, BN_MOMENTUM, _p(rm), _p(rv), _p(nbt), _st())
     return (out, mean, rstd) if stats is not None else out
 
@@ -385,9 +439,9 @@ def joint_bias(c, wst, Cout):
 
 def joint_tap_sums(dy):
     B, H, W, Cout = dy.shape
-    R = _arena(dy.device).take(B * 9 * Cout * 4, torch.float32)
+    R = _arena(dy.device).take(B * 9 * Cout * 8, torch.float64)
     S = torch.empty((B, 9, Cout), device=dy.device, dtype=torch.float32)
-    _call("sg2_joint_tap_sums", 2, _p(dy), _p(R), _p(S), B, H, W, Cout, _st())
+    _call("sg2_joint_tap_sums", 2, _p(dy), _p64(R), _p(S), B, H, W, Cout, _st())
     return S
 
 
@@ -500,5 +554,8 @@ def logits_fwd(x, w, bias, out=None):
 
 def logits_bwd(dprob, prob, x, w, dx, dx_accumulate, dw, dbias):
     B, H, W, C = x.shape
-    _call("sg2_logits_bwd", 1, _p(dprob), _p(prob), _p(x), _p(w), _p(dx), int(dx_accumulate), _p(dw), _p(dbias),
-          B, H * W, C, _st())
+    scratch = None
+    if dw is not None:
+        scratch = torch.empty(_lib.lib().sg2_logits_bwd_scratch_floats(B, H * W, C), device=x.device, dtype=torch.float32)
+    _call("sg2_logits_bwd", 1 + (dw is not None), _p(dprob), _p(prob), _p(x), _p(w), _p(dx), int(dx_accumulate), _p(dw),
+          _p(dbias), _p(scratch), B, H * W, C, _st())

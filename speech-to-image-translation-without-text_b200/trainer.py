@@ -114,6 +114,23 @@ class FlatBucket:
         for p in self.params:
             p._sg2_version = getattr(p, "_sg2_version", 0) + 1
 
+    def refresh(self):
+        """Call after writing the parameters from outside the fused kernels (load_state_dict, `p.data.copy_`, an EMA
+        swap through load_params, weights_init): re-derives the bf16 mirror from the fp32 masters and invalidates every
+        cached operand pack."""
+        ops.f32_to_bf16(self.flat, out=self.flat16)
+        self.dirty()
+
+    def swap_ema(self):
+        """Exchange the live generator weights with the EMA shadow (what the reference does around its snapshot images
+        with copy_G_params / load_params, trainer.py:592-601); call again to swap back."""
+        if self.avg is None:
+            raise RuntimeError("this bucket keeps no EMA shadow")
+        tmp = self.flat.clone()
+        self.flat.copy_(self.avg)
+        self.avg.copy_(tmp)
+        self.refresh()
+
     def ema_params(self):
         """EMA weights as a list shaped like net.parameters() (what trainer.py:256 load_params() copies in)."""
         out = []
@@ -135,12 +152,17 @@ class FusedTrainer:
         self.uncond, self.cal, self.kl = float(c.UNCOND_LOSS), float(c.CAL_LOSS), float(c.KL)
         if self.uncond <= 0:
             raise NotImplementedError("UNCOND_LOSS == 0 is not used by any reference cfg")
+        if float(getattr(c, "COLOR_LOSS", 0.0) or 0.0) > 0:
+            # train_Gnet's colour-consistency terms (trainer.py:454-477); every reference cfg sets COLOR_LOSS: 0.0
+            raise NotImplementedError("COLOR_LOSS > 0 (colour-consistency terms, trainer.py:454-477) is not implemented")
         self.lr_g = float(cfg.TRAIN.GENERATOR_LR if lr_g is None else lr_g)
         self.lr_d = float(cfg.TRAIN.DISCRIMINATOR_LR if lr_d is None else lr_d)
         self.G = netG.engine()
         self.Ds = [d.engine() for d in self.netsD]
         self.bG = FlatBucket(netG, with_ema=True)
         self.bD = [FlatBucket(d) for d in self.netsD]
+        for eng in [self.G] + self.Ds:
+            eng.set_auto_refresh(False)       # the buckets track every weight update themselves (dirty / refresh)
         self.all_reduce = all_reduce          # callable(flat_grad_tensor) or None (single GPU)
         self.concurrent = os.environ.get("SG2_CONCURRENT", "1") != "0"   # one stream per discriminator (see step())
         self.batched_d = os.environ.get("SG2_BATCHED_D", "1") != "0"     # real/wrong/fake D passes as one 3B pass
@@ -153,6 +175,31 @@ class FusedTrainer:
         # loss scalars: errD[i], errG_total, kl, cal
         self.losses = torch.zeros(len(self.Ds) + 3, device=dev, dtype=torch.float32)
         self._tables = {}
+
+    # ------------------------------------------------------------------ state (checkpoint / resume, parity tests)
+    def snapshot(self):
+        """Everything a step reads and writes, cloned: flat parameters, Adam moments and step counters, the EMA shadow,
+        BatchNorm running statistics (what the reference checkpoints with save_model plus the optimiser state)."""
+        snap = {"buckets": [], "buffers": []}
+        for b in [self.bG] + self.bD:
+            snap["buckets"].append({k: getattr(b, k).clone() for k in ("flat", "m", "v", "step", "bc")}
+                                   | ({"avg": b.avg.clone()} if b.avg is not None else {}))
+        for net in [self.netG] + self.netsD:
+            snap["buffers"].append([t.detach().clone() for t in net.buffers()])
+        return snap
+
+    def restore(self, snap):
+        for b, sb in zip([self.bG] + self.bD, snap["buckets"]):
+            for k, t in sb.items():
+                getattr(b, k).copy_(t)
+            b.refresh()
+        for net, bufs in zip([self.netG] + self.netsD, snap["buffers"]):
+            for t, src in zip(net.buffers(), bufs):
+                t.copy_(src)
+        # bring every cached operand pack up to date NOW (a captured graph re-packs a layer only after updating it)
+        for eng in [self.G] + self.Ds:
+            for op in eng.conv_ops():
+                op.packs()
 
     # ------------------------------------------------------------------ helpers
     def _layerwise(self, bucket, lr, chan=0):
@@ -251,14 +298,15 @@ class FusedTrainer:
             with torch.cuda.stream(st):
                 if st is not main:
                     st.wait_event(fork0)
-                self.bD[i].grad.zero_()
+                if not ops.DETERMINISTIC:
+                    self.bD[i].grad.zero_()       # red.global.add wgrads accumulate straight into the bucket
                 if self.batched_d:
                     S = real[i].shape[2]
                     col3[i] = torch.empty((3, B * (S // 2) * (S // 2), 64), device=self.dev, dtype=torch.bfloat16)
                     ops.stem_im2col(real[i], out=col3[i][0])
                     ops.stem_im2col(wrong[i], out=col3[i][1])
         g_zeroed = None
-        if self.concurrent:
+        if self.concurrent and not ops.DETERMINISTIC:
             with torch.cuda.stream(self._sW[nD]):
                 self._sW[nD].wait_event(fork0)
                 self.bG.grad.zero_()
@@ -342,7 +390,7 @@ class FusedTrainer:
             dmu.add_(dc)                         # mu is not detached in train_Gnet (trainer.py:438)
         if g_zeroed is not None:
             main.wait_event(g_zeroed)
-        else:
+        elif not ops.DETERMINISTIC:
             self.bG.grad.zero_()
         ready, fin = self._layerwise(self.bG, self.lr_g, nD) if self.layerwise else (None, None)
         sinkG = GradSink(self.bG.views, self._sW[nD] if self.concurrent else None, prezeroed=True, on_ready=ready)
@@ -367,11 +415,16 @@ class CapturedStep:
     once into a CUDA graph and replayed per step: the launch-bound inner loop costs one cudaGraphLaunch instead of
     ~20 ms of Python/ctypes/driver work. Inputs live in static device buffers (`load()` copies a batch in)."""
 
-    def __init__(self, trainer, batch_size, warmup=3):
+    def __init__(self, trainer, batch_size, warmup=3, draw_noise=True):
+        """draw_noise: the graph draws z ~ N(0,1) (trainer.py:542) and the reparameterisation eps (model.py:190-193) itself
+        (Philox state advanced per replay); False: both come from the static buffers `noise` / `eps` filled by load()
+        (parity tests replay the graph on given noise)."""
         self.tr = trainer
         cfg, dev = trainer.cfg, trainer.dev
         B = batch_size
-        self.noise = torch.empty(B, cfg.GAN.Z_DIM, device=dev)
+        self.draw_noise = draw_noise
+        self.noise = torch.zeros(B, cfg.GAN.Z_DIM, device=dev)
+        self.eps = torch.zeros(B, cfg.GAN.EMBEDDING_DIM, device=dev)
         self.emb = torch.zeros(B, cfg.TEXT.DIMENSION, device=dev)
         sizes = [64 * 2 ** i for i in range(len(trainer.Ds))]
         self.real = [torch.zeros(B, 3, s, s, device=dev) for s in sizes]
@@ -381,7 +434,11 @@ class CapturedStep:
         self.launches_per_step = 0
         self._warmup = warmup
 
-    def load(self, emb, real, wrong, labels, non_blocking=True):
+    def load(self, emb, real, wrong, labels, non_blocking=True, z=None, eps=None):
+        if z is not None:
+            self.noise.copy_(z, non_blocking=non_blocking)
+        if eps is not None:
+            self.eps.copy_(eps, non_blocking=non_blocking)
         self.emb.copy_(emb, non_blocking=non_blocking)
         for d, s in zip(self.real, real):
             d.copy_(s, non_blocking=non_blocking)
@@ -390,8 +447,10 @@ class CapturedStep:
         self.labels.copy_(labels, non_blocking=non_blocking)
 
     def _body(self):
-        self.noise.normal_(0, 1)                                           # trainer.py:542
-        return self.tr.step(self.noise, self.emb, self.real, self.wrong, self.labels)
+        if self.draw_noise:
+            self.noise.normal_(0, 1)                                       # trainer.py:542
+            return self.tr.step(self.noise, self.emb, self.real, self.wrong, self.labels)
+        return self.tr.step(self.noise, self.emb, self.real, self.wrong, self.labels, eps=self.eps)
 
     def capture(self):
         side = torch.cuda.Stream(device=self.tr.dev)

@@ -49,3 +49,75 @@ def report(pairs, tol):
     worst = sorted(pairs, key=lambda t: -t[1])[:8]
     ok = all(e <= tol or e != e for _, e in pairs) and all(e == e for _, e in pairs)
     return ok, "worst rel errors: " + ", ".join(f"{n}={e:.3e}" for n, e in worst)
+
+
+# ------------------------------------------------------------------------------------------------ train-step helpers
+def cos(a, b):
+    return float(torch.nn.functional.cosine_similarity(a.detach().flatten().double(), b.detach().flatten().double(), dim=0))
+
+
+def build_trainer_and_oracles(branches, seed=0, n_oracles=1, lr=None):
+    """sg2b200 networks + FusedTrainer and `n_oracles` OracleTrainers, all starting from the same weights."""
+    from oracle.stackgan_oracle import OracleTrainer
+    from sg2b200 import trainer, utils
+    fp32_strict()
+    ocfg = Cfg(BRANCH_NUM=branches)
+    if lr is not None:
+        ocfg.LR_G = ocfg.LR_D = lr
+    cfg = set_cfg(ocfg)
+    torch.manual_seed(seed)
+    netG, netsD = utils.build_networks(cfg, "cuda")
+    gs = {k: v.detach().clone() for k, v in netG.state_dict().items()}
+    dss = [{k: v.detach().clone() for k, v in d.state_dict().items()} for d in netsD]
+    orcs = [OracleTrainer(ocfg, gs, dss, device="cuda") for _ in range(n_oracles)]
+    tr = trainer.FusedTrainer(netG, netsD, cfg, lr_g=lr, lr_d=lr)
+    return cfg, ocfg, netG, netsD, tr, orcs
+
+
+def train_batch(cfg, B, seed, n_classes=3):
+    from sg2b200 import utils
+    b = utils.synthetic_batch(cfg, B, seed=seed, device="cuda", n_classes=n_classes)
+    b["eps"] = torch.randn(B, cfg.GAN.EMBEDDING_DIM, generator=torch.Generator().manual_seed(seed + 1)).cuda()
+    return b
+
+
+def oracle_step(orc, b, **kw):
+    return orc.step(dict(z=b["z"], emb=b["emb"], eps=b["eps"], real=b["real"], wrong=b["wrong"],
+                         labels=b["labels"].tolist()), **kw)
+
+
+def loss_vector(o):
+    """Oracle step output -> [errD_0.., errG_total, kl, cal] like FusedTrainer.step returns."""
+    return [float(e) for e in o["errD"]] + [float(o["errG_total"]), float(o["kl"]), float(o["cal"])]
+
+
+def bucket_grads(tr):
+    """name -> gradient tensor (reference OIHW shapes) out of the fused trainer's flat gradient buckets."""
+    out = {}
+    for tag, net, b in [("G", tr.netG, tr.bG)] + [(f"D{i}", d, tr.bD[i]) for i, d in enumerate(tr.netsD)]:
+        for k, p in net.named_parameters():
+            out[f"{tag}.{k}"] = b.views[p]
+    return out
+
+
+def oracle_grads(o):
+    out = {f"G.{k}": v for k, v in o["grads_g"].items()}
+    for i, gd in enumerate(o["grads_d"]):
+        out.update({f"D{i}.{k}": v for k, v in gd.items()})
+    return out
+
+
+def snapshot_diff(a, b):
+    """Largest relative difference between two FusedTrainer.snapshot()s, and whether they are bit-identical."""
+    worst, same = 0.0, True
+    for ba, bb in zip(a["buckets"], b["buckets"]):
+        for k in ba:
+            same = same and torch.equal(ba[k], bb[k])
+            if ba[k].is_floating_point() and ba[k].numel() > 0:
+                worst = max(worst, rel(ba[k], bb[k]))
+    for la, lb in zip(a["buffers"], b["buffers"]):
+        for ta, tb in zip(la, lb):
+            same = same and torch.equal(ta, tb)
+            if ta.is_floating_point():
+                worst = max(worst, rel(ta, tb))
+    return worst, same

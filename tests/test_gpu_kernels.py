@@ -66,17 +66,25 @@ def test_conv_fprop_dgrad_wgrad(kind, B, H, W, Ci, Co):
     dyn = dy.permute(0, 2, 3, 1).contiguous().bfloat16()
     y = ops.conv_fprop(kind, xn, wpk, Co, splitk=1)
     assert _rel(y.float().permute(0, 3, 1, 2), y_ref) < 5e-3
-    st = torch.zeros(2 * Co, device="cuda")                                            # BN statistics from the epilogue
+    st = torch.zeros(2 * Co, device="cuda", dtype=torch.float64)                                         # BN statistics from the epilogue
     y3, fused = ops.conv_fprop(kind, xn, wpk, Co, splitk=1, stats=st)
     assert fused and torch.equal(y3, y)
     yf = y.float().reshape(-1, Co)
     assert _rel(st[:Co], yf.sum(0)) < 1e-4 and _rel(st[Co:], (yf * yf).sum(0)) < 1e-5
-    y2 = ops.conv_fprop(kind, xn, wpk, Co, splitk=3)                                   # split-K, fp32 atomics
+    y2 = ops.conv_fprop(kind, xn, wpk, Co, splitk=3)                                   # split-K: ordered slab sum
     assert _rel(y2.float().permute(0, 3, 1, 2), y_ref) < 5e-3
     dx = ops.conv_dgrad(kind, dyn, wpkT, B, H, W, Ci, splitk=1)
     assert _rel(dx.float().permute(0, 3, 1, 2), dx_ref) < 5e-3
     dwpk = torch.zeros(Co, ops.JOBS[kind], Ci, device="cuda")
     ops.conv_wgrad(kind, xn, dyn, dwpk)
+    if ops.DETERMINISTIC:
+        # first=True writes every element (no clearing needed) and the ordered slab reduction is reproducible bit for bit
+        dwpk_b = torch.full_like(dwpk, float("nan"))
+        ops.conv_wgrad(kind, xn, dyn, dwpk_b, first=True)
+        assert torch.equal(dwpk_b, dwpk)
+        ops.conv_wgrad(kind, xn, dyn, dwpk_b)                                          # second pass accumulates
+        assert torch.equal(dwpk_b, dwpk + dwpk)
+        assert torch.equal(ops.conv_fprop(kind, xn, wpk, Co, splitk=3), y2)
     gk = torch.empty_like(dw_ref)
     ops.unpack_wgrad(kind, dwpk, gk, Co, Ci, Co, Ci, False)
     assert torch.allclose(gk, unpack_wgrad_ref(kind, dwpk, Co, Ci), atol=1e-5)          # unpack is a pure permute/sum
@@ -201,7 +209,7 @@ def test_joint_conv_c_code_folding(layout, B, H, W, E, Ch, Co):
     wpk = w[:, E:].permute(0, 2, 3, 1).reshape(Co, 9, Ch).contiguous().bfloat16()
     x = h.permute(0, 2, 3, 1).contiguous().bfloat16()
     bias9 = ops.joint_bias(c, wst, Co)
-    stats = torch.zeros(2 * Co, device="cuda")
+    stats = torch.zeros(2 * Co, device="cuda", dtype=torch.float64)
     y, _ = ops.conv_fprop(ops.CONV3, x, wpk, Co, stats=stats, bias9=bias9)
     yf = y.float().permute(0, 3, 1, 2)
     assert _rel(yf, ref) < 5e-3

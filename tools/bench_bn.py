@@ -28,7 +28,7 @@ for P, C, act, G in CASES:
     ys = [torch.randn(rows, C, device=dev).bfloat16() for _ in range(ncopy)]
     ds = [torch.randn(rows, Co, device=dev).bfloat16() for _ in range(ncopy)]
     gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
-    st = torch.zeros(G * 2 * C, device=dev)
+    st = torch.zeros(G * 2 * C, device=dev, dtype=torch.float64)
     ops.bn_stats(ys[0], st, groups=G)
     dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
     sts = [st.clone() for _ in range(REPS + 3)]

@@ -83,7 +83,7 @@ def main():
         dwpk = torch.zeros(Cout, ops.JOBS[kind], Cin, device=dev, dtype=torch.float32)
         fl = ops._conv_flops(kind, Bx, Hx, Wx, Cin, Cout)
         has_bn = act is not None
-        st = torch.zeros(2 * Cout, device=dev, dtype=torch.float32)
+        st = torch.zeros(2 * Cout, device=dev, dtype=torch.float64)
         t_f = timed(lambda: ops.conv_fprop(kind, x, wpk, Cout, stats=st if has_bn else None))
         t_d = timed(lambda: ops.conv_dgrad(kind, dy, wpkT, Bx, Hx, Wx, Cin))
         t_w = timed(lambda: ops.conv_wgrad(kind, x, dy, dwpk))

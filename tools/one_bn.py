@@ -10,7 +10,7 @@ dev = torch.device("cuda:0")
 y = torch.randn(24, H, H, C, device=dev).bfloat16()
 dout = torch.randn(24, H, H, C // 2, device=dev).bfloat16()
 gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
-st = torch.zeros(2 * C, device=dev)
+st = torch.zeros(2 * C, device=dev, dtype=torch.float64)
 ops.bn_stats(y.view(-1, C), st)
 dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
 for _ in range(3):

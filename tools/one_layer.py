@@ -23,7 +23,7 @@ for n, kind, H, Cin, Cout, act, cnt in lb.LAYERS:
     Ho, Wo = ops._out_hw(kind, Hx, Wx)
     dy = torch.randn(Bx, Ho, Wo, Cout, device=dev).bfloat16()
     dwpk = torch.zeros(Cout, ops.JOBS[kind], Cin, device=dev, dtype=torch.float32)
-    st = torch.zeros(2 * Cout, device=dev) if act is not None else None
+    st = torch.zeros(2 * Cout, device=dev, dtype=torch.float64) if act is not None else None
     for _ in range(reps):
         if op == "fprop":
             ops.conv_fprop(kind, x, wpk, Cout, stats=st)
