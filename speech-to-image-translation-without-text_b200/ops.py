@@ -158,6 +158,12 @@ def _auto_split(m_rows, n_cols, k_blocks, groups=1):
     return best
 
 
+def _k_blocks(taps, ck):
+    """K blocks of a launch: taps x (contraction channels / BK), BK as the kernels choose it."""
+    bk = 64 if ck % 64 == 0 else (32 if ck % 32 == 0 else 16)
+    return taps * max(1, ck // bk)
+
+
 def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, groups=1, act=ACT_NONE, bias9=None):
     """x (B,H,W,Cin) bf16 -> y bf16 (B,Ho,Wo,Cout). With `stats` (fp32 [groups*2*Cout], zeroed) the per-channel sum /
     sum of squares of each of the `groups` sub-batches is accumulated too (in the conv epilogue, in the fp32->bf16 pass
@@ -169,6 +175,7 @@ def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, grou
     pgroups = 4 if kind == UPCONV else 1          # output parity groups (separate GEMMs)
     if splitk is None:
         splitk = 1 if (act or bias9 is not None) else _auto_split(B * Ho * Wo // pgroups, Cout, taps * max(1, Cin // 64), pgroups)
+    splitk = max(1, min(splitk, _k_blocks(taps, Cin)))
     if splitk > 1:
         if DETERMINISTIC:
             y32 = torch.empty((splitk, B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
@@ -210,6 +217,7 @@ def conv_dgrad(kind, dy, wpkT, B, H, W, Cin, splitk=None, flop_scale=1.0, epi=No
     groups = 4 if kind == CONV4S2 else 1
     if splitk is None:
         splitk = _auto_split(B * H * W // groups, Cin, taps * max(1, Cout // 64), groups)
+    splitk = max(1, min(splitk, _k_blocks(taps, Cout)))
     if splitk > 1:
         if DETERMINISTIC:
             dx32 = torch.empty((splitk, B, H, W, Cin), device=dy.device, dtype=torch.float32)
