@@ -191,6 +191,39 @@ int sg2_adam_ema(float* p, const float* g, float* m, float* v, float* avg, long 
                  float beta2, float eps, const float* bc, float ema_decay, void* p_bf16 /* optional bf16 mirror of p */,
                  void* stream);
 
+/* ---- fp32-accurate ("precise") mode: relative error <= 1e-4 against the fp32 reference (model.py:125-128 runs fp32
+ * end to end) ---------------------------------------------------------------------------------------------------
+ * Activations and gradients are NHWC fp32. A convolution is SIX launches of sg2_conv_fprop / _dgrad / _wgrad on the
+ * tcgen05 kernels above: sg2_split3 writes the three bf16 planes x = hi + mid + lo of an fp32 tensor (and of the fp32
+ * weight packs from sg2_pack_weights_f32), and the cross terms (hi,hi) (hi,mid) (mid,hi) (hi,lo) (lo,hi) (mid,mid)
+ * accumulate into one fp32 output (SG2_OUT_F32_ATOMIC without split-K adds each launch's tile exactly once). The
+ * kernels below are the fp32 counterparts of the bandwidth-bound kernels; same arguments, float instead of bf16. */
+int sg2_split3(const float* x, void* out /* bf16 [3][n] */, long long n, void* stream);
+int sg2_pack_weights_f32(int kind, const float* w, float* wpk, float* wpkT, int Cout, int Cin, int Cout_pad, int Cin_pad,
+                         int src_ohwi, void* stream);
+int sg2_bn_stats_f32(const float* x, long long P, int C, int groups, double* stats, void* stream);
+int sg2_bn_act_fwd_f32(const float* x, const double* stats, float* mean, float* rstd, const float* gamma,
+                       const float* beta, const float* residual, float* out, long long P, int C, int groups, int act,
+                       float eps, float momentum, float* running_mean, float* running_var,
+                       long long* num_batches_tracked, void* stream);
+int sg2_bn_act_bwd_f32(const float* x, const float* dout, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, double* sums, float* dx, float* dgamma, float* dbeta, int accumulate,
+                       long long P, int C, int groups, int act, void* stream);
+/* mode 0: out = a + b;  mode 1: out = a > 0 ? b : 0.2 b (LeakyReLU backward, a = the activation's output) */
+int sg2_ew_f32(int mode, const float* a, const float* b, float* out, long long n, void* stream);
+/* in place on an fp32 conv output [B][H][W][C]: += bias9 (see sg2_conv_fprop; may be NULL), then act (0 | SG2_ACT_LRELU) */
+int sg2_conv_post_f32(float* y, const float* bias9, int act, int B, int H, int W, int C, void* stream);
+int sg2_concat_c_f32(const float* c, const float* h, float* out, int B, int HW, int E, int Ch, void* stream);
+int sg2_concat_c_bwd_f32(const float* dcat, float* dh, float* dc /* += */, int B, int HW, int E, int Ch, void* stream);
+int sg2_head_tanh_fwd_f32(const float* y, float* img, int B, int HW, int CP, void* stream);
+int sg2_head_tanh_bwd_f32(const float* dimg, const float* img, float* dy, int B, int HW, int CP, void* stream);
+int sg2_stem_im2col_f32(const float* img, float* col, int B, int S, void* stream);
+int sg2_stem_col2im_f32(const float* dcol, float* dimg, int B, int S, void* stream);
+int sg2_hwc_chw_f32(const float* in, float* out, int B, int HW, int C, int to_chw, void* stream);
+int sg2_logits_fwd_f32(const float* x, const float* w, const float* bias, float* prob, int B, int HW, int C, void* stream);
+int sg2_logits_bwd_f32(const float* dprob, const float* prob, const float* x, const float* w, float* dx,
+                       int dx_accumulate, float* dw /* += */, float* dbias /* += */, int B, int HW, int C, void* stream);
+
 /* EXPERIMENT (not part of the product path): conv3x3 fprop with one halo tile per channel chunk and shifted UMMA
  * descriptors per tap; used by tools/probe_halo.py to validate the addressing scheme on hardware. */
 int sg2_probe_halo_fprop(const void* x, const void* wpk, void* y, int B, int H, int W, int Cin, int Cout, int pitch,

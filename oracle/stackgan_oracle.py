@@ -339,8 +339,8 @@ class OracleTrainer:
         cfg = self.cfg
         out = {}
         bsz = batch["z"].shape[0]
-        ones = torch.ones(bsz, device=self.device)
-        zeros = torch.zeros(bsz, device=self.device)
+        ones = torch.ones(bsz, device=self.device, dtype=batch["z"].dtype)     # float64 runs: targets in float64 too
+        zeros = torch.zeros(bsz, device=self.device, dtype=batch["z"].dtype)
         fake, mu, logvar = g_forward(self.g, batch["z"], batch["emb"], batch["eps"], cfg, True)   # trainer.py:544
         out["fake"], out["mu"], out["logvar"] = [f.detach() for f in fake], mu.detach(), logvar.detach()
         # ---- train_Dnet (trainer.py:375-427)

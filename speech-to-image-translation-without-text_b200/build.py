@@ -12,7 +12,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libsg2b200.so")
-SOURCES = ["conv.cu", "elementwise.cu", "small_ops.cu", "probe.cu"]
+SOURCES = ["conv.cu", "elementwise.cu", "small_ops.cu", "precise.cu", "probe.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",

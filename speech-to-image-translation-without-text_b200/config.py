@@ -47,3 +47,17 @@ def active_cfg():
         if m is not None and hasattr(m, "cfg"):
             return m.cfg
     return cfg
+
+
+# Arithmetic mode of the engines built from now on: "bf16" (bf16 storage, fp32 accumulation: the fast path) or "fp32"
+# (fp32 storage, convolutions as 3-way bf16 splits on the same tensor-core kernels: relative error <= 1e-4 against the
+# fp32 reference, see csrc/precise.cu). Networks pick it up when their engine is first built; net.set_precision(p)
+# rebuilds it.
+PRECISION = "bf16"
+
+
+def set_precision(p):
+    global PRECISION
+    if p not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    PRECISION = p

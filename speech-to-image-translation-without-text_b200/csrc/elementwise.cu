@@ -84,8 +84,16 @@ __device__ __forceinline__ void pack_offsets(int kind, int co, int slot, int ci,
 // fp32 OIHW -> bf16 packs. One block = 16 output channels x 32 input channels x all taps, staged in shared memory:
 // the OIHW read is a contiguous run per output channel, the two packs are written in 64-byte / 32-byte runs.
 constexpr int kPackCo = 16, kPackCi = 32;
-__global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk,
-                                    __nv_bfloat16* __restrict__ wpkT, int Cout, int Cin, int CoP, int CiP,
+__device__ __forceinline__ void store8(__nv_bfloat16* dst, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(dst) = pack8(v);
+}
+__device__ __forceinline__ void store8(float* dst, const float (&v)[8]) {   // fp32 packs (precise mode: split into 3 bf16 planes later)
+  reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <typename T>
+__global__ void pack_weights_kernel(int kind, const float* __restrict__ w, T* __restrict__ wpk,
+                                    T* __restrict__ wpkT, int Cout, int Cin, int CoP, int CiP,
                                     int src_ohwi) {
   __shared__ float tile[kPackCo][kPackCi][17];
   const int kk = (kind == SG2_CONV3x3 || kind == SG2_UPCONV3x3) ? 9 : ((kind == SG2_GEMM) ? 1 : 16);   // source taps
@@ -108,7 +116,7 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_
     }
     __syncthreads();
     for (int pass = 0; pass < 2; ++pass) {
-      __nv_bfloat16* dst = pass == 0 ? wpk : wpkT;
+      T* dst = pass == 0 ? wpk : wpkT;
       if (!dst) continue;
       // each thread produces 8 consecutive elements of the destination's contiguous axis -> one 128-bit store
       const int inner8 = (pass == 0 ? kPackCi : kPackCo) / 8;
@@ -134,7 +142,7 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_
         }
         long long fo, to;
         pack_offsets(kind, co, slot, ci, CoP, CiP, fo, to);
-        *reinterpret_cast<uint4*>(dst + (pass == 0 ? fo : to)) = pack8(v);
+        store8(dst + (pass == 0 ? fo : to), v);
       }
     }
     __syncthreads();
@@ -178,8 +186,11 @@ __global__ void __launch_bounds__(256) pack_transpose_kernel(int kind, const __n
 }
 
 // 3-channel stem (tiny): GEMM over im2col rows, k = (kh*4+kw)*3 + c, padded to CiP.
-__global__ void pack_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk,
-                                 __nv_bfloat16* __restrict__ wpkT, int Cout, int CoP, int CiP, int src_ohwi) {
+__device__ __forceinline__ void cvt_store(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void cvt_store(float* p, float v) { *p = v; }
+template <typename T>
+__global__ void pack_stem_kernel(const float* __restrict__ w, T* __restrict__ wpk,
+                                 T* __restrict__ wpkT, int Cout, int CoP, int CiP, int src_ohwi) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < CoP * CiP; i += gridDim.x * blockDim.x) {
     const int ci = i % CiP, co = i / CiP;
     float v = 0.f;
@@ -187,9 +198,8 @@ __global__ void pack_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __r
       const int c = ci % 3, t = ci / 3;
       v = src_ohwi ? w[(long long)co * 48 + ci] : w[((long long)co * 3 + c) * 16 + t];
     }
-    const __nv_bfloat16 bv = __float2bfloat16_rn(v);
-    if (wpk) wpk[(long long)co * CiP + ci] = bv;
-    if (wpkT) wpkT[(long long)ci * CoP + co] = bv;
+    if (wpk) cvt_store(&wpk[(long long)co * CiP + ci], v);
+    if (wpkT) cvt_store(&wpkT[(long long)ci * CoP + co], v);
   }
 }
 
@@ -976,22 +986,35 @@ static bool attr_needed(bool (&done)[64]) {
   return true;
 }
 
-extern "C" {
-
-int sg2_pack_weights(int kind, const float* w, void* wpk, void* wpkT, int Cout, int Cin, int CoP, int CiP,
-                     int src_ohwi, void* stream) {
+template <typename T>
+static int pack_weights_t(int kind, const float* w, T* wpk, T* wpkT, int Cout, int Cin, int CoP, int CiP, int src_ohwi,
+                          void* stream) {
   if (kind < 0 || kind > 4 || CoP < Cout || CiP < Cin) EW_FAIL(SG2_EINVAL, "pack_weights: bad arguments");
   if (kind == SG2_STEM4x4 && Cin != 48) EW_FAIL(SG2_EINVAL, "pack_weights: stem expects Cin == 48 (3 x 4 x 4)");
+  if ((CoP % 8) || (CiP % 8)) EW_FAIL(SG2_EINVAL, "pack_weights: padded extents %% 8");
   if (kind == SG2_STEM4x4) {
-    pack_stem_kernel<<<grid1d((long long)CoP * CiP), 256, 0, (cudaStream_t)stream>>>(
-        w, (__nv_bfloat16*)wpk, (__nv_bfloat16*)wpkT, Cout, CoP, CiP, src_ohwi);
+    pack_stem_kernel<T><<<grid1d((long long)CoP * CiP), 256, 0, (cudaStream_t)stream>>>(w, wpk, wpkT, Cout, CoP, CiP,
+                                                                                      src_ohwi);
     return launch_ok("pack_stem");
   }
   long long nblk = (long long)((CoP + kPackCo - 1) / kPackCo) * ((CiP + kPackCi - 1) / kPackCi);
   if (nblk > 148 * 16) nblk = 148 * 16;
-  pack_weights_kernel<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(
-      kind, w, (__nv_bfloat16*)wpk, (__nv_bfloat16*)wpkT, Cout, Cin, CoP, CiP, src_ohwi);
+  pack_weights_kernel<T><<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(kind, w, wpk, wpkT, Cout, Cin, CoP, CiP,
+                                                                           src_ohwi);
   return launch_ok("pack_weights");
+}
+
+extern "C" {
+
+int sg2_pack_weights(int kind, const float* w, void* wpk, void* wpkT, int Cout, int Cin, int CoP, int CiP,
+                     int src_ohwi, void* stream) {
+  return pack_weights_t<__nv_bfloat16>(kind, w, (__nv_bfloat16*)wpk, (__nv_bfloat16*)wpkT, Cout, Cin, CoP, CiP, src_ohwi,
+                                       stream);
+}
+
+int sg2_pack_weights_f32(int kind, const float* w, float* wpk, float* wpkT, int Cout, int Cin, int CoP, int CiP,
+                         int src_ohwi, void* stream) {
+  return pack_weights_t<float>(kind, w, wpk, wpkT, Cout, Cin, CoP, CiP, src_ohwi, stream);
 }
 
 int sg2_pack_transpose(int kind, const void* wpk, void* wpkT, int Cout, int Cin, void* stream) {

@@ -575,59 +575,51 @@ __global__ void kl_loss_kernel(const float* __restrict__ mu, const float* __rest
 
 // class_aware_loss (trainer.py:298-311): S = X X^T; loss = max(0, mean(S) - mean(S[same class, off-diagonal])) / F.
 __global__ void cal_scores_kernel(const float* __restrict__ x, int B, int F, float* __restrict__ S) {
+  // fp64 accumulation: the loss is a difference of two means of these scores (cancellation amplifies their rounding)
   const int i = blockIdx.x / B, j = blockIdx.x % B;
-  float acc = 0.f;
-  if ((F & 3) == 0) {
-    const float4* xi = reinterpret_cast<const float4*>(x + (long long)i * F);
-    const float4* xj = reinterpret_cast<const float4*>(x + (long long)j * F);
-#pragma unroll 4
-    for (int f = threadIdx.x; f < (F >> 2); f += blockDim.x) {
-      const float4 a = xi[f], b = xj[f];
-      acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
-    }
-  } else {
-    for (int f = threadIdx.x; f < F; f += blockDim.x) acc += x[(long long)i * F + f] * x[(long long)j * F + f];
-  }
-  __shared__ float sh[32];
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  double acc = 0.0;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) acc += (double)x[(long long)i * F + f] * (double)x[(long long)j * F + f];
+  __shared__ double sh[128];
+  sh[threadIdx.x] = acc;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
-    v = warp_sum(v);
-    if (threadIdx.x == 0) S[blockIdx.x] = v;
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
   }
+  if (threadIdx.x == 0) S[blockIdx.x] = (float)sh[0];
 }
 // one block: loss and the symmetric coefficient matrix G = dL/dS + (dL/dS)^T   (B <= 128)
 __global__ void cal_coeff_kernel(const float* __restrict__ S, const int* __restrict__ labels, int B, int F,
                                  float* __restrict__ loss, float* __restrict__ G) {
   __shared__ float s_all, s_pair;
   __shared__ int n_pair;
-  __shared__ float sh_a[32], sh_p[32];
-  __shared__ int sh_n[32];
-  float a = 0.f, pr = 0.f;
+  __shared__ double sh_a[256], sh_p[256];
+  __shared__ int sh_n[256];
+  double a = 0.0, pr = 0.0;
   int np = 0;
   for (int i = threadIdx.x; i < B * B; i += blockDim.x) {
     const int r = i / B, c = i % B;
-    const float v = S[i];
+    const double v = (double)S[i];
     a += v;
     if (r != c && labels[r] == labels[c]) { pr += v; ++np; }
   }
-  // ordered block reduction (shuffle tree per warp, then the warps in index order): no atomics, reproducible
-  a = warp_sum(a);
-  pr = warp_sum(pr);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) np += __shfl_xor_sync(0xffffffffu, np, o);
-  if ((threadIdx.x & 31) == 0) { sh_a[threadIdx.x >> 5] = a; sh_p[threadIdx.x >> 5] = pr; sh_n[threadIdx.x >> 5] = np; }
+  // ordered block reduction (fixed tree): no atomics, reproducible; fp64 because the loss is a difference of means
+  sh_a[threadIdx.x] = a; sh_p[threadIdx.x] = pr; sh_n[threadIdx.x] = np;
   __syncthreads();
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      sh_a[threadIdx.x] += sh_a[threadIdx.x + s]; sh_p[threadIdx.x] += sh_p[threadIdx.x + s]; sh_n[threadIdx.x] += sh_n[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  __shared__ float l_sh;
   if (threadIdx.x == 0) {
-    float ta = 0.f, tp = 0.f;
-    int tn = 0;
-    for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) { ta += sh_a[wi]; tp += sh_p[wi]; tn += sh_n[wi]; }
-    s_all = ta; s_pair = tp; n_pair = tn;
+    n_pair = sh_n[0];
+    s_all = (float)sh_a[0]; s_pair = (float)sh_p[0];
+    l_sh = n_pair > 0 ? (float)(sh_a[0] / (double)(B * B) - sh_p[0] / (double)n_pair) : 0.f;
   }
   __syncthreads();
-  const float l = (n_pair > 0) ? (s_all / (float)(B * B) - s_pair / (float)n_pair) : 0.f;
+  const float l = l_sh;
   const bool active = (n_pair > 0) && (l > 0.f);
   if (threadIdx.x == 0 && active) loss[0] += l / (float)F;
   for (int i = threadIdx.x; i < B * B; i += blockDim.x) {

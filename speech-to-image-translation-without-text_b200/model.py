@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import nets
+from . import config as _config
 from .config import active_cfg
 
 __all__ = ["G_NET", "D_NET64", "D_NET128", "D_NET256", "D_NET512", "D_NET1024", "INCEPTION_V3", "GLU"]
@@ -141,11 +142,18 @@ class G_NET(nn.Module):
             self.img_net3 = GET_IMAGE_G(self.gf_dim // 4)
         self._cfg = cfg
         self._engine = None
+        self._precision = None
 
     def engine(self):
         if self._engine is None:
-            self._engine = nets.GEngine(self, self._cfg)
+            self._engine = nets.GEngine(self, self._cfg, precise=(self._precision or _config.PRECISION) == "fp32")
         return self._engine
+
+    def set_precision(self, p):
+        """'bf16' | 'fp32' (see config.PRECISION): rebuilds the execution engine in that arithmetic mode."""
+        if p not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self._precision, self._engine = p, None
 
     def forward(self, z_code, text_embedding=None, eps=None):
         if text_embedding is None:
@@ -190,6 +198,7 @@ class _DBase(nn.Module):
         self.ef_dim = cfg.GAN.EMBEDDING_DIM
         self._cfg = cfg
         self._engine = None
+        self._precision = None
         self._need_w = True
         ndf = self.df_dim
         self.img_code_s16 = nn.Sequential(      # indices as in model.py:380-398
@@ -206,8 +215,10 @@ class _DBase(nn.Module):
 
     def engine(self):
         if self._engine is None:
-            self._engine = nets.DEngine(self, self._cfg)
+            self._engine = nets.DEngine(self, self._cfg, precise=(self._precision or _config.PRECISION) == "fp32")
         return self._engine
+
+    set_precision = G_NET.set_precision
 
     def skip_param_grads(self):
         net = self

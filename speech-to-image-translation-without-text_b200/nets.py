@@ -17,9 +17,10 @@ def _pad_to(n, m):
 class ConvOperand:
     """bf16 operand packs (fprop + dgrad) and the fp32 wgrad accumulator of one conv weight."""
 
-    def __init__(self, kind, weight, cout_pad=None, cin_pad=None):
+    def __init__(self, kind, weight, cout_pad=None, cin_pad=None, precise=False):
         self.kind = kind
         self.weight = weight
+        self.precise = precise      # fp32-accurate mode: packs are 3-plane bf16 splits of the fp32 packs (ops.split3)
         self.Cout = weight.shape[0]
         self.Cin = 48 if kind == STEM else weight.shape[1]
         self.CoP = cout_pad or self.Cout
@@ -42,7 +43,7 @@ class ConvOperand:
         return getattr(self.weight, "_sg2_ohwi", None)
 
     def _direct(self):
-        return (self._ohwi() is not None and self.kind in (CONV3, CONV4S2) and self.CoP == self.Cout
+        return (not self.precise and self._ohwi() is not None and self.kind in (CONV3, CONV4S2) and self.CoP == self.Cout
                 and self.CiP == self.Cin and self.Cout % 8 == 0 and self.Cin % 8 == 0)
 
     def _pack_key(self):
@@ -67,6 +68,12 @@ class ConvOperand:
                     _, s2 = ops.pack_shapes(self.kind, self.CoP, self.CiP)
                     self.wpkT = torch.empty(s2, device=w.device, dtype=torch.bfloat16)
                 ops.pack_transpose(self.kind, self.wpk, self.wpkT, self.Cout, self.Cin)
+                self._key = None if force else key
+            return self.wpk, self.wpkT
+        if self.precise:
+            if force or key != self._key:
+                self.wpk, self.wpkT = ops.pack_weights_split3(self.kind, w.detach() if oh is None else oh, self.Cout,
+                                                              self.Cin, self.CoP, self.CiP, ohwi=oh is not None)
                 self._key = None if force else key
             return self.wpk, self.wpkT
         if force or key != self._key:
@@ -213,9 +220,9 @@ class GradSink:
 class ConvBlock:
     """conv (3x3 | fused-upsample 3x3 | 4x4 s2) -> [BatchNorm] -> GLU | LeakyReLU | (+residual)."""
 
-    def __init__(self, kind, conv, bn, act):
+    def __init__(self, kind, conv, bn, act, precise=False):
         self.kind, self.conv, self.bn, self.act = kind, conv, bn, act
-        self.op = ConvOperand(kind, conv.weight)
+        self.op = ConvOperand(kind, conv.weight, precise=precise)
 
     def fwd(self, x, training, residual=None, groups=1):
         """groups > 1: the batch is `groups` equal sub-batches with separate BatchNorm statistics (the batched
@@ -353,11 +360,18 @@ class JointOperand:
 class JointBlock:
     """jointConv of NEXT_STAGE_G: conv3x3(cat(c_code, h)) -> BatchNorm -> GLU without materialising the concatenation."""
 
-    def __init__(self, conv, bn, E):
+    def __init__(self, conv, bn, E, precise=False):
         self.conv, self.bn, self.act = conv, bn, ACT_GLU
-        self.op = JointOperand(conv.weight, E)
+        self.E = E
+        # fp32-accurate mode: the concatenation is materialised and convolved with the whole weight, exactly like the
+        # reference (model.py:274-279); the folding below is an optimisation of the bf16 path
+        self.full = ConvBlock(CONV3, conv, bn, ACT_GLU, precise=True) if precise else None
+        self.op = self.full.op if precise else JointOperand(conv.weight, E)
 
     def fwd(self, c, h, training):
+        if self.full is not None:
+            out, sv = self.full.fwd(ops.concat_c(c, h), training)
+            return out, sv + (c,)
         op, bn = self.op, self.bn
         wpk, _ = op.packs()
         bias9 = ops.joint_bias(c, op.w_f32(), op.Cout)
@@ -375,6 +389,9 @@ class JointBlock:
 
     def bwd(self, saved, dout, sink, dc):
         """-> dh; dc (B, E) fp32 += the c_code gradient of this layer."""
+        if self.full is not None:
+            dcat = self.full.bwd(saved[:4], dout, sink)
+            return ops.concat_c_bwd(dcat, self.E, dc)
         h, y, mean, rstd, c = saved
         op = self.op
         (dg, acc), (db, _) = sink.slot(self.bn.weight), sink.slot(self.bn.bias)
@@ -397,9 +414,10 @@ class HeadBlock:
     """GET_IMAGE_G (model.py:287-298): conv3x3 C->3 + tanh; output NCHW fp32 image."""
     CP = 16
 
-    def __init__(self, conv):
+    def __init__(self, conv, precise=False):
         self.conv = conv
-        self.op = ConvOperand(CONV3, conv.weight, cout_pad=self.CP)
+        self.precise = precise
+        self.op = ConvOperand(CONV3, conv.weight, cout_pad=self.CP, precise=precise)
 
     def fwd(self, h):
         wpk, _ = self.op.packs()
@@ -408,7 +426,7 @@ class HeadBlock:
         return ops.head_tanh_fwd(y, B, H, W), h
 
     def bwd(self, h, img, dimg, sink):
-        dy = ops.head_tanh_bwd(dimg, img, self.CP)
+        dy = ops.head_tanh_bwd(dimg, img, self.CP, f32=self.precise)
         sink.conv(self.op, h, dy)
         _, wpkT = self.op.packs()
         B, H, W, C = h.shape
@@ -427,25 +445,26 @@ def _acc(a, b):
 
 # =============================================================================================== generator
 class GEngine:
-    def __init__(self, net, cfg):
+    def __init__(self, net, cfg, precise=False):
         self.net = net
+        self.precise = pr = precise     # fp32-accurate mode (fp32 activations, 3-way bf16 split convolutions)
         self.E = cfg.GAN.EMBEDDING_DIM
         self.Z = cfg.GAN.Z_DIM
         self.branches = cfg.TREE.BRANCH_NUM
         self.ngf = cfg.GAN.GF_DIM * 16
         h1 = net.h_net1
-        self.ups1 = [ConvBlock(UPCONV, getattr(h1, f"upsample{i}")[1], getattr(h1, f"upsample{i}")[2], ACT_GLU)
+        self.ups1 = [ConvBlock(UPCONV, getattr(h1, f"upsample{i}")[1], getattr(h1, f"upsample{i}")[2], ACT_GLU, pr)
                      for i in (1, 2, 3, 4)]
-        self.heads = [HeadBlock(net.img_net1.img[0])]
+        self.heads = [HeadBlock(net.img_net1.img[0], pr)]
         self.stages = []
         for s in range(2, self.branches + 1):
             hn = getattr(net, f"h_net{s}")
-            joint = JointBlock(hn.jointConv[0], hn.jointConv[1], self.E)
-            res = [(ConvBlock(CONV3, r.block[0], r.block[1], ACT_GLU), ConvBlock(CONV3, r.block[3], r.block[4], ACT_NONE))
+            joint = JointBlock(hn.jointConv[0], hn.jointConv[1], self.E, pr)
+            res = [(ConvBlock(CONV3, r.block[0], r.block[1], ACT_GLU, pr), ConvBlock(CONV3, r.block[3], r.block[4], ACT_NONE, pr))
                    for r in hn.residual]
-            up = ConvBlock(UPCONV, hn.upsample[1], hn.upsample[2], ACT_GLU)
+            up = ConvBlock(UPCONV, hn.upsample[1], hn.upsample[2], ACT_GLU, pr)
             self.stages.append((joint, res, up))
-            self.heads.append(HeadBlock(getattr(net, f"img_net{s}").img[0]))
+            self.heads.append(HeadBlock(getattr(net, f"img_net{s}").img[0], pr))
 
     def params(self):
         return [p for p in self.net.parameters()]
@@ -474,11 +493,11 @@ class GEngine:
         h32 = ops.linear_fwd(c, z, fc.weight.detach(), None, False)                    # (B, ngf*32) fp32
         if training:
             st = ops.bn_stats32(h32.shape[1], h32.device)
-            h = ops.f32_to_bf16_stats(h32, st)
+            h = ops.f32_to_bf16_stats(h32, st, keep_f32=self.precise)
             g, mean, rstd = ops.bn_act_fwd(h, bn.weight.detach(), bn.bias.detach(), ACT_GLU, stats=st,
                                            running=(bn.running_mean, bn.running_var, bn.num_batches_tracked))
         else:
-            h = ops.f32_to_bf16(h32)
+            h = h32 if self.precise else ops.f32_to_bf16(h32)
             mean, rstd = ops.bn_eval_stats(bn.running_mean, bn.running_var)
             g = ops.bn_act_fwd(h, bn.weight.detach(), bn.bias.detach(), ACT_GLU, mean=mean, rstd=rstd)  # CHW order
         T["fc"] = (h, mean, rstd)
@@ -556,16 +575,17 @@ class GEngine:
 class StemBlock:
     """encode_image_by_16times[0:2] (model.py:383-384): conv4x4 s2 3->ndf (no BN) + LeakyReLU, as im2col + GEMM."""
 
-    def __init__(self, conv):
+    def __init__(self, conv, precise=False):
         self.conv = conv
-        self.op = ConvOperand(STEM, conv.weight, cin_pad=64)
+        self.precise = precise
+        self.op = ConvOperand(STEM, conv.weight, cin_pad=64, precise=precise)
 
     def fwd(self, img, col=None):
         """col: optional precomputed im2col rows of `img` (the G step reuses the fake third of the D update's); `img`
         may then be just the (B, S) pair."""
         B, S = img if isinstance(img, tuple) else (img.shape[0], img.shape[2])
         if col is None:
-            col = ops.stem_im2col(img)
+            col = ops.stem_im2col(img, f32=self.precise)
         wpk, _ = self.op.packs()
         # LeakyReLU runs in the GEMM epilogue; backward only needs the sign, and sign(lrelu(y)) == sign(y).
         # The im2col rows are presented as a (B, S/2, S/2, 64) NHWC tensor: a 1x1 conv on the tile-resident kernel.
@@ -590,19 +610,20 @@ class StemBlock:
 
 
 class DEngine:
-    def __init__(self, net, cfg):
+    def __init__(self, net, cfg, precise=False):
         self.net = net
+        self.precise = pr = precise
         self.E = cfg.GAN.EMBEDDING_DIM
         s16 = net.img_code_s16
-        self.stem = StemBlock(s16[0])
-        self.trunk = [ConvBlock(CONV4S2, s16[2], s16[3], ACT_LRELU), ConvBlock(CONV4S2, s16[5], s16[6], ACT_LRELU),
-                      ConvBlock(CONV4S2, s16[8], s16[9], ACT_LRELU)]
+        self.stem = StemBlock(s16[0], pr)
+        self.trunk = [ConvBlock(CONV4S2, s16[2], s16[3], ACT_LRELU, pr), ConvBlock(CONV4S2, s16[5], s16[6], ACT_LRELU, pr),
+                      ConvBlock(CONV4S2, s16[8], s16[9], ACT_LRELU, pr)]
         for name, kind in (("img_code_s32", CONV4S2), ("img_code_s64", CONV4S2), ("img_code_s32_1", CONV3),
                            ("img_code_s64_1", CONV3), ("img_code_s64_2", CONV3)):
             if hasattr(net, name):
                 m = getattr(net, name)
-                self.trunk.append(ConvBlock(kind, m[0], m[1], ACT_LRELU))
-        self.joint = ConvBlock(CONV3, net.jointConv[0], net.jointConv[1], ACT_LRELU)
+                self.trunk.append(ConvBlock(kind, m[0], m[1], ACT_LRELU, pr))
+        self.joint = ConvBlock(CONV3, net.jointConv[0], net.jointConv[1], ACT_LRELU, pr)
 
     def params(self):
         return [p for p in self.net.parameters()]
@@ -665,7 +686,7 @@ class DEngine:
                            sink.g[ul.weight] if need_w else None, sink.g[ul.bias] if need_w else None)
         if dx_imm is not None:
             _, H, W, C = x.shape
-            dxi = ops.nchw_f32_to_nhwc(dx_imm, B, H, W, C)
+            dxi = ops.nchw_f32_to_nhwc(dx_imm, B, H, W, C, f32=self.precise)
             dx = dxi if dx is None else ops.add_bf16(dx, dxi)
         if dx is None:
             raise RuntimeError("sg2b200: D backward without any output gradient")

@@ -165,9 +165,11 @@ def _k_blocks(taps, ck):
 
 
 def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, groups=1, act=ACT_NONE, bias9=None):
-    """x (B,H,W,Cin) bf16 -> y bf16 (B,Ho,Wo,Cout). With `stats` (fp32 [groups*2*Cout], zeroed) the per-channel sum /
+    """x (B,H,W,Cin) bf16 -> y bf16 (B,Ho,Wo,Cout).  (fp32 x + 3-plane packs: the fp32-accurate mode, see _conv3_f32.) With `stats` (fp32 [groups*2*Cout], zeroed) the per-channel sum /
     sum of squares of each of the `groups` sub-batches is accumulated too (in the conv epilogue, in the fp32->bf16 pass
     of a split-K layer, or by sg2_bn_stats when a pixel tile would straddle sub-batches); returns (y, True)."""
+    if x.dtype == torch.float32:
+        return _conv_fprop_f32(kind, x, wpk, Cout, stats, groups, act, bias9)
     B, H, W, Cin = x.shape
     fl = flop_scale * _conv_flops(kind, B, H, W, Cin, Cout)
     Ho, Wo = _out_hw(kind, H, W)
@@ -211,6 +213,8 @@ def _epi_apply(dx, epi):
 def conv_dgrad(kind, dy, wpkT, B, H, W, Cin, splitk=None, flop_scale=1.0, epi=None):
     """dy (B,Ho,Wo,Cout) bf16 -> dx bf16 (B,H,W,Cin). epi = (src, EPI_ADD | EPI_LRELU_MASK): src (shape of dx) is added
     to / masks the result, in the conv epilogue when the shape allows it, else by the separate kernel."""
+    if dy.dtype == torch.float32:
+        return _conv_dgrad_f32(kind, dy, wpkT, B, H, W, Cin, epi)
     Cout = dy.shape[-1]
     fl = flop_scale * _conv_flops(kind, B, H, W, Cin, Cout)
     taps = {CONV3: 9, UPCONV: 16, CONV4S2: 4, GEMM: 1}[kind]
@@ -243,6 +247,11 @@ def conv_dgrad(kind, dy, wpkT, B, H, W, Cin, splitk=None, flop_scale=1.0, epi=No
 
 def conv_wgrad(kind, x, dy, dwpk, splitk=None, flop_scale=1.0, first=False):
     """dwpk (Cout, jobs, Cin) fp32 += dy^T im2col(x).  first: dwpk holds nothing yet (write instead of accumulate)."""
+    if x.dtype == torch.float32:
+        xs, dys = split3(x), split3(dy)
+        for k, (i, j) in enumerate(_PAIRS):
+            conv_wgrad(kind, xs[i], dys[j], dwpk, splitk, flop_scale, first and k == 0)
+        return
     B, H, W, Cin = x.shape
     Cout = dy.shape[-1]
     fl = flop_scale * _conv_flops(kind, B, H, W, Cin, Cout)
@@ -292,6 +301,53 @@ def splitk_finish(parts, nsplit, shape, stats=None, groups=1, epi=None):
     _call("sg2_splitk_finish", 1, _p(parts), nsplit, n, _p(y), n // C, C, groups, _p64(stats),
           _p(epi[0]) if epi is not None else None, epi[1] if epi is not None else 0, _st())
     return y
+
+
+# ------------------------------------------------------------------------------------------ fp32-accurate mode
+# (hi,hi) ... (mid,mid) cross terms of the 3-way bf16 split, smallest first (see csrc/precise.cu and sg2b200.h)
+_PAIRS = ((1, 1), (0, 2), (2, 0), (0, 1), (1, 0), (0, 0))
+
+
+def split3(x):
+    """fp32 tensor -> bf16 (3, *shape): x = hi + mid + lo to ~2^-24."""
+    out = torch.empty((3,) + tuple(x.shape), device=x.device, dtype=torch.bfloat16)
+    _call("sg2_split3", 1, _p(x), _p(out), x.numel(), _st())
+    return out
+
+
+def pack_weights_split3(kind, w, Cout, Cin, CoP, CiP, ohwi=False):
+    """fp32 master -> (fprop packs, dgrad packs), each bf16 (3, *pack shape)."""
+    s1, s2 = pack_shapes(GEMM if kind == STEM else kind, CoP, CiP)
+    a = torch.empty(s1, device=w.device, dtype=torch.float32)
+    b = torch.empty(s2, device=w.device, dtype=torch.float32)
+    _call("sg2_pack_weights_f32", 1, kind, _p(w), _p(a), _p(b), Cout, Cin, CoP, CiP, int(ohwi), _st())
+    return split3(a), split3(b)
+
+
+def _conv_fprop_f32(kind, x, wpk3, Cout, stats, groups, act, bias9):
+    B, H, W, Cin = x.shape
+    Ho, Wo = _out_hw(kind, H, W)
+    xs = split3(x)
+    y = torch.zeros((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
+    for i, j in _PAIRS:
+        _call("sg2_conv_fprop", 1, kind, _p(xs[i]), _p(wpk3[j]), _p(y), OUT_F32_ATOMIC, B, H, W, Cin, Cout, 1, None, 1, 0,
+              None, _st())
+    if bias9 is not None or act:
+        _call("sg2_conv_post_f32", 1, _p(y), _p(bias9), act, B, Ho, Wo, Cout, _st())
+    if stats is None:
+        return y
+    _call("sg2_bn_stats_f32", 1, _p(y), y.numel() // Cout, Cout, groups, _p64(stats), _st())
+    return y, True
+
+
+def _conv_dgrad_f32(kind, dy, wpkT3, B, H, W, Cin, epi):
+    Cout = dy.shape[-1]
+    dys = split3(dy)
+    dx = torch.zeros((B, H, W, Cin), device=dy.device, dtype=torch.float32)
+    for i, j in _PAIRS:
+        _call("sg2_conv_dgrad", 1, kind, _p(dys[i]), _p(wpkT3[j]), _p(dx), OUT_F32_ATOMIC, B, H, W, Cin, Cout, 1, None, 0,
+              _st())
+    return dx if epi is None else _epi_apply(dx, epi)
 
 
 # ------------------------------------------------------------------------------------------ BN / activations
@@ -347,12 +403,16 @@ def bn_stats32(C, device, groups=1):
 
 def bn_stats(x2d, stats, groups=1):
     P, C = x2d.shape
-    _call("sg2_bn_stats", 1, _p(x2d), P, C, groups, _p64(stats), _st())
+    _call("sg2_bn_stats_f32" if x2d.dtype == torch.float32 else "sg2_bn_stats", 1, _p(x2d), P, C, groups, _p64(stats), _st())
 
 
-def f32_to_bf16_stats(x32, stats, groups=1):
-    """fp32 [..., C] -> bf16 copy, and += per-channel sums of the rounded values into `stats`."""
+def f32_to_bf16_stats(x32, stats, groups=1, keep_f32=False):
+    """fp32 [..., C] -> bf16 copy, and += per-channel sums of the rounded values into `stats`.
+    keep_f32 (fp32-accurate mode): no rounding — returns x32 itself with its exact statistics."""
     C = x32.shape[-1]
+    if keep_f32:
+        bn_stats(x32.view(-1, C), stats, groups)
+        return x32
     y = torch.empty(x32.shape, device=x32.device, dtype=torch.bfloat16)
     _call("sg2_f32_to_bf16_stats", 1, _p(x32), _p(y), x32.numel() // C, C, groups, _p64(stats), _st())
     return y
@@ -374,16 +434,18 @@ def bn_act_fwd(x, gamma, beta, act, residual=None, stats=None, mean=None, rstd=N
     groups > 1: the rows are `groups` equal sub-batches, each normalised on its own statistics (mean/rstd [groups][C])."""
     C = x.shape[-1]
     P = x.numel() // C
-    out = torch.empty(x.shape[:-1] + ((C // 2) if act == ACT_GLU else C,), device=x.device, dtype=torch.bfloat16)
+    f32 = x.dtype == torch.float32
+    fn = "sg2_bn_act_fwd_f32" if f32 else "sg2_bn_act_fwd"
+    out = torch.empty(x.shape[:-1] + ((C // 2) if act == ACT_GLU else C,), device=x.device, dtype=x.dtype)
     if gamma is None:
-        _call("sg2_bn_act_fwd", 1, _p(x), None, None, None, None, None, _p(residual), _p(out), P, C, 1, act, BN_EPS,
+        _call(fn, 1, _p(x), None, None, None, None, None, _p(residual), _p(out), P, C, 1, act, BN_EPS,
               BN_MOMENTUM, None, None, None, _st())
         return out
     if stats is not None:
         mr = torch.empty(2, groups * C, device=x.device, dtype=torch.float32)
         mean, rstd = mr[0], mr[1]
     rm, rv, nbt = running if (running is not None and stats is not None) else (None, None, None)
-    _call("sg2_bn_act_fwd", 1, _p(x), _p64(stats), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(out), P, C,
+    _call(fn, 1 + f32, _p(x), _p64(stats), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(out), P, C,
           groups, act, BN_EPS, BN_MOMENTUM, _p(rm), _p(rv), _p(nbt), _st())
     return (out, mean, rstd) if stats is not None else out
 
@@ -394,20 +456,27 @@ def bn_act_bwd(x, dout, mean, rstd, gamma, beta, act, dgamma=None, dbeta=None, a
     P = x.numel() // C
     dx = torch.empty_like(x)
     sums = _arena(x.device).take(groups * 2 * C * 8, torch.float64)
-    _call("sg2_bn_act_bwd", 2, _p(x), _p(dout), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(sums), _p(dx),
-          _p(dgamma), _p(dbeta), int(accumulate), P, C, groups, act, _st())
+    _call("sg2_bn_act_bwd_f32" if x.dtype == torch.float32 else "sg2_bn_act_bwd", 2, _p(x), _p(dout), _p(mean), _p(rstd),
+          _p(gamma), _p(beta), _p64(sums), _p(dx), _p(dgamma), _p(dbeta), int(accumulate), P, C, groups, act, _st())
     return dx
 
 
 def lrelu_bwd(x, dout):
     dx = torch.empty_like(x)
-    _call("sg2_lrelu_bwd", 1, _p(x), _p(dout), _p(dx), x.numel(), _st())
+    if x.dtype == torch.float32:
+        _call("sg2_ew_f32", 1, 1, _p(x), _p(dout), _p(dx), x.numel(), _st())
+    else:
+        _call("sg2_lrelu_bwd", 1, _p(x), _p(dout), _p(dx), x.numel(), _st())
     return dx
 
 
 def add_bf16(a, b, out=None):
+    """out = a + b, elementwise, in the activations' storage type (bf16, or fp32 in the fp32-accurate mode)."""
     out = torch.empty_like(a) if out is None else out
-    _call("sg2_add_bf16", 1, _p(a), _p(b), _p(out), a.numel(), _st())
+    if a.dtype == torch.float32:
+        _call("sg2_ew_f32", 1, 0, _p(a), _p(b), _p(out), a.numel(), _st())
+    else:
+        _call("sg2_add_bf16", 1, _p(a), _p(b), _p(out), a.numel(), _st())
     return out
 
 
@@ -422,16 +491,17 @@ def f32_to_bf16(x, out=None):
 def concat_c(c, h):
     B, H, W, Ch = h.shape
     E = c.shape[1]
-    out = torch.empty((B, H, W, E + Ch), device=h.device, dtype=torch.bfloat16)
-    _call("sg2_concat_c", 1, _p(c), _p(h), _p(out), B, H * W, E, Ch, _st())
+    out = torch.empty((B, H, W, E + Ch), device=h.device, dtype=h.dtype)
+    _call("sg2_concat_c_f32" if h.dtype == torch.float32 else "sg2_concat_c", 1, _p(c), _p(h), _p(out), B, H * W, E, Ch, _st())
     return out
 
 
 def concat_c_bwd(dcat, E, dc, want_dh=True):
     B, H, W, Ct = dcat.shape
     Ch = Ct - E
-    dh = torch.empty((B, H, W, Ch), device=dcat.device, dtype=torch.bfloat16) if want_dh else None
-    _call("sg2_concat_c_bwd", 1, _p(dcat), _p(dh), _p(dc), B, H * W, E, Ch, _st())
+    dh = torch.empty((B, H, W, Ch), device=dcat.device, dtype=dcat.dtype) if want_dh else None
+    _call("sg2_concat_c_bwd_f32" if dcat.dtype == torch.float32 else "sg2_concat_c_bwd", 1, _p(dcat), _p(dh), _p(dc), B,
+          H * W, E, Ch, _st())
     return dh
 
 
@@ -462,21 +532,29 @@ def joint_c_bwd(S, c, wst, dc=None, dw=None, dw_accumulate=False):
 
 def head_tanh_fwd(y, B, H, W):
     img = torch.empty((B, 3, H, W), device=y.device, dtype=torch.float32)
-    _call("sg2_head_tanh_fwd", 1, _p(y), _p(img), B, H * W, y.shape[-1], _st())
+    _call("sg2_head_tanh_fwd_f32" if y.dtype == torch.float32 else "sg2_head_tanh_fwd", 1, _p(y), _p(img), B, H * W,
+          y.shape[-1], _st())
     return img
 
 
-def head_tanh_bwd(dimg, img, CP):
+def head_tanh_bwd(dimg, img, CP, f32=False):
     B, _, H, W = img.shape
-    dy = torch.empty((B, H, W, CP), device=img.device, dtype=torch.bfloat16)
-    _call("sg2_head_tanh_bwd", 1, _p(dimg), _p(img), _p(dy), B, H * W, CP, _st())
+    dy = torch.empty((B, H, W, CP), device=img.device, dtype=torch.float32 if f32 else torch.bfloat16)
+    _call("sg2_head_tanh_bwd_f32" if f32 else "sg2_head_tanh_bwd", 1, _p(dimg), _p(img), _p(dy), B, H * W, CP, _st())
     return dy
 
 
-def stem_im2col(img, out=None):
+def stem_im2col(img, out=None, f32=False):
     """(B,3,S,S) fp32 -> im2col rows (1,1,B*(S/2)^2,64) bf16 of the 4x4 s2 stem; `out`: a contiguous slice to fill."""
     B, _, S, _ = img.shape
     rows = B * (S // 2) * (S // 2)
+    if f32 or (out is not None and out.dtype == torch.float32):
+        if out is None:
+            out = torch.empty((1, 1, rows, 64), device=img.device, dtype=torch.float32)
+        elif out.numel() != rows * 64 or not out.is_contiguous():
+            raise RuntimeError("sg2b200: stem_im2col: bad output slice")
+        _call("sg2_stem_im2col_f32", 1, _p(img), _p(out), B, S, _st())
+        return out
     if out is None:
         out = torch.empty((1, 1, rows, 64), device=img.device, dtype=torch.bfloat16)
     elif out.numel() != rows * 64 or not out.is_contiguous() or out.dtype != torch.bfloat16:
@@ -487,20 +565,26 @@ def stem_im2col(img, out=None):
 
 def stem_col2im(dcol, B, S):
     dimg = torch.empty((B, 3, S, S), device=dcol.device, dtype=torch.float32)
-    _call("sg2_stem_col2im", 1, _p(dcol), _p(dimg), B, S, _st())
+    _call("sg2_stem_col2im_f32" if dcol.dtype == torch.float32 else "sg2_stem_col2im", 1, _p(dcol), _p(dimg), B, S, _st())
     return dimg
 
 
 def nhwc_to_nchw_f32(x):
     B, H, W, C = x.shape
     out = torch.empty((B, C * H * W), device=x.device, dtype=torch.float32)
-    _call("sg2_nhwc_to_nchw_f32", 1, _p(x), _p(out), B, H * W, C, _st())
+    if x.dtype == torch.float32:
+        _call("sg2_hwc_chw_f32", 1, _p(x), _p(out), B, H * W, C, 1, _st())
+    else:
+        _call("sg2_nhwc_to_nchw_f32", 1, _p(x), _p(out), B, H * W, C, _st())
     return out
 
 
-def nchw_f32_to_nhwc(x, B, H, W, C):
-    out = torch.empty((B, H, W, C), device=x.device, dtype=torch.bfloat16)
-    _call("sg2_nchw_f32_to_nhwc", 1, _p(x), _p(out), B, H * W, C, _st())
+def nchw_f32_to_nhwc(x, B, H, W, C, f32=False):
+    out = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32 if f32 else torch.bfloat16)
+    if f32:
+        _call("sg2_hwc_chw_f32", 1, _p(x), _p(out), B, H * W, C, 0, _st())
+    else:
+        _call("sg2_nchw_f32_to_nhwc", 1, _p(x), _p(out), B, H * W, C, _st())
     return out
 
 
@@ -549,19 +633,27 @@ def ca_glu_reparam_bwd(fc, eps, dmu, dlogvar, dc):
 
 def chw_hwc(x, B, C, HW, to_hwc):
     out = torch.empty_like(x)
-    _call("sg2_chw_hwc_bf16", 1, _p(x), _p(out), B, C, HW, int(to_hwc), _st())
+    if x.dtype == torch.float32:
+        _call("sg2_hwc_chw_f32", 1, _p(x), _p(out), B, HW, C, int(not to_hwc), _st())
+    else:
+        _call("sg2_chw_hwc_bf16", 1, _p(x), _p(out), B, C, HW, int(to_hwc), _st())
     return out
 
 
 def logits_fwd(x, w, bias, out=None):
     B, H, W, C = x.shape
     prob = torch.empty(B, device=x.device, dtype=torch.float32) if out is None else out
-    _call("sg2_logits_fwd", 1, _p(x), _p(w), _p(bias), _p(prob), B, H * W, C, _st())
+    _call("sg2_logits_fwd_f32" if x.dtype == torch.float32 else "sg2_logits_fwd", 1, _p(x), _p(w), _p(bias), _p(prob), B,
+          H * W, C, _st())
     return prob
 
 
 def logits_bwd(dprob, prob, x, w, dx, dx_accumulate, dw, dbias):
     B, H, W, C = x.shape
+    if x.dtype == torch.float32:
+        _call("sg2_logits_bwd_f32", 1, _p(dprob), _p(prob), _p(x), _p(w), _p(dx), int(dx_accumulate), _p(dw), _p(dbias), B,
+              H * W, C, _st())
+        return
     scratch = None
     if dw is not None:
         scratch = torch.empty(_lib.lib().sg2_logits_bwd_scratch_floats(B, H * W, C), device=x.device, dtype=torch.float32)

@@ -145,8 +145,12 @@ class FlatBucket:
 
 
 class FusedTrainer:
-    def __init__(self, netG, netsD, cfg, lr_g=None, lr_d=None, all_reduce=None):
+    def __init__(self, netG, netsD, cfg, lr_g=None, lr_d=None, all_reduce=None, precision=None):
+        """precision: None (config.PRECISION / what the networks were set to), 'bf16' or 'fp32' (fp32-accurate mode)."""
         self.netG, self.netsD = netG, list(netsD)
+        if precision is not None:
+            for net in [netG] + list(netsD):
+                net.set_precision(precision)
         self.cfg = cfg
         c = cfg.TRAIN.COEFF
         self.uncond, self.cal, self.kl = float(c.UNCOND_LOSS), float(c.CAL_LOSS), float(c.KL)
@@ -159,6 +163,9 @@ class FusedTrainer:
         self.lr_d = float(cfg.TRAIN.DISCRIMINATOR_LR if lr_d is None else lr_d)
         self.G = netG.engine()
         self.Ds = [d.engine() for d in self.netsD]
+        self.precise = self.G.precise
+        if any(d.precise != self.precise for d in self.Ds):
+            raise RuntimeError("sg2b200: G and D engines must run in the same precision")
         self.bG = FlatBucket(netG, with_ema=True)
         self.bD = [FlatBucket(d) for d in self.netsD]
         for eng in [self.G] + self.Ds:
@@ -302,7 +309,8 @@ class FusedTrainer:
                     self.bD[i].grad.zero_()       # red.global.add wgrads accumulate straight into the bucket
                 if self.batched_d:
                     S = real[i].shape[2]
-                    col3[i] = torch.empty((3, B * (S // 2) * (S // 2), 64), device=self.dev, dtype=torch.bfloat16)
+                    col3[i] = torch.empty((3, B * (S // 2) * (S // 2), 64), device=self.dev,
+                                          dtype=torch.float32 if self.precise else torch.bfloat16)
                     ops.stem_im2col(real[i], out=col3[i][0])
                     ops.stem_im2col(wrong[i], out=col3[i][1])
         g_zeroed = None

@@ -56,8 +56,19 @@ def cos(a, b):
     return float(torch.nn.functional.cosine_similarity(a.detach().flatten().double(), b.detach().flatten().double(), dim=0))
 
 
-def build_trainer_and_oracles(branches, seed=0, n_oracles=1, lr=None):
-    """sg2b200 networks + FusedTrainer and `n_oracles` OracleTrainers, all starting from the same weights."""
+def f64_state(sd):
+    """State dict for a float64 run of the oracle (the ground truth of the reference's arithmetic)."""
+    return {k: (v.detach().double() if v.is_floating_point() else v.detach().clone()) for k, v in sd.items()}
+
+
+def f64_batch(b):
+    cv = lambda t: t.double() if torch.is_tensor(t) and t.is_floating_point() else t
+    return {k: ([cv(t) for t in v] if isinstance(v, list) else cv(v)) for k, v in b.items()}
+
+
+def build_trainer_and_oracles(branches, seed=0, n_oracles=1, lr=None, oracle_f64=False):
+    """sg2b200 networks + FusedTrainer and `n_oracles` OracleTrainers, all starting from the same weights.
+    oracle_f64: the oracles run in float64."""
     from oracle.stackgan_oracle import OracleTrainer
     from sg2b200 import trainer, utils
     fp32_strict()
@@ -69,6 +80,8 @@ def build_trainer_and_oracles(branches, seed=0, n_oracles=1, lr=None):
     netG, netsD = utils.build_networks(cfg, "cuda")
     gs = {k: v.detach().clone() for k, v in netG.state_dict().items()}
     dss = [{k: v.detach().clone() for k, v in d.state_dict().items()} for d in netsD]
+    if oracle_f64:
+        gs, dss = f64_state(gs), [f64_state(d) for d in dss]
     orcs = [OracleTrainer(ocfg, gs, dss, device="cuda") for _ in range(n_oracles)]
     tr = trainer.FusedTrainer(netG, netsD, cfg, lr_g=lr, lr_d=lr)
     return cfg, ocfg, netG, netsD, tr, orcs
@@ -82,6 +95,8 @@ def train_batch(cfg, B, seed, n_classes=3):
 
 
 def oracle_step(orc, b, **kw):
+    if next(iter(orc.g.values())).dtype == torch.float64:
+        b = f64_batch(b)
     return orc.step(dict(z=b["z"], emb=b["emb"], eps=b["eps"], real=b["real"], wrong=b["wrong"],
                          labels=b["labels"].tolist()), **kw)
 
