@@ -1,27 +1,48 @@
-"""GPU parity: sg2b200 G_NET / D_NET* (CUDA kernels through the C ABI) vs the oracle on identical weights + inputs.
+"""GPU parity of the bf16 path: sg2b200 G_NET / D_NET* (CUDA kernels through the C ABI) against the oracle on identical
+weights and inputs.
 
-Metric: per-tensor relative error ||a-b|| / ||b|| against the fp32 oracle (TF32 off). The CUDA path stores every
-activation in bf16 (fp32 accumulation), so the error grows with depth: measured on B200 (profiles/r01_parity.md)
-img64 0.8e-2, img128 1.2e-2, img256 1.9e-2 after 8 / 14 / 20 conv+BN layers — the north-star 1e-2 holds per layer
-(tests/test_gpu_kernels.py: <= 5e-3) and for the first stage, not end-to-end through 20 bf16 layers.
-Gradients through LeakyReLU additionally see mask flips of pre-activations that lie within bf16 rounding of zero
-(each flip changes a local derivative from 1 to 0.2), which dominates the l2 error of D's gradients; they are
-therefore checked by cosine similarity as well. Tolerances below = measured value + margin, stated per check."""
+Metric: per-tensor relative error ||a - b|| / ||b|| against a FLOAT64 run of the oracle (the ground truth of the
+reference's arithmetic). The CUDA path stores every activation and every backward tensor in bf16 (fp32 accumulation).
+What that storage format costs is measured, not assumed: the oracle is run a second time with bf16 rounding at exactly
+the points where the CUDA path stores a tensor, forward and backward (`emulate_bf16`), i.e. an IDEAL implementation of
+bf16 storage in otherwise exact fp32 arithmetic. The test then is: the kernels are as close to the truth as that ideal
+implementation (factor YARD, plus a small floor for tensors whose error is itself tiny) — anything the kernels did
+wrong on top of the storage format would show up as a ratio > 1. Measured ratios on B200: 0.95 - 1.05 for every image,
+logit vector and flat gradient (profiles/r02_parity.md).
+
+Absolute numbers for the record (B200, profiles/r02_parity.md): images 64 / 128 / 256 px 0.8e-2 / 1.2e-2 / 1.8e-2 after
+8 / 14 / 20 bf16 conv + BN layers; G gradients 1-2e-2 flat; D logits 1-6e-3, x_immediate <= 1.2e-2; D gradients 6-11e-2
+flat (cosine >= 0.986): gradients through LeakyReLU are discontinuous at 0, so their relative error scales like the
+SQUARE ROOT of the storage precision (tests/test_gpu_precise.py explains and shows the same for fp32: 1e-3, not 1e-7).
+The north star's 1e-2 holds per layer (tests/test_gpu_kernels.py: <= 5e-3), for the first stage's image and for every
+loss (<= 1e-3); the fp32-accurate mode (tests/test_gpu_precise.py) is the one that reaches 1e-4."""
 import pytest
 import torch
 
-from oracle.stackgan_oracle import Cfg, d_forward, g_forward, is_param
-from tests.parity_util import fp32_strict, make_d, make_g, rel, report
+from oracle.stackgan_oracle import Cfg, d_forward, emulate_bf16, g_forward, is_param
+from tests.parity_util import f64_state, fp32_strict, make_d, make_g, rel, report
 
 pytestmark = pytest.mark.gpu
-FWD_TOL = 2.5e-2       # G images after up to 20 bf16 layers (measured <= 1.9e-2); mu / logvar are fp32 (1e-6)
-D_FWD_TOL = 2e-2       # D logits / x_immediate (measured <= 1.2e-2)
-G_GRAD_TOL = 7e-2      # GLU is smooth: measured 1-5e-2, cosine >= 0.999
-D_GRAD_COS = 0.98      # LeakyReLU mask flips: measured cosine 0.986-0.9999, l2 5-15e-2
+YARD = 1.3             # ours-vs-truth <= YARD x (ideal bf16 storage)-vs-truth (+ floor); measured 0.95 - 1.05
+FWD_TOL = 2.5e-2       # absolute backstop: G images after up to 20 bf16 layers (measured <= 1.84e-2)
+D_FWD_TOL = 2e-2       # absolute backstop: D logits / x_immediate (measured <= 1.23e-2)
+G_GRAD_TOL = 7e-2      # absolute backstop, per tensor (measured <= 5.7e-2, flat 2e-2, cosine >= 0.998)
+D_GRAD_COS = 0.98      # absolute backstop (measured cosine >= 0.986)
 
 
 def cos(a, b):
     return float(torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0))
+
+
+def _flat(ts):
+    return torch.cat([t.detach().double().flatten() for t in ts])
+
+
+def _track(sd):
+    for k in sd:
+        if is_param(k):
+            sd[k].requires_grad_(True)
+    return sd
 
 
 def _g_case(cfg, B, training=True):
@@ -39,33 +60,36 @@ def _g_case(cfg, B, training=True):
 def test_g_forward_backward(branches, B):
     cfg = Cfg(BRANCH_NUM=branches)
     net, sd, z, emb, eps, g = _g_case(cfg, B)
-    for k in sd:
-        if is_param(k):
-            sd[k].requires_grad_(True)
+    sdq = _track({k: v.clone() for k, v in sd.items()})          # ideal bf16 storage
+    sdt = _track(f64_state(sd))                                   # truth
     imgs, mu, logvar = net(z, emb, eps=eps)
-    oimgs, omu, ologvar = g_forward(sd, z, emb, eps, cfg, True)
-    pairs = [(f"img{i}", rel(a, b)) for i, (a, b) in enumerate(zip(imgs, oimgs))]
-    pairs += [("mu", rel(mu, omu)), ("logvar", rel(logvar, ologvar))]
-    ok, msg = report(pairs, FWD_TOL)
-    assert ok, msg
+    timgs, tmu, tlogvar = g_forward(sdt, z.double(), emb.double(), eps.double(), cfg, True)
+    with emulate_bf16():
+        qimgs, qmu, qlogvar = g_forward(sdq, z, emb, eps, cfg, True)
+    for i, (a, q, t) in enumerate(zip(imgs, qimgs, timgs)):
+        e, eq = rel(a, t), rel(q, t)
+        assert e <= YARD * eq + 1e-3 and e <= FWD_TOL, (f"img{i}", e, eq)
+    assert rel(mu, tmu) < 1e-5 and rel(logvar, tlogvar) < 1e-5     # CA_NET runs in fp32
     # BN running statistics updated like nn.BatchNorm (momentum 0.1, unbiased var)
     st = net.state_dict()
-    pairs = [(k, rel(st[k].float(), sd[k].float())) for k in sd if "running" in k]
-    ok, msg = report(pairs, FWD_TOL)
+    ok, msg = report([(k, rel(st[k].float(), sdt[k].float())) for k in sdt if "running" in k], FWD_TOL)
     assert ok, msg
-    assert all(int(st[k]) == int(sd[k]) for k in sd if "num_batches" in k)
+    assert all(int(st[k]) == int(sdt[k]) for k in sdt if "num_batches" in k)
     # backward: random cotangents on every output
-    rs = [torch.randn(i.shape, generator=g).cuda() for i in oimgs]
+    rs = [torch.randn(i.shape, generator=g).cuda() for i in timgs]
     rmu, rlv = torch.randn(mu.shape, generator=g).cuda(), torch.randn(mu.shape, generator=g).cuda()
-    loss = sum((a * r).sum() for a, r in zip(imgs, rs)) + (mu * rmu).sum() + (logvar * rlv).sum()
-    oloss = sum((a * r).sum() for a, r in zip(oimgs, rs)) + (omu * rmu).sum() + (ologvar * rlv).sum()
-    loss.backward()
-    oloss.backward()
-    pairs = [(k, rel(p.grad, sd[k].grad)) for k, p in net.named_parameters()]
-    ok, msg = report(pairs, G_GRAD_TOL)
+    L = lambda t3: sum((a * r).sum() for a, r in zip(t3[0], rs)) + (t3[1] * rmu).sum() + (t3[2] * rlv).sum()
+    L((imgs, mu, logvar)).backward()
+    L((timgs, tmu, tlogvar)).backward()
+    with emulate_bf16():
+        L((qimgs, qmu, qlogvar)).backward()
+    names = [k for k, _ in net.named_parameters()]
+    ours = {k: p.grad for k, p in net.named_parameters()}
+    e, eq = rel(_flat(ours[k] for k in names), _flat(sdt[k].grad for k in names)), rel(_flat(sdq[k].grad for k in names), _flat(sdt[k].grad for k in names))
+    assert e <= YARD * eq + 1e-3, (e, eq)
+    ok, msg = report([(k, rel(ours[k], sdt[k].grad)) for k in names], G_GRAD_TOL)
     assert ok, msg
-    worst = min(cos(p.grad, sd[k].grad) for k, p in net.named_parameters())
-    assert worst > 0.998, worst
+    assert min(cos(ours[k], sdt[k].grad) for k in names) > 0.998
 
 
 def test_g_eval_mode_uses_running_stats():
@@ -107,35 +131,42 @@ def test_d_forward_backward(which, B):
     cfg = Cfg()
     fp32_strict()
     net, sd = make_d(cfg, which, seed=2)
-    for k in sd:
-        if is_param(k):
-            sd[k].requires_grad_(True)
+    sdq = _track({k: v.clone() for k, v in sd.items()})
+    sdt = _track(f64_state(sd))
     g = torch.Generator().manual_seed(5)
     S = 64 * 2 ** which
     base = (torch.rand(B, 3, S, S, generator=g) * 2 - 1).cuda()
     c0 = torch.randn(B, cfg.EMBEDDING_DIM, generator=g).cuda()
     # non-leaf image and c (the G-step situation): gradients must flow to both
-    img = base.clone().requires_grad_(True)
-    c = c0.clone().requires_grad_(True)
-    oimg = base.clone().requires_grad_(True)
-    oc = c0.clone().requires_grad_(True)
+    img, c = base.clone().requires_grad_(True), c0.clone().requires_grad_(True)
+    qimg, qc = base.clone().requires_grad_(True), c0.clone().requires_grad_(True)
+    timg, tc = base.double().requires_grad_(True), c0.double().requires_grad_(True)
     (cond, uncond), x_imm = net(img * 1.0, c * 1.0)
-    (ocond, ouncond), ox = d_forward(sd, oimg * 1.0, oc * 1.0, which, cfg, True)
-    pairs = [("cond", rel(cond, ocond)), ("uncond", rel(uncond, ouncond)), ("x_immediate", rel(x_imm, ox))]
-    ok, msg = report(pairs, D_FWD_TOL)
-    assert ok, msg
+    (tcond, tuncond), tx = d_forward(sdt, timg * 1.0, tc * 1.0, which, cfg, True)
+    with emulate_bf16():
+        (qcond, quncond), qx = d_forward(sdq, qimg * 1.0, qc * 1.0, which, cfg, True)
+    for name, a, q, t in (("cond", cond, qcond, tcond), ("uncond", uncond, quncond, tuncond), ("x_immediate", x_imm, qx, tx)):
+        e, eq = rel(a, t), rel(q, t)
+        # B-element logit vectors: the two bf16 realisations differ by up to 2x on a handful of numbers
+        assert e <= 2.0 * eq + 2e-3 and e <= D_FWD_TOL, (name, e, eq)
     r1, r2 = torch.randn(B, generator=g).cuda(), torch.randn(B, generator=g).cuda()
-    r3 = torch.randn(ox.shape, generator=g).cuda() * 0.01
+    r3 = torch.randn(tx.shape, generator=g).cuda() * 0.01
     ((cond * r1).sum() + (uncond * r2).sum() + (x_imm * r3).sum()).backward()
-    ((ocond * r1).sum() + (ouncond * r2).sum() + (ox * r3).sum()).backward()
-    coss = [(k, cos(p.grad, sd[k].grad)) for k, p in net.named_parameters()]
-    coss += [("d_img", cos(img.grad, oimg.grad)), ("d_c", cos(c.grad, oc.grad))]
-    bad = [(k, v) for k, v in coss if not v > D_GRAD_COS]
+    ((tcond * r1).sum() + (tuncond * r2).sum() + (tx * r3).sum()).backward()
+    with emulate_bf16():
+        ((qcond * r1).sum() + (quncond * r2).sum() + (qx * r3).sum()).backward()
+    names = [k for k, _ in net.named_parameters()]
+    ours = {k: p.grad for k, p in net.named_parameters()} | {"d_img": img.grad, "d_c": c.grad}
+    emu = {k: sdq[k].grad for k in names} | {"d_img": qimg.grad, "d_c": qc.grad}
+    truth = {k: sdt[k].grad for k in names} | {"d_img": timg.grad, "d_c": tc.grad}
+    e, eq = rel(_flat(ours[k] for k in truth), _flat(truth.values())), rel(_flat(emu[k] for k in truth), _flat(truth.values()))
+    assert e <= YARD * eq + 1e-3, (e, eq)
+    bad = [(k, cos(ours[k], truth[k])) for k in truth if not cos(ours[k], truth[k]) > D_GRAD_COS]
     assert not bad, bad
-    norms = [(k, float(p.grad.norm() / (sd[k].grad.norm() + 1e-30))) for k, p in net.named_parameters()]
+    norms = [(k, float(ours[k].norm() / (truth[k].norm() + 1e-30))) for k in names]
     assert all(0.9 < v < 1.1 for _, v in norms), [kv for kv in norms if not 0.9 < kv[1] < 1.1]
     st = net.state_dict()
-    ok, msg = report([(k, rel(st[k].float(), sd[k].float())) for k in sd if "running" in k], D_FWD_TOL)
+    ok, msg = report([(k, rel(st[k].float(), sdt[k].float())) for k in sdt if "running" in k], D_FWD_TOL)
     assert ok, msg
 
 

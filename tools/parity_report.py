@@ -70,48 +70,45 @@ def section_repro(branches, B, steps=2):
     return out
 
 
-def section_step(branches, B, steps=1):
-    cfg, ocfg, netG, netsD, tr, (o32, oq) = build_trainer_and_oracles(branches, seed=0, n_oracles=2)
-    out = {"steps": []}
-    for s in range(steps):
-        b = train_batch(cfg, B, 11 + s)
-        w0 = {k: v.detach().clone() for k, v in netG.state_dict().items() if is_param(k)}
+def _flat(d, prefix):
+    return torch.cat([v.detach().double().flatten() for k, v in d.items() if k.startswith(prefix)])
+
+
+def section_step(branches, B, precision="bf16", lr=0.0):
+    """One fused step against the FLOAT64 oracle (truth); the fp32 oracle (PyTorch CUDA fp32, the reference's own
+    arithmetic) and the bf16-emulating oracle (ideal bf16 storage) are measured against the same truth as yardsticks.
+    lr = 0: a comparison of gradients (the G step sees identical D weights in every arm)."""
+    from oracle.stackgan_oracle import OracleTrainer
+    from sg2b200 import config
+    from tests.parity_util import f64_state
+    config.set_precision(precision)
+    try:
+        cfg, ocfg, netG, netsD, tr, (o32, oq) = build_trainer_and_oracles(branches, seed=0, n_oracles=2, lr=lr)
+        o64 = OracleTrainer(ocfg, f64_state({k: v.detach() for k, v in o32.g.items()}),
+                            [f64_state({k: v.detach() for k, v in d.items()}) for d in o32.ds], device="cuda")
+        b = train_batch(cfg, B, 11)
         losses = tr.step(b["z"], b["emb"], b["real"], b["wrong"], b["labels"], eps=b["eps"]).cpu().tolist()
+        rt = oracle_step(o64, b, keep_grads=True)
         r32 = oracle_step(o32, b, keep_grads=True)
         with emulate_bf16():
             rq = oracle_step(oq, b, keep_grads=True)
         names = [f"errD{i}" for i in range(branches)] + ["errG_total", "kl", "cal"]
-        rec = {"losses": {n: {"ours": a, "fp32": x, "emu": y, "rel_fp32": abs(a - x) / (abs(x) + 1e-12),
-                              "rel_emu": abs(a - y) / (abs(y) + 1e-12)}
-                          for n, a, x, y in zip(names, losses, loss_vector(r32), loss_vector(rq))}}
-        ours = bucket_grads(tr)
-        for tag, ref in (("fp32", oracle_grads(r32)), ("emu", oracle_grads(rq))):
-            per_net = {}
-            for k, g in ours.items():
-                net = k.split(".")[0]
-                per_net.setdefault(net, []).append((k, rel(g, ref[k]), cos(g, ref[k])))
-            rec[f"grads_vs_{tag}"] = {net: summarise(v) for net, v in per_net.items()}
-            # whole-network gradient (all parameters concatenated)
-            for net in per_net:
-                a = torch.cat([ours[k].flatten() for k in ours if k.startswith(net + ".")])
-                r = torch.cat([ref[k].flatten() for k in ours if k.startswith(net + ".")])
-                rec[f"grads_vs_{tag}"][net]["flat_rel"] = rel(a, r)
-                rec[f"grads_vs_{tag}"][net]["flat_cos"] = cos(a, r)
-        # emu oracle vs fp32 oracle: the quantisation gap itself
-        per = [(k, rel(oracle_grads(rq)[k], oracle_grads(r32)[k]), cos(oracle_grads(rq)[k], oracle_grads(r32)[k])) for k in ours]
-        rec["emu_vs_fp32_grads"] = summarise(per)
-        # updated weights: how far apart are the Adam steps (units of lr)
-        lr = ocfg.LR_G
+        lt = loss_vector(rt)
+        relv = lambda xs: [abs(a - t) / (abs(t) + 1e-12) for a, t in zip(xs, lt)]
+        rec = {"precision": precision, "lr": lr,
+               "loss_rel_vs_f64": {"names": names, "ours": relv(losses), "fp32_oracle": relv(loss_vector(r32)),
+                                   "bf16_emulating_oracle": relv(loss_vector(rq))}}
+        truth = oracle_grads(rt)
+        arms = {"ours": bucket_grads(tr), "fp32_oracle": oracle_grads(r32), "bf16_emulating_oracle": oracle_grads(rq)}
+        nets_ = ["G"] + [f"D{i}" for i in range(branches)]
+        rec["grad_flat_rel_vs_f64"] = {arm: {n: rel(_flat(g, n + "."), _flat(truth, n + ".")) for n in nets_} for arm, g in arms.items()}
+        rec["grad_flat_cos_vs_f64"] = {arm: {n: cos(_flat(g, n + "."), _flat(truth, n + ".")) for n in nets_} for arm, g in arms.items()}
+        rec["grad_per_tensor_vs_f64"] = {arm: summarise([(k, rel(g[k], truth[k]), cos(g[k], truth[k])) for k in truth]) for arm, g in arms.items()}
         sd = netG.state_dict()
-        upd = []
-        for k in param_keys(o32.g):
-            d_ours, d_ref = sd[k].detach() - w0[k], o32.g[k].detach() - w0[k]
-            upd.append((k, float((d_ours - d_ref).abs().mean()) / lr, cos(d_ours, d_ref)))
-        rec["G_update_vs_fp32"] = {"mean_abs_diff_over_lr_max": max(u[1] for u in upd), "cos_min": min(u[2] for u in upd)}
-        bn = [(k, rel(sd[k].float(), o32.g[k].float())) for k in o32.g if "running" in k]
-        rec["G_running_stats_rel_max_fp32"] = max(v for _, v in bn)
-        out["steps"].append(rec)
-    return out
+        rec["G_running_stats_rel_max_vs_f64"] = max(rel(sd[k].float(), o64.g[k].float()) for k in o64.g if "running" in k)
+        return rec
+    finally:
+        config.set_precision("bf16")
 
 
 def section_forward():
@@ -124,33 +121,40 @@ def section_forward():
         z = torch.randn(B, cfg.Z_DIM, generator=g).cuda()
         emb = torch.randn(B, cfg.TEXT_DIM, generator=g).cuda()
         eps = torch.randn(B, cfg.EMBEDDING_DIM, generator=g).cuda()
+        from tests.parity_util import f64_state
         sdq = {k: v.clone() for k, v in sd.items()}
-        sds = [sd, sdq]
-        for s in sds:
+        sdt = f64_state(sd)
+        for s in (sd, sdq, sdt):
             for k in s:
                 if is_param(k):
                     s[k].requires_grad_(True)
         imgs, mu, logvar = net(z, emb, eps=eps)
         o = g_forward(sd, z, emb, eps, cfg, True)
+        t = g_forward(sdt, z.double(), emb.double(), eps.double(), cfg, True)
         with emulate_bf16():
             q = g_forward(sdq, z, emb, eps, cfg, True)
         rs = [torch.randn(i.shape, generator=g).cuda() for i in o[0]]
         rmu, rlv = torch.randn(mu.shape, generator=g).cuda(), torch.randn(mu.shape, generator=g).cuda()
-        L = lambda t: sum((a * r).sum() for a, r in zip(t[0], rs)) + (t[1] * rmu).sum() + (t[2] * rlv).sum()
+        L = lambda t_: sum((a * r).sum() for a, r in zip(t_[0], rs)) + (t_[1] * rmu).sum() + (t_[2] * rlv).sum()
         L((imgs, mu, logvar)).backward()
         L(o).backward()
+        L(t).backward()
         with emulate_bf16():
             L(q).backward()
-        rec = {"img_rel_fp32": [rel(a, b) for a, b in zip(imgs, o[0])], "img_rel_emu": [rel(a, b) for a, b in zip(imgs, q[0])],
-               "emu_vs_fp32_img": [rel(a, b) for a, b in zip(q[0], o[0])], "mu_rel": rel(mu, o[1])}
-        rec["grads_vs_fp32"] = summarise([(k, rel(p.grad, sd[k].grad), cos(p.grad, sd[k].grad)) for k, p in net.named_parameters()])
-        rec["grads_vs_emu"] = summarise([(k, rel(p.grad, sdq[k].grad), cos(p.grad, sdq[k].grad)) for k, p in net.named_parameters()])
+        rec = {"img_rel_vs_f64": {"ours": [rel(a, b) for a, b in zip(imgs, t[0])], "fp32_oracle": [rel(a, b) for a, b in zip(o[0], t[0])],
+                                  "bf16_emulating_oracle": [rel(a, b) for a, b in zip(q[0], t[0])]}, "mu_rel": rel(mu, t[1])}
+        for tag, s_ in (("ours", None), ("fp32_oracle", sd), ("bf16_emulating_oracle", sdq)):
+            gr = {k: (p.grad if s_ is None else s_[k].grad) for k, p in net.named_parameters()}
+            rec[f"grads_vs_f64_{tag}"] = summarise([(k, rel(gr[k], sdt[k].grad), cos(gr[k], sdt[k].grad)) for k in gr])
+            rec[f"grads_vs_f64_{tag}"]["flat_rel"] = rel(torch.cat([gr[k].double().flatten() for k in gr]), torch.cat([sdt[k].grad.flatten() for k in gr]))
         out[f"G_branches{branches}_B{B}"] = rec
     for which, B in ((0, 8), (1, 6), (2, 4)):
         cfg = Cfg()
         net, sd = make_d(cfg, which, seed=2)
+        from tests.parity_util import f64_state
         sdq = {k: v.clone() for k, v in sd.items()}
-        for s in (sd, sdq):
+        sdt = f64_state(sd)
+        for s in (sd, sdq, sdt):
             for k in s:
                 if is_param(k):
                     s[k].requires_grad_(True)
@@ -159,23 +163,27 @@ def section_forward():
         base = (torch.rand(B, 3, S, S, generator=g) * 2 - 1).cuda()
         c0 = torch.randn(B, cfg.EMBEDDING_DIM, generator=g).cuda()
         leaves = [(base.clone().requires_grad_(True), c0.clone().requires_grad_(True)) for _ in range(3)]
+        lt = (base.double().requires_grad_(True), c0.double().requires_grad_(True))
         (cond, uncond), x_imm = net(leaves[0][0] * 1.0, leaves[0][1] * 1.0)
         (oc, ou), ox = d_forward(sd, leaves[1][0] * 1.0, leaves[1][1] * 1.0, which, cfg, True)
+        (tc, tu), tx = d_forward(sdt, lt[0] * 1.0, lt[1] * 1.0, which, cfg, True)
         with emulate_bf16():
             (qc, qu), qx = d_forward(sdq, leaves[2][0] * 1.0, leaves[2][1] * 1.0, which, cfg, True)
         r1, r2 = torch.randn(B, generator=g).cuda(), torch.randn(B, generator=g).cuda()
         r3 = torch.randn(ox.shape, generator=g).cuda() * 0.01
         ((cond * r1).sum() + (uncond * r2).sum() + (x_imm * r3).sum()).backward()
         ((oc * r1).sum() + (ou * r2).sum() + (ox * r3).sum()).backward()
+        ((tc * r1).sum() + (tu * r2).sum() + (tx * r3).sum()).backward()
         with emulate_bf16():
             ((qc * r1).sum() + (qu * r2).sum() + (qx * r3).sum()).backward()
-        rec = {"fwd_rel_fp32": [rel(cond, oc), rel(uncond, ou), rel(x_imm, ox)],
-               "fwd_rel_emu": [rel(cond, qc), rel(uncond, qu), rel(x_imm, qx)]}
-        for tag, s, lv in (("fp32", sd, leaves[1]), ("emu", sdq, leaves[2])):
-            pairs = [(k, rel(p.grad, s[k].grad), cos(p.grad, s[k].grad)) for k, p in net.named_parameters()]
-            pairs += [("d_img", rel(leaves[0][0].grad, lv[0].grad), cos(leaves[0][0].grad, lv[0].grad)),
-                      ("d_c", rel(leaves[0][1].grad, lv[1].grad), cos(leaves[0][1].grad, lv[1].grad))]
-            rec[f"grads_vs_{tag}"] = summarise(pairs)
+        rec = {"fwd_rel_vs_f64": {"names": ["cond", "uncond", "x_immediate"], "ours": [rel(cond, tc), rel(uncond, tu), rel(x_imm, tx)],
+                                  "fp32_oracle": [rel(oc, tc), rel(ou, tu), rel(ox, tx)],
+                                  "bf16_emulating_oracle": [rel(qc, tc), rel(qu, tu), rel(qx, tx)]}}
+        tg = {k: sdt[k].grad for k, _ in net.named_parameters()} | {"d_img": lt[0].grad, "d_c": lt[1].grad}
+        for tag, s, lv in (("ours", None, leaves[0]), ("fp32_oracle", sd, leaves[1]), ("bf16_emulating_oracle", sdq, leaves[2])):
+            gr = {k: (p.grad if s is None else s[k].grad) for k, p in net.named_parameters()} | {"d_img": lv[0].grad, "d_c": lv[1].grad}
+            rec[f"grads_vs_f64_{tag}"] = summarise([(k, rel(gr[k], tg[k]), cos(gr[k], tg[k])) for k in gr])
+            rec[f"grads_vs_f64_{tag}"]["flat_rel"] = rel(torch.cat([gr[k].double().flatten() for k in gr]), torch.cat([tg[k].flatten() for k in gr]))
         out[f"D{which}_B{B}"] = rec
     return out
 
@@ -187,17 +195,17 @@ def main():
     args = ap.parse_args()
     res = {}
     res["forward"] = section_forward()
-    print(json.dumps(res["forward"], indent=1), flush=True)
     res["repro_3stage_B6"] = section_repro(3, 6)
-    print(json.dumps(res["repro_3stage_B6"], indent=1), flush=True)
-    res["step_1stage_B8"] = section_step(1, 8)
-    res["step_3stage_B6"] = section_step(3, 6)
+    for prec in ("bf16", "fp32"):
+        res[f"step_1stage_B8_{prec}"] = section_step(1, 8, prec)
+        if not args.quick:
+            res[f"step_3stage_B24_{prec}"] = section_step(3, 24, prec)
     if not args.quick:
-        res["step_3stage_B24"] = section_step(3, 24)
+        res["step_3stage_B24_bf16_lr2e-4"] = section_step(3, 24, "bf16", lr=2e-4)
         res["repro_3stage_B24"] = section_repro(3, 24)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
-    print(json.dumps({k: v for k, v in res.items() if k != "forward"}, indent=1))
+    print(json.dumps(res, indent=1))
 
 
 if __name__ == "__main__":
