@@ -403,7 +403,6 @@ static int launch_tile(const GatherDesc& d, cudaStream_t st) {
   const int nt = d.ntaps / d.nmaps;
   if (nt == 1 && bn == 64 && bk == 64) return launch_tile_t<64, 64, 1>(d, pl, st);   // 64 -> 64 GEMM tiles (D stems)
   if (nt != 4 && nt != 9) return 1;
-  if (d.stats && d.stats_bg > 0 && (bn + 31) / 32 > 4) return 1;  // grouped statistics need the register-held sums
 #define SG2_CASE(BN_, BK_)                                                   \
   if (bn == BN_ && bk == BK_)                                                \
     return nt == 9 ? launch_tile_t<BN_, BK_, 9>(d, pl, st) : launch_tile_t<BN_, BK_, 4>(d, pl, st);

@@ -33,7 +33,7 @@ struct Geo {
   int vc, cpb, rpb;
   dim3 grid, block;
 };
-static Geo make_geo(long long P, int C, int max_row_blocks, int width = 8) {
+static Geo make_geo(long long P, int C, int max_row_blocks, int width = 8, int min_iters = 8) {
   Geo g;
   g.vc = C / width;
   g.cpb = g.vc < 256 ? g.vc : 256;
@@ -42,7 +42,7 @@ static Geo make_geo(long long P, int C, int max_row_blocks, int width = 8) {
   g.rpb = 256 / g.cpb;
   if (g.rpb < 1) g.rpb = 1;
   const int col_blocks = g.vc / g.cpb;
-  long long rb = (P + (long long)g.rpb * 8 - 1) / ((long long)g.rpb * 8);   // >= 8 row iterations per block
+  long long rb = (P + (long long)g.rpb * min_iters - 1) / ((long long)g.rpb * min_iters);   // >= min_iters row iterations per block
   long long cap = max_row_blocks / col_blocks;
   if (cap < 1) cap = 1;
   if (rb > cap) rb = cap;
@@ -254,6 +254,109 @@ __global__ void unpack_wgrad_kernel(int kind, const float* __restrict__ dwpk, fl
   }
 }
 
+// ---- fused-upsample layers stored [Cout][3x3][Cin] (the fused trainer's buckets): streaming pack / unpack.
+// These run on the tail of the generator's backward pass (wgrad -> unpack -> Adam -> pack of the first, largest
+// layers), so they are written for bandwidth: every global access is a 16-byte vector in a fully coalesced row.
+// up_lo / up_hi give the 3x3 taps that collapse onto 2x2 tap (a, b) of output parity (py, px).
+__device__ __forceinline__ void upconv_presum(const float (&t)[9], float (&o)[16]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int py = g >> 1, px = g & 1;
+        float acc = 0.f;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+            if (kh >= up_lo(py, a) && kh <= up_hi(py, a) && kw >= up_lo(px, b) && kw <= up_hi(px, b)) acc += t[kh * 3 + kw];
+        o[g * 4 + a * 2 + b] = acc;
+      }
+}
+// master [Cout][9][Cin] fp32 -> wpk [4][Cout][4][Cin] bf16 and wpkT [Cin][16][Cout] bf16. Tile = 64 co x 64 ci per block.
+__global__ void __launch_bounds__(256) pack_upconv_ohwi_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk,
+                                                               __nv_bfloat16* __restrict__ wpkT, int Cout, int Cin) {
+  __shared__ __nv_bfloat16 tile[4][64][72];   // [slot within group][ci][co (+pad)]
+  const int ci_tiles = Cin / 64;
+  const int co0 = (blockIdx.x / ci_tiles) * 64, ci0 = (blockIdx.x % ci_tiles) * 64;
+  for (int g = 0; g < 4; ++g) {
+    for (int e = threadIdx.x; e < 64 * 8; e += 256) {    // (co, 8-channel vector)
+      const int v8 = e & 7, col = e >> 3;
+      const int co = co0 + col, ci = ci0 + v8 * 8;
+      float sl[4][8];
+#pragma unroll
+      for (int j8 = 0; j8 < 2; ++j8) {
+        float4 t4[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) t4[t] = *reinterpret_cast<const float4*>(w + ((long long)co * 9 + t) * Cin + ci + j8 * 4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float t9[9], o16[16];
+#pragma unroll
+          for (int t = 0; t < 9; ++t) t9[t] = c == 0 ? t4[t].x : (c == 1 ? t4[t].y : (c == 2 ? t4[t].z : t4[t].w));
+          upconv_presum(t9, o16);
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) sl[s4][j8 * 4 + c] = o16[g * 4 + s4];
+        }
+      }
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const uint4 pk = pack8(sl[s4]);
+        if (wpk) *reinterpret_cast<uint4*>(wpk + ((((long long)g * Cout + co) * 4) + s4) * Cin + ci) = pk;
+        const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(&pk);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tile[s4][v8 * 8 + j][col] = pb[j];
+      }
+    }
+    __syncthreads();
+    if (wpkT) {
+      for (int e = threadIdx.x; e < 4 * 64 * 8; e += 256) {   // (slot, ci, 8-co vector): 128-byte rows of wpkT
+        const int v8 = e & 7, cl = (e >> 3) & 63, s4 = e >> 9;
+        *reinterpret_cast<uint4*>(wpkT + ((long long)(ci0 + cl) * 16 + g * 4 + s4) * Cout + co0 + v8 * 8) =
+            *reinterpret_cast<const uint4*>(&tile[s4][cl][v8 * 8]);
+      }
+    }
+    __syncthreads();
+  }
+}
+// dwpk [Cout][16 jobs][Cin] fp32 -> grad [Cout][9][Cin] fp32 (=|+=): tap (kh, kw) sums the jobs it was folded into
+__global__ void __launch_bounds__(256) unpack_upconv_ohwi_kernel(const float4* __restrict__ dwpk, float4* __restrict__ grad,
+                                                                 int Cout, int Cin4, int accumulate) {
+  const long long total = (long long)Cout * Cin4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long co = i / Cin4;
+    const int c4 = (int)(i - co * Cin4);
+    float4 j16[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) j16[j] = dwpk[(co * 16 + j) * Cin4 + c4];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            if (kh < up_lo(py, a) || kh > up_hi(py, a)) continue;
+#pragma unroll
+            for (int px = 0; px < 2; ++px)
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                if (kw < up_lo(px, b) || kw > up_hi(px, b)) continue;
+                const float4 t = j16[(py * 2 + px) * 4 + a * 2 + b];
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+              }
+          }
+        float4* o = grad + (co * 9 + kh * 3 + kw) * Cin4 + c4;
+        if (accumulate) { const float4 d = *o; v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w; }
+        *o = v;
+      }
+  }
+}
+
 // ============================================================================================ BN statistics
 // Per-channel sum / sum of squares of a [P][C] tensor into a ZEROED fp64 workspace stats[2][C]. Each block forms its
 // partial sums in a fixed order in fp32; blocks combine with fp64 atomics (order-independent beyond 2^-53).
@@ -281,12 +384,24 @@ __global__ void bn_stats_kernel(const void* __restrict__ xin, uint4* __restrict_
     if (IN_F32) {
       const float4* x4 = reinterpret_cast<const float4*>(xin) + (r * vc + col) * 2;
       float4 lo = x4[0], hi = x4[1];
-      for (int sp = 1; sp < nsplit; ++sp) {
-        const float4* xs = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xin) + (long long)sp * slab) +
-                           (r * vc + col) * 2;
-        const float4 a = xs[0], b = xs[1];
-        lo.x += a.x; lo.y += a.y; lo.z += a.z; lo.w += a.w;
-        hi.x += b.x; hi.y += b.y; hi.z += b.z; hi.w += b.w;
+      // slabs are added in slab order (fixed summation order); four slabs' loads are in flight at a time
+      for (int sp = 1; sp < nsplit; sp += 4) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int s2 = sp + u < nsplit ? sp + u : 0;
+          const float4* xs = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xin) + (long long)s2 * slab) +
+                             (r * vc + col) * 2;
+          a[u] = xs[0];
+          b[u] = xs[1];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (sp + u < nsplit) {
+            lo.x += a[u].x; lo.y += a[u].y; lo.z += a[u].z; lo.w += a[u].w;
+            hi.x += b[u].x; hi.y += b[u].y; hi.z += b[u].z; hi.w += b[u].w;
+          }
+        }
       }
       float t[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
       if (epi_mode) {
@@ -318,6 +433,38 @@ __global__ void bn_stats_kernel(const void* __restrict__ xin, uint4* __restrict_
       atomicAdd(&stats[col * 8 + j], (double)s[j]);
       atomicAdd(&stats[C + col * 8 + j], (double)q[j]);
     }
+  }
+}
+
+// Many slabs (the tile wgrad kernel writes one per CTA lane, up to 148): block = 32 float4 columns x 8 slab lanes; lane l
+// adds slabs l, l+8, ... in order, the 8 lane sums are combined in lane order through shared memory — a fixed summation
+// tree (reproducible) with 8 x the loads in flight of the serial loop below.
+__global__ void __launch_bounds__(256) reduce_slabs_wide_kernel(const float4* __restrict__ parts, int nslabs, long long n4,
+                                                                long long slab4, float4* __restrict__ dst, int accumulate) {
+  __shared__ float4 sh[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (long long c0 = (long long)blockIdx.x * 32; c0 < n4; c0 += (long long)gridDim.x * 32) {
+    const long long col = c0 + tx;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < n4) {
+      for (int sp = ty; sp < nslabs; sp += 32) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = parts[(long long)(sp + 8 * u < nslabs ? sp + 8 * u : ty) * slab4 + col];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (sp + 8 * u < nslabs) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+      }
+    }
+    sh[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && col < n4) {
+#pragma unroll
+      for (int l = 1; l < 8; ++l) { const float4 b = sh[l][tx]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+      if (accumulate) { const float4 d = dst[col]; a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w; }
+      dst[col] = a;
+    }
+    __syncthreads();
   }
 }
 
@@ -1008,6 +1155,12 @@ extern "C" {
 
 int sg2_pack_weights(int kind, const float* w, void* wpk, void* wpkT, int Cout, int Cin, int CoP, int CiP,
                      int src_ohwi, void* stream) {
+  if (kind == SG2_UPCONV3x3 && src_ohwi && CoP == Cout && CiP == Cin && Cout % 64 == 0 && Cin % 64 == 0 &&
+      !(reinterpret_cast<uintptr_t>(w) & 15)) {
+    pack_upconv_ohwi_kernel<<<(Cout / 64) * (Cin / 64), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wpk,
+                                                                                      (__nv_bfloat16*)wpkT, Cout, Cin);
+    return launch_ok("pack_upconv_ohwi");
+  }
   return pack_weights_t<__nv_bfloat16>(kind, w, (__nv_bfloat16*)wpk, (__nv_bfloat16*)wpkT, Cout, Cin, CoP, CiP, src_ohwi,
                                        stream);
 }
@@ -1031,6 +1184,12 @@ int sg2_pack_transpose(int kind, const void* wpk, void* wpkT, int Cout, int Cin,
 int sg2_unpack_wgrad(int kind, const float* dwpk, float* grad, int Cout, int Cin, int CoP, int CiP, int accumulate,
                      int dst_ohwi, void* stream) {
   if (kind < 0 || kind > 4) EW_FAIL(SG2_EINVAL, "unpack_wgrad: bad kind");
+  if (kind == SG2_UPCONV3x3 && dst_ohwi && CoP == Cout && CiP == Cin && Cin % 4 == 0 &&
+      !((reinterpret_cast<uintptr_t>(dwpk) | reinterpret_cast<uintptr_t>(grad)) & 15)) {
+    unpack_upconv_ohwi_kernel<<<grid1d((long long)Cout * (Cin / 4)), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)dwpk, (float4*)grad, Cout, Cin / 4, accumulate);
+    return launch_ok("unpack_upconv_ohwi");
+  }
   const int kk = (kind == SG2_CONV3x3 || kind == SG2_UPCONV3x3) ? 9 : ((kind == SG2_GEMM || kind == SG2_STEM4x4) ? 1 : 16);
   (void)kk;
   long long nblk = (long long)Cout * ((Cin + 31) / 32);
@@ -1063,7 +1222,8 @@ int sg2_splitk_finish(const float* parts, int nsplit, long long slab, void* y, l
   if (epi_mode != 0 && epi_mode != SG2_EPI_ADD && epi_mode != SG2_EPI_LRELU_MASK) EW_FAIL(SG2_EINVAL, "splitk_finish: epilogue mode %d", epi_mode);
   if (epi_mode && !epi_src) EW_FAIL(SG2_EINVAL, "splitk_finish: epilogue operand missing");
   P /= groups;
-  Geo g = make_geo(P, C, 148 * 4);
+  // split-K outputs are small (the layers that cannot fill the GPU): one or two rows per thread, many blocks
+  Geo g = make_geo(P, C, 148 * 16, 8, nsplit > 1 ? 1 : 4);
   g.grid.z = groups;
   bn_stats_kernel<true><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(parts, (uint4*)y, P, g.vc, g.cpb, g.rpb, stats, C,
                                                                       nsplit, slab, (const uint4*)epi_src, epi_mode);
@@ -1074,8 +1234,15 @@ int sg2_reduce_slabs(const float* parts, int nslabs, long long n, long long slab
                      void* stream) {
   if (nslabs < 1 || (n % 4) || (slab % 4)) EW_FAIL(SG2_EINVAL, "reduce_slabs: %d slabs, n %lld, slab %lld", nslabs, n, slab);
   if ((reinterpret_cast<uintptr_t>(parts) | reinterpret_cast<uintptr_t>(dst)) & 15) EW_FAIL(SG2_EINVAL, "reduce_slabs: 16-byte alignment");
-  reduce_slabs_kernel<<<grid1d(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)parts, nslabs, n / 4, slab / 4,
-                                                                       (float4*)dst, accumulate);
+  if (nslabs > 4) {
+    long long blocks = (n / 4 + 31) / 32;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    reduce_slabs_wide_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)parts, nslabs, n / 4,
+                                                                                 slab / 4, (float4*)dst, accumulate);
+  } else {
+    reduce_slabs_kernel<<<grid1d(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)parts, nslabs, n / 4, slab / 4,
+                                                                         (float4*)dst, accumulate);
+  }
   return launch_ok("reduce_slabs");
 }
 

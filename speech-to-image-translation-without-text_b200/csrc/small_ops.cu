@@ -82,6 +82,106 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
   }
 }
 
+// Register-tiled form for K <= 1024 (both linears of the path: 1024 -> 512 and 228 -> 32768): the kernel above reads
+// shared memory 32 times per weight element (one batch row each), which caps it near 27 us for the 30 MB weight matrix
+// and leaves it latency bound at ~70 us. Here a warp owns 8 batch rows (m-group = warp & 3) and keeps their activations
+// for its lane's k values in registers (8 k x 8 rows); four features are in flight per step (32 coalesced weight loads
+// per lane), the 8 row sums of a feature are reduced across the lanes with a halving butterfly (9 shuffles). The whole
+// activation matrix [32][K] sits in shared memory once per block.
+__device__ __forceinline__ float warp_reduce8(float (&v)[8], int lane) {
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = (lane & 4) != 0;
+    const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];   // every lane: the sum of row ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)
+}
+constexpr int kRtF = 4;   // features in flight per warp step
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(256) linear_fwd_rt_kernel(const float* __restrict__ x1, int K1, const float* __restrict__ x2,
+                                                            int K2, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, void* __restrict__ out, int M,
+                                                            int N, int Kp) {
+  extern __shared__ float xs[];   // [32][Kp]
+  const int K = K1 + K2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mg = warp & 3, fs = warp >> 2;
+  const int nchunks = (Kp + 255) / 256;
+  const int ngroups = (N + kRtF - 1) / kRtF;
+  const int row = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  for (int m0 = 0; m0 < M; m0 += 32) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * Kp; e += 256) {
+      const int m = m0 + e / Kp, k = e % Kp;
+      xs[e] = (m < M && k < K) ? lin_x(x1, K1, x2, K2, m, k) : 0.f;
+    }
+    __syncthreads();
+    float xr[8][8];
+    auto load_x = [&](int ch) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = ch * 256 + j * 32 + lane;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) xr[j][r] = k < Kp ? xs[(mg * 8 + r) * Kp + k] : 0.f;
+      }
+    };
+    if (nchunks == 1) load_x(0);
+    for (int g = blockIdx.x * 2 + fs; g < ngroups; g += gridDim.x * 2) {
+      const int n = g * kRtF;
+      float acc[kRtF][8];
+#pragma unroll
+      for (int f = 0; f < kRtF; ++f)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[f][r] = 0.f;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        if (nchunks > 1) load_x(ch);
+        float wv[kRtF][8];
+#pragma unroll
+        for (int f = 0; f < kRtF; ++f)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = ch * 256 + j * 32 + lane;
+            wv[f][j] = (n + f < N && k < K) ? w[(long long)(n + f) * K + k] : 0.f;
+          }
+#pragma unroll
+        for (int f = 0; f < kRtF; ++f)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) acc[f][r] = fmaf(wv[f][j], xr[j][r], acc[f][r]);
+      }
+#pragma unroll
+      for (int f = 0; f < kRtF; ++f) {
+        const float s = warp_reduce8(acc[f], lane);
+        const int m = m0 + mg * 8 + row;
+        if ((lane & 3) == 0 && n + f < N && m < M) {
+          const float v = s + (bias ? bias[n + f] : 0.f);
+          if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[(long long)m * N + n + f] = __float2bfloat16_rn(v);
+          else reinterpret_cast<float*>(out)[(long long)m * N + n + f] = v;
+        }
+      }
+    }
+  }
+}
+
 // dw[n][k] (+)= sum_m dy[m][n] * x(m,k);  dbias[n] (+)= sum_m dy[m][n].   M <= 32 per launch.
 // block = 256 consecutive k (grid.y = k slabs) x kLinNB features (grid.x): thread k keeps its activation column in
 // registers, the dy columns of the block sit in shared memory (broadcast reads), dw rows are written coalesced.
@@ -660,6 +760,26 @@ extern "C" {
 int sg2_linear_fwd(const float* x1, int K1, const float* x2, int K2, const float* w, const float* bias, void* out,
                    int out_bf16, int M, int N, void* stream) {
   if (M < 1 || M > 4096) SG2_FAIL(SG2_EINVAL, "linear_fwd: M=%d", M);
+  if (K1 + K2 <= 1024) {
+    const int Kp = (K1 + K2 + 31) / 32 * 32;
+    const size_t smem = (size_t)32 * Kp * sizeof(float);
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+      cudaFuncSetAttribute(linear_fwd_rt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4);
+      cudaFuncSetAttribute(linear_fwd_rt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4);
+      attr_done[dev] = true;
+    }
+    const int ngroups = (N + kRtF - 1) / kRtF;
+    int blocks = (ngroups + 1) / 2;                 // two feature slots per block
+    if (blocks > 148 * 2) blocks = 148 * 2;
+    if (out_bf16)
+      linear_fwd_rt_kernel<true><<<blocks, 256, smem, (cudaStream_t)stream>>>(x1, K1, x2, K2, w, bias, out, M, N, Kp);
+    else
+      linear_fwd_rt_kernel<false><<<blocks, 256, smem, (cudaStream_t)stream>>>(x1, K1, x2, K2, w, bias, out, M, N, Kp);
+    SG2_LAUNCH_OK("linear_fwd_rt");
+  }
   // feature groups per warp: enough to amortise the activation staging, few enough to fill the SMs (8 warps per block)
   int npw = N / (kLinF * 8 * 148 * 4);
   npw = npw < 1 ? 1 : (npw > 8 ? 8 : npw);

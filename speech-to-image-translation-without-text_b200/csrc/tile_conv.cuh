@@ -87,7 +87,13 @@ struct TileCfg {
   static constexpr int kSN = BN < 32 ? 32 : BN;
   static constexpr int kChunks = (BN + 31) / 32;       // 32-column blocks of the accumulator
   static constexpr int kCPW = (kChunks + 1) / 2;        // blocks per epilogue warp (two warps share a lane quarter)
-  static constexpr bool kRegStats = kCPW <= 2;          // BatchNorm sums live in registers across all units of the CTA
+  // BatchNorm sums live in registers across all units of the CTA only while that costs 64 registers per thread
+  // (one 32-column block per warp). Two blocks per warp (BN = 128) would need 128 accumulator registers on top of the
+  // 32-wide TMEM read: ptxas spills them (664 bytes of spill loads per thread) and the epilogue runs ~5x slower than
+  // the MMAs it is supposed to hide behind (tools/tile_waits.py: 7.1k cycles per 128 x 128 tile against 2.3k). Wider
+  // tiles therefore reduce each 32 x 32 block across the warp's rows with one butterfly and keep per-quarter
+  // partial sums in shared memory.
+  static constexpr bool kRegStats = kCPW <= 1;
   __host__ __device__ static int tmem_cols(int mt) {
     const int need = 2 * mt * BN;
     return need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
@@ -391,9 +397,27 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
-    // register-held statistics belong to one statistics group (sub-batch) at a time; tiles arrive in image order
+    // the running statistics belong to one statistics group (sub-batch) at a time; tiles arrive in image order
     int cur_grp = -1;
     auto flush_stats = [&](int grp) {
+      if constexpr (!Cfg::kRegStats) {
+        // every epilogue warp reaches this point for the same tile (the group only depends on the tile's image)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        double* st = p.stats + (long long)grp * 2 * p.N;
+        for (int i = et; i < BN; i += 256) {
+          float cs = 0.f, cq = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            cs += s_stats[qq * 2 * Cfg::kSN + i];
+            cq += s_stats[qq * 2 * Cfg::kSN + Cfg::kSN + i];
+          }
+          atomicAdd(&st[n0 + i], (double)cs);
+          atomicAdd(&st[p.N + n0 + i], (double)cq);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = et; i < 4 * 2 * Cfg::kSN; i += 256) s_stats[i] = 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       if constexpr (Cfg::kRegStats) {
         double* st = p.stats + (long long)grp * 2 * p.N;
 #pragma unroll
@@ -428,7 +452,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
         tile_decode(p, tile_ok ? t : pix_tiles - 1, tiles_img, b, ty, tx);
         const int y = ty * kTileH + yi, x = tx * kTileW + xi;
         const bool valid = tile_ok && (x < p.Wo) && (y < p.Ho);
-        if (do_stats && Cfg::kRegStats && tile_ok) {
+        if (do_stats && tile_ok) {
           const int grp = p.stats_bg > 0 ? b / p.stats_bg : 0;
           if (grp != cur_grp) {
             if (cur_grp >= 0) flush_stats(cur_grp);
@@ -552,23 +576,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
       p.dbg_out[blockIdx.x * 16 + 9] = w_tf;
       p.dbg_out[blockIdx.x * 16 + 10] = my_units;
     }
-    if (do_stats) {
-      if constexpr (Cfg::kRegStats) {
-        if (cur_grp >= 0) flush_stats(cur_grp);
-      } else {
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int i = et; i < BN; i += 256) {
-          float cs = 0.f, cq = 0.f;
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            cs += s_stats[qq * 2 * Cfg::kSN + i];
-            cq += s_stats[qq * 2 * Cfg::kSN + Cfg::kSN + i];
-          }
-          atomicAdd(&p.stats[n0 + i], (double)cs);
-          atomicAdd(&p.stats[p.N + n0 + i], (double)cq);
-        }
-      }
-    }
+    if (do_stats && cur_grp >= 0) flush_stats(cur_grp);
   }
   tc_fence_before();
   __syncthreads();
