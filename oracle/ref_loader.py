@@ -10,7 +10,11 @@ import os
 import sys
 import types
 
-REF_CANDIDATES = [os.environ.get("SG2_REF", ""), "/root/reference/StackGAN_v2"]
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# $SG2_REF, a driver-provided install under baseline/_ref (git-ignored; never created by this repo: the reference is a
+# Python source tree that must not be copied), or the read-only mount of the build container
+REF_CANDIDATES = [os.environ.get("SG2_REF", ""), os.path.join(_ROOT, "baseline", "_ref", "StackGAN_v2"),
+                  "/root/reference/StackGAN_v2"]
 
 
 def reference_dir():
@@ -119,3 +123,28 @@ def build_reference_trainer(cfg, batch_size):
     t.fake_labels = torch.zeros(batch_size)
     t.batch_size = batch_size
     return t, ref_model, ref_trainer
+
+
+class ReferenceStepper:
+    """The reference's own inner train loop (trainer.py:537-572 minus Inception) on the UNMODIFIED reference modules and
+    the unmodified condGANTrainer.prepare_data / train_Dnet / train_Gnet, on the CPU: what `bench.py --impl reference`
+    times when a reference tree is available (else it times the oracle port)."""
+
+    def __init__(self, cfg, batch_size):
+        import torch
+        self.torch = torch
+        self.t, self.ref_model, self.ref_trainer = build_reference_trainer(cfg, batch_size)
+        self.avg_param_G = self.ref_trainer.copy_G_params(self.t.netG)
+        self.count = 0
+
+    def step(self, b):
+        torch, t = self.torch, self.t
+        data = (b["real"], b["wrong"], b["emb"], None, torch.as_tensor(b["labels"]))
+        t.imgs_tcpu, t.real_imgs, t.wrong_imgs, t.txt_embedding, t.class_labels = t.prepare_data(data)
+        t.fake_imgs, t.mu, t.logvar = t.netG(b["z"].clone().requires_grad_(True), t.txt_embedding)
+        errD = [float(t.train_Dnet(i, self.count)) for i in range(t.num_Ds)]
+        kl, err_g = t.train_Gnet(self.count)
+        for p, avg_p in zip(t.netG.parameters(), self.avg_param_G):
+            avg_p.mul_(0.999).add_(p.data, alpha=0.001)
+        self.count += 1
+        return errD, float(err_g), float(kl)

@@ -8,6 +8,10 @@ import re
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsg2b200.so")
+# tools/ only: SG2_PROBES=1 loads the diagnostics build (product sources + probes, `python -m sg2b200.build --probes`)
+_PROBES = os.environ.get("SG2_PROBES", "0") == "1"
+if _PROBES:
+    LIB_PATH = os.path.join(_PKG, "..", "tools", "libsg2b200_probes.so")
 
 _c_int, _c_vp, _c_float = ctypes.c_int, ctypes.c_void_p, ctypes.c_float
 _c_ll = ctypes.c_longlong
@@ -36,6 +40,8 @@ def parse_header(path=HEADER_PATH):
 
 
 SIGNATURES = parse_header()
+if _PROBES:
+    SIGNATURES.update(parse_header(os.path.join(_PKG, "..", "include", "sg2b200_probes.h")))
 
 _lib = None
 

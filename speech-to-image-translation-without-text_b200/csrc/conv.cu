@@ -7,9 +7,14 @@
 #include <mutex>
 
 #include "../../include/sg2b200.h"
+#ifdef SG2_BUILD_PROBES
+#include "../../include/sg2b200_probes.h"
+#endif
 #include "common.cuh"
 #include "igemm.cuh"
+#ifdef SG2_BUILD_PROBES
 #include "halo_probe.cuh"
+#endif
 #include "tile_conv.cuh"
 #include "tile_wgrad.cuh"
 
@@ -322,7 +327,19 @@ static int plan_tile(const GatherDesc& d, TilePlan& pl) {
   const int budget = 200 * 1024;
   const int taps_src = d.ntaps / d.nmaps;
   int bn = bn0, b_total;
-  const int b_all = d.ntaps * d.Cin * bn0 * 2;
+  int b_all = d.ntaps * d.Cin * bn0 * 2;
+  // A weight slice that does not fit at the natural N tile but fits at half of it (e.g. conv4x4-s2 64 -> 128: 262 KB vs
+  // 131 KB): the ring mode re-streams the whole slice for every pixel-tile unit (420 KB of TMA per unit against ~8k
+  // cycles of MMAs: L2 -> SMEM bound), the half-width resident form loads it once per CTA. SG2_RES_HALF=0 disables.
+  static const int res_half = [] {
+    const char* e = getenv("SG2_RES_HALF");
+    return e ? atoi(e) : 1;
+  }();
+  if (res_half && b_all + 2 * p.a_box_bytes > budget && bn0 >= 128 && (bn0 % 2) == 0 && d.N % (bn0 / 2) == 0 &&
+      b_all / 2 + 2 * p.a_box_bytes <= budget) {
+    bn = bn0 / 2;
+    b_all /= 2;
+  }
   if (b_all + 2 * p.a_box_bytes <= budget && tile_mode() != 2) {
     p.b_resident = 1;  // weight-stationary: this CTA's weight slice is loaded once
     p.mt = 1;
@@ -956,6 +973,7 @@ static int wgrad_entry(int kind, const void* x, const void* dy, float* dwpk, int
 
 }  // extern "C"
 
+#ifdef SG2_BUILD_PROBES
 // EXPERIMENT (tools/probe_halo.py): shifted-window UMMA descriptors over one halo tile; see halo_probe.cuh.
 template <int BN, int BK>
 static int launch_halo_probe(const void* x, const void* wpk, void* y, int B, int H, int W, int Cin, int Cout, int pitch,
@@ -1003,3 +1021,4 @@ int sg2_probe_halo_fprop(const void* x, const void* wpk, void* y, int B, int H, 
 }
 
 }  // extern "C"
+#endif  // SG2_BUILD_PROBES

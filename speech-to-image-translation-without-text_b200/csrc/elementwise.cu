@@ -1223,7 +1223,8 @@ int sg2_splitk_finish(const float* parts, int nsplit, long long slab, void* y, l
   if (epi_mode && !epi_src) EW_FAIL(SG2_EINVAL, "splitk_finish: epilogue operand missing");
   P /= groups;
   // split-K outputs are small (the layers that cannot fill the GPU): one or two rows per thread, many blocks
-  Geo g = make_geo(P, C, 148 * 16, 8, nsplit > 1 ? 1 : 4);
+  static const int finish_iters = env_int("SG2_FINISH_ITERS", 2);
+  Geo g = make_geo(P, C, 148 * 16, 8, nsplit > 1 ? finish_iters : 4);
   g.grid.z = groups;
   bn_stats_kernel<true><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(parts, (uint4*)y, P, g.vc, g.cpb, g.rpb, stats, C,
                                                                       nsplit, slab, (const uint4*)epi_src, epi_mode);

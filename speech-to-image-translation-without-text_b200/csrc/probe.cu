@@ -2,7 +2,7 @@
 // One CTA per SM; one thread issues `iters` MMAs (M=128, N, K=16, bf16) whose operands already sit in shared memory
 // and measures cycles until the commit arrives. Variants: descriptor start aligned to the swizzle atom or shifted by
 // rows (halo-window addressing), SBO 8 rows or 10 rows, accumulators rotated over `nacc` TMEM tiles.
-#include "../../include/sg2b200.h"
+#include "../../include/sg2b200_probes.h"
 #include "common.cuh"
 #include "ptx.cuh"
 

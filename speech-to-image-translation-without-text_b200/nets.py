@@ -130,7 +130,7 @@ class GradSink:
     BN / linear / logit gradients accumulate in place. `views` optionally maps parameter -> preallocated
     fp32 tensor (a slice of a flat gradient bucket) that receives the result."""
 
-    def __init__(self, views=None, side_stream=None, prezeroed=False, on_ready=None):
+    def __init__(self, views=None, side_stream=None, prezeroed=False, on_ready=None, opt_stream=None):
         self.g = {}
         self.views = views or {}
         self.pending = []
@@ -146,6 +146,9 @@ class GradSink:
         # Weight gradients hang off the backward chain (only the optimiser consumes them), so they can run on a
         # side stream next to the dgrad / BatchNorm-backward chain; finish() joins.
         self.side = side_stream
+        # optional second side stream for what follows a layer's wgrad (unpack, all-reduce, Adam, operand re-pack): the
+        # next layer's wgrad then runs beside the previous layer's optimiser work instead of behind it
+        self.opt = opt_stream if side_stream is not None else None
         self.keep = []
 
     def slot(self, p):
@@ -185,14 +188,23 @@ class GradSink:
             return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(ev)
+        st = self.opt if self.opt is not None else self.side
+        with torch.cuda.stream(st):
+            st.wait_event(ev)
             self.on_repack(op)
 
     def _wgrad(self, op, x, dy):
         if self.on_ready is not None:
             op.wgrad_begin(x.device, self.prezeroed)
             op.wgrad_add(x, dy)
+            if self.opt is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())       # = the wgrad side stream
+                with torch.cuda.stream(self.opt):
+                    self.opt.wait_event(ev)
+                    self.g[op.weight] = op.wgrad_finish(self.views.get(op.weight))
+                    self.on_ready(op.weight)
+                return
             self.g[op.weight] = op.wgrad_finish(self.views.get(op.weight))
             self.on_ready(op.weight)
             return
@@ -212,6 +224,10 @@ class GradSink:
                 ev = torch.cuda.Event()
                 ev.record(self.side)
             torch.cuda.current_stream().wait_event(ev)
+            if self.opt is not None:
+                ev2 = torch.cuda.Event()
+                ev2.record(self.opt)
+                torch.cuda.current_stream().wait_event(ev2)
         self.pending = []
         self.keep = []
         return self.g

@@ -275,6 +275,9 @@ class FusedTrainer:
             prio = [hi if i == n - 1 and n > 1 else 0 for i in range(n)]
             self._sD = [torch.cuda.Stream(device=self.dev, priority=prio[i]) for i in range(n)]
             self._sW = [torch.cuda.Stream(device=self.dev, priority=(prio + [0])[i]) for i in range(n + 1)]  # wgrad side
+            # per-layer optimiser work (unpack, all-reduce, Adam, re-pack) beside the wgrad stream (SG2_OPT_STREAM=0: off)
+            two = os.environ.get("SG2_OPT_STREAM", "1") != "0"
+            self._sO = [torch.cuda.Stream(device=self.dev, priority=(prio + [0])[i]) if two else None for i in range(n + 1)]
         return self._sD
 
     def step(self, z, emb, real, wrong, labels, eps=None):
@@ -339,7 +342,8 @@ class FusedTrainer:
                 # ---------------- (2) update D_i, trainer.py:375-427
                 bucket = self.bD[i]
                 ready, fin = self._layerwise(bucket, self.lr_d, i) if (self.batched_d and self.layerwise) else (None, None)
-                sink = GradSink(bucket.views, self._sW[i] if self.concurrent else None, prezeroed=True, on_ready=ready)
+                sink = GradSink(bucket.views, self._sW[i] if self.concurrent else None, prezeroed=True, on_ready=ready,
+                                opt_stream=self._sO[i] if self.concurrent else None)
                 sink.on_repack = ready.repack if ready is not None else None
                 if self.batched_d:
                     # real | wrong | fake in ONE pass of 3B samples with per-sub-batch BatchNorm statistics: the same
@@ -401,7 +405,8 @@ class FusedTrainer:
         elif not ops.DETERMINISTIC:
             self.bG.grad.zero_()
         ready, fin = self._layerwise(self.bG, self.lr_g, nD) if self.layerwise else (None, None)
-        sinkG = GradSink(self.bG.views, self._sW[nD] if self.concurrent else None, prezeroed=True, on_ready=ready)
+        sinkG = GradSink(self.bG.views, self._sW[nD] if self.concurrent else None, prezeroed=True, on_ready=ready,
+                         opt_stream=self._sO[nD] if self.concurrent else None)
         sinkG.on_repack = ready.repack if ready is not None else None
         self.G.backward(Tg, dimgs, dmu, dlogvar, sinkG)
         sinkG.finish()

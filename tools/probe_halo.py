@@ -1,6 +1,7 @@
 """EXPERIMENT: does a UMMA descriptor that starts at a shifted row of a TMA-loaded halo tile read the right data?
 Runs conv3x3 fprop through sg2_probe_halo_fprop for pitch in {10, 16} x base-offset mode in {0, 1} and compares
 with the production kernel and torch. Each case runs in a child process with a timeout."""
+import os as _os; _os.environ["SG2_PROBES"] = "1"   # diagnostics build: python -m sg2b200.build --probes
 import ctypes, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -1,4 +1,5 @@
 """tcgen05.mma microbenchmark: cycles per MMA for issue styles, N, aligned vs shifted descriptors."""
+import os as _os; _os.environ["SG2_PROBES"] = "1"   # diagnostics build: python -m sg2b200.build --probes
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -1,4 +1,5 @@
 """TMA streaming-bandwidth microbenchmark: GB/s vs row bytes (channels), box shape, ring depth, CTAs per SM."""
+import os as _os; _os.environ["SG2_PROBES"] = "1"   # diagnostics build: python -m sg2b200.build --probes
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

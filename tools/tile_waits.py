@@ -1,4 +1,5 @@
 """Per-role wait-cycle breakdown of the tile conv kernel for one layer: SG2_TILE_DBG=64 python tools/tile_waits.py G.head2 fprop"""
+import os as _os; _os.environ["SG2_PROBES"] = "1"   # diagnostics build: python -m sg2b200.build --probes
 import ctypes, os, sys
 os.environ["SG2_TILE_DBG"] = str(int(os.environ.get("SG2_TILE_DBG", "0")) | 64)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
