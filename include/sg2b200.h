@@ -34,6 +34,10 @@ enum { SG2_OUT_BF16 = 0, SG2_OUT_F32_ATOMIC = 1, SG2_OUT_F32_STORE = 2 };
 
 int sg2_version(void);
 const char* sg2_last_error(void);
+/* Data-parallel runs: leave `n_sms` SMs out of the persistent (one CTA per SM) convolution grids so that NCCL's all-reduce
+ * CTAs (trainer.py:165-171's DataParallel gradient exchange, here one ncclAllReduce per gradient bucket slice) can run
+ * beside them. 0 (default): use every SM. Process-wide. */
+int sg2_set_sm_reserve(int n_sms);
 
 /* ---- weights ------------------------------------------------------------------------------------------
  * fp32 OIHW master weights (the nn.Conv2d .weight the optimiser owns) -> bf16 operand packs.
@@ -138,6 +142,7 @@ int sg2_bn_act_bwd(const void* x, const void* dout, const float* mean, const flo
 int sg2_lrelu_bwd(const void* x, const void* dout, void* dx, long long n, void* stream);
 int sg2_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
 int sg2_f32_to_bf16(const float* in, void* out, long long n, void* stream);
+int sg2_bf16_to_f32(const void* in, float* out, long long n, void* stream);   /* n % 4 == 0 (gradient slices on the bf16 wire) */
 
 /* ---- broadcast c_code concat (model.py:274-277, 431-434): out[b,y,x,:] = (c[b,:E] | h[b,y,x,:Ch]) -------- */
 int sg2_concat_c(const float* c, const void* h, void* out, int B, int HW, int E, int Ch, void* stream);

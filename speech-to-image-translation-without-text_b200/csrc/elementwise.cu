@@ -866,6 +866,13 @@ __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __rest
   }
 }
 
+__global__ void bf16_to_f32_kernel(const uint2* __restrict__ in, float4* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint2 v = in[i];
+    out[i] = make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+  }
+}
 __global__ void f32_to_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1223,7 +1230,7 @@ int sg2_splitk_finish(const float* parts, int nsplit, long long slab, void* y, l
   if (epi_mode && !epi_src) EW_FAIL(SG2_EINVAL, "splitk_finish: epilogue operand missing");
   P /= groups;
   // split-K outputs are small (the layers that cannot fill the GPU): one or two rows per thread, many blocks
-  static const int finish_iters = env_int("SG2_FINISH_ITERS", 2);
+  static const int finish_iters = env_int("SG2_FINISH_ITERS", 4);
   Geo g = make_geo(P, C, 148 * 16, 8, nsplit > 1 ? finish_iters : 4);
   g.grid.z = groups;
   bn_stats_kernel<true><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(parts, (uint4*)y, P, g.vc, g.cpb, g.rpb, stats, C,
@@ -1346,6 +1353,12 @@ int sg2_f32_to_bf16(const float* in, void* out, long long n, void* stream) {
   if (n % 4) EW_FAIL(SG2_EINVAL, "f32_to_bf16: n %% 4");
   f32_to_bf16_kernel<<<grid1d(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)in, (uint2*)out, n / 4);
   return launch_ok("f32_to_bf16");
+}
+
+int sg2_bf16_to_f32(const void* in, float* out, long long n, void* stream) {
+  if (n % 4) EW_FAIL(SG2_EINVAL, "bf16_to_f32: n %% 4");
+  bf16_to_f32_kernel<<<grid1d(n / 4), 256, 0, (cudaStream_t)stream>>>((const uint2*)in, (float4*)out, n / 4);
+  return launch_ok("bf16_to_f32");
 }
 
 int sg2_concat_c(const float* c, const void* h, void* out, int B, int HW, int E, int Ch, void* stream) {

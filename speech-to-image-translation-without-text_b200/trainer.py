@@ -170,7 +170,15 @@ class FusedTrainer:
         self.bD = [FlatBucket(d) for d in self.netsD]
         for eng in [self.G] + self.Ds:
             eng.set_auto_refresh(False)       # the buckets track every weight update themselves (dirty / refresh)
-        self.all_reduce = all_reduce          # callable(flat_grad_tensor) or None (single GPU)
+        self.all_reduce = all_reduce          # callable(flat_grad_tensor, chan) or None (single GPU)
+        # Data parallel: (1) the persistent conv grids leave SG2_SM_RESERVE SMs (default 12) to NCCL's CTAs, so that the
+        # per-layer all-reduces issued on the side streams advance while backward is still running instead of only in the
+        # gaps between kernels; (2) SG2_GRAD_WIRE=bf16 halves the bytes on NVLink (468 -> 234 MB per step): the slice is
+        # rounded to bf16, averaged, and widened back for Adam. Default fp32: the all-reduce is then exactly DDP's.
+        self.wire_bf16 = all_reduce is not None and os.environ.get("SG2_GRAD_WIRE", "fp32") == "bf16"
+        if all_reduce is not None:
+            from . import _lib
+            _lib.call("sg2_set_sm_reserve", int(os.environ.get("SG2_SM_RESERVE", "12")))
         self.concurrent = os.environ.get("SG2_CONCURRENT", "1") != "0"   # one stream per discriminator (see step())
         self.batched_d = os.environ.get("SG2_BATCHED_D", "1") != "0"     # real/wrong/fake D passes as one 3B pass
         # per-layer Adam (+ re-pack) on the wgrad side streams while backward is still running; data parallel: the large
@@ -209,6 +217,19 @@ class FusedTrainer:
                 op.packs()
 
     # ------------------------------------------------------------------ helpers
+    def _reduce(self, bucket, o, n, chan):
+        """Average gradient elements [o, o+n) of the bucket over the ranks (in place)."""
+        g = bucket.grad[o:o + n]
+        if not self.wire_bf16:
+            self.all_reduce(g, chan)
+            return
+        if getattr(bucket, "grad16", None) is None:
+            bucket.grad16 = torch.empty(bucket.n, device=bucket.grad.device, dtype=torch.bfloat16)
+        g16 = bucket.grad16[o:o + n]
+        ops.f32_to_bf16(g, out=g16)
+        self.all_reduce(g16, chan)
+        ops._call("sg2_bf16_to_f32", 1, _p(g16), _p(g), n, _st())
+
     def _layerwise(self, bucket, lr, chan=0):
         """-> (on_ready, finish): all-reduce + Adam of each conv weight as soon as its wgrad is done (on the wgrad side
         stream, overlapping the rest of backward), then the small parameters and any leftover in finish()."""
@@ -221,7 +242,7 @@ class FusedTrainer:
             if dp:
                 if o < bucket.small_n:
                     return                       # small layer: reduced + updated with the rest in finish()
-                self.all_reduce(bucket.grad[o:o + n], chan)
+                self._reduce(bucket, o, n, chan)
             bucket.adam_range(o, n, lr)
             done.add(w)
 
@@ -236,7 +257,7 @@ class FusedTrainer:
 
         def finish():
             if dp:
-                self.all_reduce(bucket.grad[:bucket.small_n], chan)
+                self._reduce(bucket, 0, bucket.small_n, chan)
                 bucket.adam_range(0, bucket.small_n, lr)
             else:
                 bucket.adam_range(0, bucket.head_n, lr)
@@ -378,7 +399,7 @@ class FusedTrainer:
                     fin()
                 else:
                     if self.all_reduce is not None:
-                        self.all_reduce(bucket.grad, i)
+                        self._reduce(bucket, 0, bucket.n, i)
                     bucket.adam(self.lr_d)
                 # ---------------- (3a) D_i's share of the G step, trainer.py:436-446 (updated D weights, live fake, mu)
                 probs = torch.empty(2, B, device=self.dev, dtype=torch.float32)
@@ -414,7 +435,7 @@ class FusedTrainer:
             fin()                                # + EMA avg = 0.999 avg + 0.001 p (trainer.py:571-572)
         else:
             if self.all_reduce is not None:
-                self.all_reduce(self.bG.grad, nD)
+                self._reduce(self.bG, 0, self.bG.n, nD)
             self.bG.adam(self.lr_g)
         # errG_total = sum_i errG_i + kl + sum_i cal_i (trainer.py:486)
         cal = self.losses[nD + 2:nD + 3]
