@@ -62,6 +62,8 @@ def lib():
             fn.argtypes = args
             fn.restype = _c_int
         _lib = l
+        if os.environ.get("SG2_SM_RESERVE_ALWAYS"):      # tests: run every kernel with the data-parallel grid sizes
+            check(l.sg2_set_sm_reserve(int(os.environ["SG2_SM_RESERVE_ALWAYS"])), "sg2_set_sm_reserve")
     return _lib
 
 

@@ -39,7 +39,9 @@ class FlatBucket:
     buys: the bf16 fprop operand of a CONV3x3 / CONV4x4S2 layer is a plain cast of the master (the Adam kernel writes
     it as a bf16 mirror of the bucket) and the wgrad kernels accumulate straight into the gradient bucket."""
 
-    LARGE = 8 << 20      # elements (32 MB of fp32 gradient)
+    # elements: conv weights at least this large are all-reduced one by one as soon as their wgrad is done (data-parallel
+    # runs); everything smaller goes in one call per network after its backward pass, which sits on the critical path
+    LARGE = int(os.environ.get("SG2_DP_LARGE", str(8 << 20)))
 
     def __init__(self, net, with_ema=False):
         self.params = [p for p in net.parameters()]
