@@ -173,14 +173,14 @@ class FusedTrainer:
         for eng in [self.G] + self.Ds:
             eng.set_auto_refresh(False)       # the buckets track every weight update themselves (dirty / refresh)
         self.all_reduce = all_reduce          # callable(flat_grad_tensor, chan) or None (single GPU)
-        # Data parallel: (1) the persistent conv grids leave SG2_SM_RESERVE SMs (default 12) to NCCL's CTAs, so that the
+        # Data parallel: (1) the persistent conv grids leave SG2_SM_RESERVE SMs (default 8) to NCCL's CTAs, so that the
         # per-layer all-reduces issued on the side streams advance while backward is still running instead of only in the
         # gaps between kernels; (2) SG2_GRAD_WIRE=bf16 halves the bytes on NVLink (468 -> 234 MB per step): the slice is
         # rounded to bf16, averaged, and widened back for Adam. Default fp32: the all-reduce is then exactly DDP's.
         self.wire_bf16 = all_reduce is not None and os.environ.get("SG2_GRAD_WIRE", "fp32") == "bf16"
         if all_reduce is not None:
             from . import _lib
-            _lib.call("sg2_set_sm_reserve", int(os.environ.get("SG2_SM_RESERVE", "12")))
+            _lib.call("sg2_set_sm_reserve", int(os.environ.get("SG2_SM_RESERVE", "8")))
         self.concurrent = os.environ.get("SG2_CONCURRENT", "1") != "0"   # one stream per discriminator (see step())
         self.batched_d = os.environ.get("SG2_BATCHED_D", "1") != "0"     # real/wrong/fake D passes as one 3B pass
         # per-layer Adam (+ re-pack) on the wgrad side streams while backward is still running; data parallel: the large
