@@ -85,7 +85,11 @@ struct TileCfg {
   static constexpr int kRowB = BK * 2;
   static constexpr int kBBytes = BN * kRowB;
   static constexpr int kSN = BN < 32 ? 32 : BN;
-  static constexpr int kChunks = (BN + 31) / 32;       // 32-column blocks of the accumulator
+  // Column block one epilogue warp handles per step. 32 in general; BN = 32 is split into two 16-column blocks so that
+  // BOTH warps of a TMEM lane quarter work (with one 32-column block the second warp of each quarter idles and the
+  // epilogue, not the MMAs, bounds the 32-channel layers of generator stage 3: tools/tile_waits.py, 1.4k vs 0.9k cycles).
+  static constexpr int kCB = BN == 32 ? 16 : 32;
+  static constexpr int kChunks = (BN + kCB - 1) / kCB;  // column blocks of the accumulator
   static constexpr int kCPW = (kChunks + 1) / 2;        // blocks per epilogue warp (two warps share a lane quarter)
   // BatchNorm sums live in registers across all units of the CTA only while that costs 64 registers per thread
   // (one 32-column block per warp). Two blocks per warp (BN = 128) would need 128 accumulator registers on top of the
@@ -422,11 +426,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
         double* st = p.stats + (long long)grp * 2 * p.N;
 #pragma unroll
         for (int ci = 0; ci < Cfg::kCPW; ++ci) {
-          const int c0 = (half + 2 * ci) * 32;
+          const int c0 = (half + 2 * ci) * Cfg::kCB;
           if (c0 < BN) {
             const float cs = warp_transpose_sum(acc_s[ci], lane);
             const float cq = warp_transpose_sum(acc_q[ci], lane);
-            if (c0 + lane < BN) {
+            if (lane < Cfg::kCB && c0 + lane < BN) {
               atomicAdd(&st[n0 + c0 + lane], (double)cs);
               atomicAdd(&st[p.N + n0 + c0 + lane], (double)cq);
             }
@@ -464,12 +468,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t((acc * MT + m) * BN);
 #pragma unroll
         for (int ci = 0; ci < Cfg::kCPW; ++ci) {
-          const int c0 = (half + 2 * ci) * 32;
+          constexpr int kCB = Cfg::kCB;
+          const int c0 = (half + 2 * ci) * kCB;
           if (c0 < BN) {
             uint32_t v[32];
-            if (BN - c0 >= 32) {
+            if (kCB == 32 && BN - c0 >= 32) {
               tmem_ld_32x32(taddr + c0, v);
-            } else {  // BN = 16 / 80: the last column block is 16 wide
+            } else {  // BN = 16 / 80: the last column block is 16 wide; BN = 32: two 16-column blocks
               uint32_t w[16];
               tmem_ld_32x16(taddr + c0, w);
 #pragma unroll
@@ -483,7 +488,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
               const float4* bp =
                   reinterpret_cast<const float4*>(p.bias9 + ((long long)(b * 9 + ry * 3 + rx) * p.N + n0 + c0));
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < kCB / 4; ++j) {
                 if (c0 + 4 * j < BN) {
                   const float4 t = __ldg(bp + j);
                   v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + t.x);
@@ -496,7 +501,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
             if (p.epi_mode != 0 && valid) {
               const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.epi_src) + row_off + c0);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int j = 0; j < kCB / 8; ++j) {
                 if (c0 + 8 * j < BN) {
                   const uint4 sv = __ldg(sp + j);
                   const uint32_t w4[4] = {sv.x, sv.y, sv.z, sv.w};
@@ -514,7 +519,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
             }
             if (p.act == 2) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
+              for (int j = 0; j < kCB; ++j) {
                 const float f = __uint_as_float(v[j]);
                 v[j] = __float_as_uint(f > 0.f ? f : 0.2f * f);
               }
@@ -524,7 +529,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
               if constexpr (Cfg::kRegStats) {
                 if (valid) {
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) {
+                  for (int j = 0; j < kCB; ++j) {
                     const float rr = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j])));
                     acc_s[ci][j] += rr;
                     acc_q[ci][j] = fmaf(rr, rr, acc_q[ci][j]);
@@ -548,7 +553,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_conv_kernel(const __grid
             }
             if (valid) {
               uint4* dst = reinterpret_cast<uint4*>(dst_row + c0);
-              const int nvec = (BN - c0 >= 32) ? 4 : (BN - c0) / 8;
+              const int nvec = (BN - c0 >= kCB) ? kCB / 8 : (BN - c0) / 8;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 if (j < nvec) {

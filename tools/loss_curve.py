@@ -28,8 +28,14 @@ def main():
     ap.add_argument("--batch", type=int, default=24)
     ap.add_argument("--window", type=int, default=100)
     ap.add_argument("--out", default="gpurun_out/loss_curve.json")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"], help="arithmetic mode of the CUDA arm")
+    ap.add_argument("--emu", action="store_true",
+                    help="also run the bf16-EMULATING oracle on the same streams: its distance from the fp32 oracle is the "
+                         "envelope an ideal bf16-storage implementation stays in")
     args = ap.parse_args()
-    from oracle.stackgan_oracle import Cfg, OracleTrainer
+    from oracle.stackgan_oracle import Cfg, OracleTrainer, emulate_bf16
+    from sg2b200 import config as _cfgmod
+    _cfgmod.set_precision(args.precision)
     from sg2b200 import config, trainer, utils
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -41,10 +47,12 @@ def main():
     ocfg = Cfg(BRANCH_NUM=args.branches)
     orc = OracleTrainer(ocfg, {k: v.detach().clone() for k, v in netG.state_dict().items()},
                         [{k: v.detach().clone() for k, v in d.state_dict().items()} for d in netsD], device=dev)
+    orq = OracleTrainer(ocfg, {k: v.detach().clone() for k, v in netG.state_dict().items()},
+                        [{k: v.detach().clone() for k, v in d.state_dict().items()} for d in netsD], device=dev) if args.emu else None
     tr = trainer.FusedTrainer(netG, netsD, cfg)
     nD = args.branches
     names = [f"errD{i}" for i in range(nD)] + ["errG_total", "kl", "cal"]
-    ours, ref = [], []
+    ours, ref, emu = [], [], []
     for s in range(args.steps):
         b = utils.synthetic_batch(cfg, args.batch, seed=1000 + s, device=dev, n_classes=6)
         eps = torch.randn(args.batch, cfg.GAN.EMBEDDING_DIM, device=dev, generator=torch.Generator(device=dev).manual_seed(s))
@@ -53,6 +61,10 @@ def main():
         lr = [float(x) for x in o["errD"]] + [float(o["errG_total"]), float(o["kl"]), float(o["cal"])]
         ours.append(lo)
         ref.append(lr)
+        if orq is not None:
+            with emulate_bf16():
+                q = orq.step(dict(z=b["z"], emb=b["emb"], eps=eps, real=b["real"], wrong=b["wrong"], labels=b["labels"].tolist()))
+            emu.append([float(x) for x in q["errD"]] + [float(q["errG_total"]), float(q["kl"]), float(q["cal"])])
         if s % PRINT_EVERY == 0 or max(lo[:nD]) > 4 or max(lr[:nD]) > 4:
             print(f"step {s}: ours {[round(v, 4) for v in lo]} ref {[round(v, 4) for v in lr]}", flush=True)
     A, R = torch.tensor(ours, dtype=torch.float64), torch.tensor(ref, dtype=torch.float64)
@@ -70,6 +82,28 @@ def main():
     out["whole_run_rel_dev_of_means"] = {n: float(abs(A[:, i].mean() - R[:, i].mean()) / (abs(R[:, i].mean()) + 1e-3))
                                          for i, n in enumerate(names)}
     out["finite"] = bool(torch.isfinite(A).all())
+    out["precision"] = args.precision
+    if emu:
+        Q = torch.tensor(emu, dtype=torch.float64)
+        relq = (Q - R).abs() / (R.abs() + 1e-3)
+        out["envelope_bf16_emulating_oracle_vs_fp32_oracle"] = {
+            "first_steps_max_rel": {n: float(relq[:10, i].max()) for i, n in enumerate(names)},
+            "first_50_mean_rel": {n: float(relq[:50, i].mean()) for i, n in enumerate(names)},
+            "whole_run_rel_dev_of_means": {n: float(abs(Q[:, i].mean() - R[:, i].mean()) / (abs(R[:, i].mean()) + 1e-3))
+                                           for i, n in enumerate(names)}}
+        # per 100-step window: our deviation from the fp32 oracle next to the ideal-bf16 envelope (mean |rel| of errG_total
+        # and of the discriminator losses), and the first step where ours leaves 3x the envelope's running mean deviation
+        gi = names.index("errG_total")
+        wins = []
+        for w0 in range(0, args.steps, W):
+            sl = slice(w0, w0 + W)
+            wins.append({"steps": [w0, min(args.steps, w0 + W)],
+                         "ours_mean_rel": {"errG_total": float(rel[sl, gi].mean()), "errD": float(rel[sl, :nD].mean())},
+                         "envelope_mean_rel": {"errG_total": float(relq[sl, gi].mean()), "errD": float(relq[sl, :nD].mean())}})
+        out["windows_vs_envelope"] = wins
+        run_o, run_q = torch.cumsum(rel[:, gi], 0) / torch.arange(1, args.steps + 1), torch.cumsum(relq[:, gi], 0) / torch.arange(1, args.steps + 1)
+        leave = [int(i) for i in torch.nonzero(run_o > 3 * run_q + 1e-3).flatten()[:1]]
+        out["first_step_running_mean_errG_dev_exceeds_3x_envelope"] = leave[0] if leave else None
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     json.dump(out, open(args.out, "w"), indent=1)
     print(json.dumps({k: out[k] for k in ("first_steps_max_rel", "first_50_mean_rel", "whole_run_rel_dev_of_means", "finite")}))
