@@ -92,7 +92,7 @@ def main():
             "whole_run_rel_dev_of_means": {n: float(abs(Q[:, i].mean() - R[:, i].mean()) / (abs(R[:, i].mean()) + 1e-3))
                                            for i, n in enumerate(names)}}
         # per 100-step window: our deviation from the fp32 oracle next to the ideal-bf16 envelope (mean |rel| of errG_total
-        # and of the discriminator losses), and the first step where ours leaves 3x the envelope's running mean deviation
+        # and of the discriminator losses)
         gi = names.index("errG_total")
         wins = []
         for w0 in range(0, args.steps, W):
@@ -101,9 +101,6 @@ def main():
                          "ours_mean_rel": {"errG_total": float(rel[sl, gi].mean()), "errD": float(rel[sl, :nD].mean())},
                          "envelope_mean_rel": {"errG_total": float(relq[sl, gi].mean()), "errD": float(relq[sl, :nD].mean())}})
         out["windows_vs_envelope"] = wins
-        run_o, run_q = torch.cumsum(rel[:, gi], 0) / torch.arange(1, args.steps + 1), torch.cumsum(relq[:, gi], 0) / torch.arange(1, args.steps + 1)
-        leave = [int(i) for i in torch.nonzero(run_o > 3 * run_q + 1e-3).flatten()[:1]]
-        out["first_step_running_mean_errG_dev_exceeds_3x_envelope"] = leave[0] if leave else None
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     json.dump(out, open(args.out, "w"), indent=1)
     print(json.dumps({k: out[k] for k in ("first_steps_max_rel", "first_50_mean_rel", "whole_run_rel_dev_of_means", "finite")}))
