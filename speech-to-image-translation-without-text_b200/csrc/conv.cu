@@ -215,6 +215,80 @@ static int launch_fprop_t(const GatherDesc& d, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ cluster split-K launch
+template <int BN, int BK>
+static int launch_fprop_cluster_t(const GatherDesc& d, cudaStream_t st) {
+  using Cfg = FpropCfg<BN, BK>;
+  using CC = ClusterCfg<BN, BK>;
+  FpropParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = pick_tile(d.Wg, d.Hg, kBlockM, &p.tw, &p.th, &p.nb))) return rc;
+  for (int i = 0; i < d.nmaps; ++i)
+    if ((rc = make_act_map(&p.tmA[i], d.a[i], BK, p.tw, p.th, p.nb))) return rc;
+  const long long K = (long long)d.ntaps * d.Cin;
+  if ((rc = make_w_map(&p.tmB, d.w, (long long)d.ngroups * d.N, K, BK, BN))) return rc;
+  memcpy(p.taps, d.taps, sizeof(p.taps));
+  p.ntaps = d.ntaps;
+  p.kchunks = d.Cin / BK;
+  p.ngroups = d.ngroups;
+  const int KB = p.ntaps * p.kchunks;
+  p.splitk = d.splitk > KB ? KB : d.splitk;
+  if (p.splitk < 2 || p.splitk > 16) SG2_FAIL(SG2_ENOFUSE, "cluster split-K: %d splits (2..16)", p.splitk);
+  p.tiles_x = (d.Wg + p.tw - 1) / p.tw;
+  p.tiles_y = (d.Hg + p.th - 1) / p.th;
+  p.tiles_b = (d.B + p.nb - 1) / p.nb;
+  p.Wo = d.Wg;
+  p.Ho = d.Hg;
+  p.B = d.B;
+  p.N = d.N;
+  for (int g = 0; g < 4; ++g) p.out_off[g] = d.out_off[g];
+  p.sb = d.osb;
+  p.sy = d.osy;
+  p.sx = d.osx;
+  p.out = d.out;
+  p.out_mode = OUT_BF16;
+  p.stats = d.stats;
+  p.stats_bg = d.stats_bg;
+  p.act = d.act;
+  p.epi_src = d.epi_src;
+  p.epi_mode = d.epi_mode;
+  if (d.stats && d.stats_bg > 0 && (d.stats_bg % p.nb))
+    SG2_FAIL(SG2_ENOFUSE, "fused BN statistics: a %d-image tile would straddle statistics groups of %d images", p.nb, d.stats_bg);
+  int stages = (int)((200 * 1024) / Cfg::kStageBytes);
+  if (stages > 8) stages = 8;
+  if (stages > KB / p.splitk + 1) stages = KB / p.splitk + 1;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  static bool attr_done[64] = {};
+  if (attr_needed(attr_done)) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_cluster_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)CC::smem_bytes(8 < (int)((200 * 1024) / Cfg::kStageBytes) ? 8 : (int)((200 * 1024) / Cfg::kStageBytes)));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(igemm_fprop_cluster_kernel<BN, BK>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(fprop_cluster<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(p.tiles_x * p.tiles_y * p.tiles_b, d.N / BN, p.ngroups * p.splitk);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = CC::smem_bytes(stages);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = p.splitk;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_fprop_cluster_kernel<BN, BK>, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    SG2_FAIL((int)e, "fprop_cluster<%d,%d> launch (cluster %d): %s", BN, BK, p.splitk, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ tile-resident launch
 static long long* g_tile_dbg = nullptr;
 static int tile_mode() {
@@ -449,6 +523,12 @@ static int launch_fprop(const GatherDesc& d, cudaStream_t st) {
     if (rc != 1) return rc;
   }
   if (d.bias9) SG2_FAIL(SG2_EINVAL, "conv_fprop: the region bias needs a tile-resident shape (Cin %d, N %d)", d.Cin, d.N);
+  if (d.out_mode == OUT_BF16 && d.splitk > 1) {   // split-K with an in-cluster reduction (bf16 out, statistics, epilogue operand)
+    if (bk == 64 && bn == 256) return launch_fprop_cluster_t<256, 64>(d, st);
+    if (bk == 64 && bn == 128) return launch_fprop_cluster_t<128, 64>(d, st);
+    if (bk == 64 && bn == 64) return launch_fprop_cluster_t<64, 64>(d, st);
+    SG2_FAIL(SG2_ENOFUSE, "cluster split-K: no instance for BN=%d BK=%d", bn, bk);
+  }
   if (d.epi_mode) SG2_FAIL(SG2_ENOFUSE, "epilogue operand: this shape runs on the gather kernel (K %d, N %d)", d.Cin, d.N);
 #define SG2_CASE(BN_, BK_) \
   if (bn == BN_ && bk == BK_) return launch_fprop_t<BN_, BK_>(d, st);
@@ -719,14 +799,13 @@ int sg2_conv_fprop(int kind, const void* x, const void* wpk, void* y, int out_mo
     SG2_FAIL(SG2_EINVAL, "conv_fprop: the region bias applies to a plain bf16 3x3 convolution");
   d.bias9 = bias9;
   if (act != 0 && act != SG2_ACT_LRELU) SG2_FAIL(SG2_EINVAL, "conv_fprop: epilogue activation %d", act);
-  if (act && (stats || out_mode != SG2_OUT_BF16 || splitk > 1)) SG2_FAIL(SG2_EINVAL, "conv_fprop: fused activation needs a plain bf16 epilogue");
+  if (act && (stats || out_mode != SG2_OUT_BF16)) SG2_FAIL(SG2_EINVAL, "conv_fprop: fused activation needs a bf16 epilogue");
   d.act = act;
   if (stats && stats_groups > 1) {
     if (B % stats_groups) SG2_FAIL(SG2_EINVAL, "conv_fprop: batch %d in %d statistics groups", B, stats_groups);
     d.stats_bg = B / stats_groups;
   }
-  if (stats && (out_mode != SG2_OUT_BF16 || splitk > 1))
-    SG2_FAIL(SG2_EINVAL, "fused BN statistics need SG2_OUT_BF16 without split-K");
+  if (stats && out_mode != SG2_OUT_BF16) SG2_FAIL(SG2_EINVAL, "fused BN statistics need SG2_OUT_BF16");
   d.Cin = Cin;
   d.w = wpk;
   d.N = Cout;
@@ -809,8 +888,7 @@ int sg2_conv_dgrad(int kind, const void* dy, const void* wpkT, void* dx, int out
   if (epi_mode != 0 && epi_mode != SG2_EPI_ADD && epi_mode != SG2_EPI_LRELU_MASK)
     SG2_FAIL(SG2_EINVAL, "conv_dgrad: epilogue mode %d", epi_mode);
   if (epi_mode && (!epi_src || (Cin % 8))) SG2_FAIL(SG2_EINVAL, "conv_dgrad: epilogue operand missing / Cin %% 8");
-  if (epi_mode && (out_mode != SG2_OUT_BF16 || splitk > 1))
-    SG2_FAIL(SG2_ENOFUSE, "conv_dgrad: the epilogue operand needs a plain bf16 epilogue");
+  if (epi_mode && out_mode != SG2_OUT_BF16) SG2_FAIL(SG2_ENOFUSE, "conv_dgrad: the epilogue operand needs a bf16 epilogue");
   d.epi_src = epi_src;
   d.epi_mode = epi_mode;
   d.Cin = Cout;  // contraction runs over the forward output channels

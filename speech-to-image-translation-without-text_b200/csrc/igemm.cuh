@@ -43,6 +43,10 @@ struct FpropParams {
   double* stats;  // optional [groups][2][N] fp64: per-channel sum / sum of squares of the (bf16-rounded) outputs, += (BN statistics)
   int stats_bg;  // images per statistics group (0: one group); a tile never straddles groups (checked on the host)
   int act;       // epilogue activation: 0 none, 2 LeakyReLU(0.2) (layers without BatchNorm: the D stems)
+  // cluster split-K (igemm_fprop_cluster_kernel): bf16 output, the `splitk` CTAs of a tile form a cluster and reduce
+  // their partial tiles through distributed shared memory in rank order
+  const void* epi_src;     // optional epilogue operand (layout of the output, bf16), see sg2_conv_dgrad
+  int epi_mode;
   long long split_stride;  // OUT_F32_STORE with split-K: split s stores its partial tile into slab s (out + s * split_stride);
                            // the slabs are summed in split order by sg2_splitk_finish (deterministic, no atomics)
 };
@@ -251,6 +255,238 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
     tc_fence_before();
   }
   __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cluster split-K
+// Same main loop as igemm_fprop_kernel, for layers whose 128 x BN tiles cannot fill the GPU (D's 4x4 / 8x8 maps, the
+// generator's first upBlocks). The `splitk` CTAs that share an output tile are ONE thread-block cluster (cluster dims
+// (1, 1, splitk)): each accumulates its K range in TMEM, parks the fp32 partial tile in its own shared memory (over the
+// operand ring, which is idle by then), and after a cluster barrier CTA r reduces the column units [r*U/S, (r+1)*U/S) of
+// the tile over all peers' shared memory in RANK ORDER (deterministic), applies the epilogue (dgrad operand, bf16
+// rounding, BatchNorm statistics) and stores bf16. No fp32 slab round trip through HBM, no separate finish launch.
+constexpr int kPartPad = 4;   // floats of padding per partial-tile row (bank spread for the 128-bit reads)
+template <int BN, int BK>
+struct ClusterCfg {
+  static constexpr int kPartRow = BN + kPartPad;
+  static constexpr size_t kPartBytes = size_t(kBlockM) * kPartRow * sizeof(float);
+  static size_t smem_bytes(int stages) {
+    const size_t ring = size_t(stages) * FpropCfg<BN, BK>::kStageBytes;
+    return (ring > kPartBytes ? ring : kPartBytes) + 1024 + 512 + 8192 + 256;   // align slack, barriers, statistics partials
+  }
+};
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(kNumThreads, 1) igemm_fprop_cluster_kernel(const __grid_constant__ FpropParams p) {
+  using Cfg = FpropCfg<BN, BK>;
+  using CC = ClusterCfg<BN, BK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.stages;
+  const size_t ring = size_t(S) * Cfg::kStageBytes;
+  const size_t data_bytes = ring > CC::kPartBytes ? ring : CC::kPartBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + data_bytes);
+  uint64_t* empty = full + S;
+  uint64_t* tmem_full = empty + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* s_red = reinterpret_cast<float*>(smem + data_bytes + 512);   // [128 slots][16] statistics partials (8 KB max use 4 KB)
+  float* part = reinterpret_cast<float*>(smem);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x;
+  t /= p.tiles_x;
+  const int ty = t % p.tiles_y;
+  const int tb = t / p.tiles_y;
+  const int x0 = tx * p.tw, y0 = ty * p.th, b0 = tb * p.nb;
+  const int n0 = blockIdx.y * BN;
+  const int g = blockIdx.z / p.splitk;
+  const int split = blockIdx.z % p.splitk;       // == rank in the cluster (cluster dims (1, 1, splitk))
+  const int KB = p.ntaps * p.kchunks;
+  const int kb_begin = (int)((long long)KB * split / p.splitk);
+  const int kb_end = (int)((long long)KB * (split + 1) / p.splitk);
+  const int nkb = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmA[0]);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nkb; ++it) {
+      mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&full[s], Cfg::kStageBytes);
+        const int kb = kb_begin + it;
+        const int tap = kb / p.kchunks;
+        const int ch = kb - tap * p.kchunks;
+        const TapF tp = p.taps[g][tap];
+        uint8_t* sa = smem + size_t(s) * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        tma_load_4d(&p.tmA[tp.map], &full[s], sa, ch * BK, x0 + tp.dx, y0 + tp.dy, b0);
+        tma_load_2d(&p.tmB, &full[s], sb, kb * BK, n0 + g * p.N);
+      }
+      __syncwarp();
+      if (++s == S) {
+        s = 0;
+        ph ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 0, 0);
+    constexpr uint32_t swc = swizzle_code(Cfg::kSw);
+    const uint64_t adesc0 = make_smem_desc(smem_u32(smem), 16, 8 * Cfg::kSw, swc);
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + Cfg::kABytes, 16, 8 * Cfg::kSw, swc);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nkb; ++it) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t so = uint64_t((uint32_t(s) * uint32_t(Cfg::kStageBytes)) >> 4);
+        const uint64_t adesc = adesc0 + so, bdesc = bdesc0 + so;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_f16(tmem_base, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      __syncwarp();
+      if (++s == S) {
+        s = 0;
+        ph ^= 1;
+      }
+    }
+    if (elect_one()) umma_commit(tmem_full);
+    __syncwarp();
+  } else {
+    // ---- phase 1: my partial tile TMEM -> my shared memory (the operand ring is idle once tmem_full has fired: every
+    // MMA that read it has completed)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
+    float* prow = part + (size_t)row * CC::kPartRow;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                               __uint_as_float(v[j + 3]));
+        if (nkb <= 0) o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + j < BN) *reinterpret_cast<float4*>(prow + c0 + j) = o;
+      }
+    }
+    tc_fence_before();
+  }
+  cluster_sync_all();   // all partial tiles of the cluster are in shared memory
+
+  if (warp >= 2) {
+    // ---- phase 2: CTA `split` owns column units [u0, u1) of 8 channels; thread = (row slot, unit): it walks its rows,
+    // sums the S partials of its 8 columns in rank order, applies the epilogue and stores 16 bytes of bf16
+    constexpr int U = BN / 8;
+    const int Sx = p.splitk;
+    const int u0 = split * U / Sx, u1 = (split + 1) * U / Sx;
+    const int nu = u1 - u0;
+    const int et = threadIdx.x - 64;
+    const bool do_stats = p.stats != nullptr;
+    float cs[8], cq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] = cq[j] = 0.f;
+    int slots = 0, slot = 0, uu = 0;
+    if (nu > 0) {
+      slots = 128 / nu;
+      slot = et / nu;
+      uu = et - slot * nu;
+    }
+    const bool active = nu > 0 && slot < slots;
+    if (active) {
+      const int col = (u0 + uu) * 8;
+      const uint32_t my_off = smem_u32(part) + uint32_t(col) * 4u;
+      for (int r = slot; r < kBlockM; r += slots) {
+        const int xi = r % p.tw, yi = (r / p.tw) % p.th, bi = r / (p.tw * p.th);
+        const int x = x0 + xi, y = y0 + yi, b = b0 + bi;
+        if (!((x < p.Wo) && (y < p.Ho) && (b < p.B))) continue;
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = 0.f;
+        const uint32_t roff = my_off + uint32_t(r) * uint32_t(CC::kPartRow * 4);
+        for (int s2 = 0; s2 < Sx; ++s2) {
+          const uint32_t ra = dsmem_addr(roff, (uint32_t)s2);
+          const float4 lo = dsmem_ld_f4(ra), hi = dsmem_ld_f4(ra + 16);
+          a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += lo.w;
+          a[4] += hi.x; a[5] += hi.y; a[6] += hi.z; a[7] += hi.w;
+        }
+        const long long off = p.out_off[g] + (long long)b * p.sb + (long long)y * p.sy + (long long)x * p.sx + n0 + col;
+        if (p.epi_mode != 0) {
+          const uint4 sv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.epi_src) + off));
+          const uint32_t w4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float elo = bf16_lo(w4[k]), ehi = bf16_hi(w4[k]);
+            if (p.epi_mode == 1) { a[2 * k] += elo; a[2 * k + 1] += ehi; }
+            else { a[2 * k] = elo > 0.f ? a[2 * k] : 0.2f * a[2 * k]; a[2 * k + 1] = ehi > 0.f ? a[2 * k + 1] : 0.2f * a[2 * k + 1]; }
+          }
+        }
+        if (p.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = a[j] > 0.f ? a[j] : 0.2f * a[j];
+        }
+        uint4 o;
+        o.x = pack_bf16x2(a[0], a[1]); o.y = pack_bf16x2(a[2], a[3]);
+        o.z = pack_bf16x2(a[4], a[5]); o.w = pack_bf16x2(a[6], a[7]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = o;
+        if (do_stats) {
+          const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float f0 = bf16_lo(w4[k]), f1 = bf16_hi(w4[k]);
+            cs[2 * k] += f0; cq[2 * k] = fmaf(f0, f0, cq[2 * k]);
+            cs[2 * k + 1] += f1; cq[2 * k + 1] = fmaf(f1, f1, cq[2 * k + 1]);
+          }
+        }
+      }
+    }
+    if (do_stats) {
+      // ordered combine of the row slots: s_red[et][16]; thread (uu, j) of slot 0 sums the slots in order
+      float* mine = s_red + et * 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { mine[j] = cs[j]; mine[8 + j] = cq[j]; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int task = et; task < nu * 16; task += 128) {     // nu can exceed 8 units for clusters of 2 or 3
+        const int u2 = task / 16, k = task % 16;
+        float tsum = 0.f;
+        for (int sl = 0; sl < slots; ++sl) tsum += s_red[(sl * nu + u2) * 16 + k];
+        double* st = p.stats + (p.stats_bg > 0 ? (long long)(b0 / p.stats_bg) * 2 * p.N : 0);
+        const int c = n0 + (u0 + u2) * 8 + (k & 7);
+        atomicAdd(&st[(k < 8 ? 0 : p.N) + c], (double)tsum);
+      }
+    }
+  }
+  cluster_sync_all();   // nobody leaves (and frees its shared memory) while a peer may still read it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);

@@ -15,6 +15,9 @@ ACT_NONE, ACT_GLU, ACT_LRELU = 0, 1, 2
 OUT_BF16, OUT_F32_ATOMIC, OUT_F32_STORE = 0, 1, 2
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 N_SM = 148
+# SMs a split-K launch is sized for: in the fused step several streams share the GPU, so a split layer does not have to
+# fill every SM by itself — fewer splits = fewer fp32 slabs to write and re-read (SG2_SPLIT_SMS, measured in DESIGN.md)
+SPLIT_SMS = int(os.environ.get("SG2_SPLIT_SMS", "148"))
 
 _launches = 0   # kernels of ours launched through this module (bench.py reports it as gpu_launches)
 
@@ -23,6 +26,12 @@ _launches = 0   # kernels of ours launched through this module (bench.py reports
 # tap sums) is an fp64 atomic over per-block partials formed in a fixed order. SG2_DETERMINISTIC=0 switches the split-K
 # and wgrad reductions back to fp32 red.global.add into a zeroed buffer (order not reproducible run to run).
 DETERMINISTIC = os.environ.get("SG2_DETERMINISTIC", "1") != "0"
+# Split-K reduction inside a thread-block cluster (the splits of a tile exchange their fp32 partial tiles through
+# distributed shared memory and reduce them in rank order: no slab round trip, no finish launch). Largest cluster used
+# (= cap of the split factor); 0 = always the slab path. Measured on the train step (ms/step): slabs 7.93, clusters of
+# 2 / 3 / 4 / 6 / 8 / 16: 7.79 / 7.89 / 7.90 / 7.98 / 8.05 / 8.19 — a cluster is gang-scheduled onto free SMs of ONE GPC,
+# which the other streams of the step make scarce, and in the shared GPU a split layer need not fill every SM itself.
+CLUSTER_SPLITK = int(os.environ.get("SG2_CLUSTER_SPLITK", "2")) if DETERMINISTIC else 0
 
 
 def launches():
@@ -134,7 +143,7 @@ def _out_hw(kind, H, W):
     return H, W
 
 
-def _auto_split(m_rows, n_cols, k_blocks, groups=1):
+def _auto_split(m_rows, n_cols, k_blocks, groups=1, cap=None):
     """Split-K factor for GEMMs whose 128 x BN output tiles cannot fill the 148 SMs.
 
     One CTA per (tile, split): the launch runs in ceil(tiles * s / 148) waves and a CTA's time is its K range plus a fixed
@@ -150,8 +159,10 @@ def _auto_split(m_rows, n_cols, k_blocks, groups=1):
         return max(1, min(k_blocks // 8, -(-N_SM // tiles)))
     tiles *= groups                                   # output-parity groups are separate GEMMs of the same launch
     best, best_cost = 1, None
-    for sp in range(1, max(1, min(k_blocks // 8, 32)) + 1):      # >= 8 K blocks per CTA: fewer fp32 atomics per output
-        waves = -(-tiles * sp // N_SM)
+    if cap is None:
+        cap = CLUSTER_SPLITK if CLUSTER_SPLITK >= 2 else 32
+    for sp in range(1, max(1, min(k_blocks // 8, cap)) + 1):     # >= 8 K blocks per CTA: little reduction work per output
+        waves = -(-tiles * sp // SPLIT_SMS)
         cost = waves * (k_blocks / sp + (6.0 if sp > 1 else 3.0))
         if best_cost is None or cost < best_cost - 1e-9:
             best, best_cost = sp, cost
@@ -178,6 +189,14 @@ def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, grou
     if splitk is None:
         splitk = 1 if (act or bias9 is not None) else _auto_split(B * Ho * Wo // pgroups, Cout, taps * max(1, Cin // 64), pgroups)
     splitk = max(1, min(splitk, _k_blocks(taps, Cin)))
+    if 1 < splitk <= CLUSTER_SPLITK and Cin % 64 == 0 and Cout % 64 == 0:
+        y = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
+        try:
+            _conv_call("sg2_conv_fprop", 1, fl, kind, _p(x), _p(wpk), _p(y), OUT_BF16, B, H, W, Cin, Cout, splitk,
+                       _p64(stats), groups, act, None, _st())
+            return y if stats is None else (y, True)
+        except _lib.NoFuse:
+            pass
     if splitk > 1:
         if DETERMINISTIC:
             y32 = torch.empty((splitk, B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
@@ -222,6 +241,14 @@ def conv_dgrad(kind, dy, wpkT, B, H, W, Cin, splitk=None, flop_scale=1.0, epi=No
     if splitk is None:
         splitk = _auto_split(B * H * W // groups, Cin, taps * max(1, Cout // 64), groups)
     splitk = max(1, min(splitk, _k_blocks(taps, Cout)))
+    if 1 < splitk <= CLUSTER_SPLITK and Cin % 64 == 0 and Cout % 64 == 0:
+        dx = torch.empty((B, H, W, Cin), device=dy.device, dtype=torch.bfloat16)
+        try:
+            _conv_call("sg2_conv_dgrad", 1, fl, kind, _p(dy), _p(wpkT), _p(dx), OUT_BF16, B, H, W, Cin, Cout, splitk,
+                       _p(epi[0]) if epi is not None else None, epi[1] if epi is not None else 0, _st())
+            return dx
+        except _lib.NoFuse:
+            pass
     if splitk > 1:
         if DETERMINISTIC:
             dx32 = torch.empty((splitk, B, H, W, Cin), device=dy.device, dtype=torch.float32)

@@ -85,6 +85,12 @@ def test_conv_fprop_dgrad_wgrad(kind, B, H, W, Ci, Co):
         ops.conv_wgrad(kind, xn, dyn, dwpk_b)                                          # second pass accumulates
         assert torch.equal(dwpk_b, dwpk + dwpk)
         assert torch.equal(ops.conv_fprop(kind, xn, wpk, Co, splitk=3), y2)
+        for sk in (2, 3, 5):        # BatchNorm statistics out of the split-K reduction (cluster or slab path)
+            st_s = torch.zeros(2 * Co, device="cuda", dtype=torch.float64)
+            ys, _ = ops.conv_fprop(kind, xn, wpk, Co, splitk=sk, stats=st_s)
+            ysf = ys.float().reshape(-1, Co)
+            assert _rel(ys.float().permute(0, 3, 1, 2), y_ref) < 5e-3
+            assert _rel(st_s[:Co], ysf.sum(0)) < 1e-4 and _rel(st_s[Co:], (ysf * ysf).sum(0)) < 1e-5, sk
     gk = torch.empty_like(dw_ref)
     ops.unpack_wgrad(kind, dwpk, gk, Co, Ci, Co, Ci, False)
     assert torch.allclose(gk, unpack_wgrad_ref(kind, dwpk, Co, Ci), atol=1e-5)          # unpack is a pure permute/sum
@@ -177,8 +183,9 @@ def test_conv_dgrad_epilogue_operand(kind, B, H, W, Ci, Co):
     fused_add = ops.conv_dgrad(kind, dy, wpkT, B, H, W, Ci, epi=(src, ops.EPI_ADD)).float()
     n1 = ops.launches()
     fused_mask = ops.conv_dgrad(kind, dy, wpkT, B, H, W, Ci, epi=(src, ops.EPI_LRELU_MASK)).float()
-    # output grids >= 16 x 8 run on the tile-resident kernel: ONE launch; the 4 x 4 map falls back to conv + kernel
-    assert (n1 - n0 == 1) if H >= 16 else (n1 - n0 >= 2), n1 - n0
+    # output grids >= 16 x 8 run on the tile-resident kernel and the split 4 x 4 map on the cluster split-K kernel, both
+    # with the operand in the epilogue: ONE launch (the slab path, SG2_CLUSTER_SPLITK=0, needs conv + finish)
+    assert (n1 - n0 == 1) if (H >= 16 or ops.CLUSTER_SPLITK >= 2) else (n1 - n0 >= 2), n1 - n0
     ref_add = base + src.float()
     ref_mask = torch.where(src.float() > 0, base, 0.2 * base)
     scale = base.abs() + src.float().abs() + 1e-2           # the sum may cancel: error relative to the operands

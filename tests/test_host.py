@@ -97,16 +97,19 @@ def test_split_k_factor_fills_whole_waves():
     must count the output-parity groups of fused-upsample / stride-2-dgrad launches, and leaves full launches alone."""
     from sg2b200 import ops
     n_sm = ops.N_SM
-    assert ops._auto_split(72 * 16, 2048, 256) == 2            # 9 x 8 tiles
-    assert ops._auto_split(24 * 16, 2048, 256) == 6            # 3 x 8 tiles
-    assert ops._auto_split(24 * 16, 1024, 64, groups=4) == 3   # 3 x 4 tiles x 4 parity groups
-    assert ops._auto_split(72 * 64 * 64, 256, 32) == 1         # thousands of tiles
-    assert ops._auto_split(24 * 16, 512, 4) == 1               # too little K to split
+    split = lambda *a, **k: ops._auto_split(*a, cap=32, **k)    # the wave logic, without the cluster-size cap
+    assert split(72 * 16, 2048, 256) == 2            # 9 x 8 tiles
+    assert split(24 * 16, 2048, 256) == 6            # 3 x 8 tiles
+    assert split(24 * 16, 1024, 64, groups=4) == 3   # 3 x 4 tiles x 4 parity groups
+    assert split(72 * 64 * 64, 256, 32) == 1         # thousands of tiles
+    assert split(24 * 16, 512, 4) == 1               # too little K to split
+    if ops.CLUSTER_SPLITK >= 2:                      # default: the splits of a tile form one cluster of at most this size
+        assert ops._auto_split(24 * 16, 2048, 256) == min(6, ops.CLUSTER_SPLITK)
     for rows in (96, 384, 1152, 1536, 4608):
         for n in (256, 512, 1024, 2048):
             for kb in (16, 64, 144, 256, 288):
                 for groups in (1, 4):
-                    s = ops._auto_split(rows, n, kb, groups)
+                    s = split(rows, n, kb, groups)
                     tiles = -(-rows // 128) * (n // 256) * groups
                     assert 1 <= s <= max(1, kb // 8)
                     if s > 1:   # a split launch is a whole number of (nearly) full waves, or a single partial one
