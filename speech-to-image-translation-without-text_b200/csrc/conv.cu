@@ -553,6 +553,7 @@ struct WgradDesc {
   int Cout, Cin;
   float* dw;
   int splitk;
+  int lane_cap;     // tile kernel: upper bound on the CTA lanes per output block (0: fill the SMs)
   float* partials;  // deterministic mode: per-split / per-lane slabs (each laid out like dw), summed by the caller
   int* slabs_out;   // plan only: receives the number of slabs this launch would write; nothing is launched
 };
@@ -709,6 +710,7 @@ static int launch_tile_wgrad(const WgradDesc& d, cudaStream_t st) {
   const int base = p.ngroups * p.tap_sets * p.m_tiles * p.n_tiles;
   int lanes = (num_sms() + base - 1) / base;
   if (lanes > pix_tiles) lanes = pix_tiles;
+  if (d.lane_cap > 0 && lanes > d.lane_cap) lanes = d.lane_cap;   // fewer CTA lanes = fewer partial slabs to reduce
   if (lanes < 1) lanes = 1;
   p.lanes = lanes;
   p.partials = d.partials;
@@ -993,6 +995,13 @@ static int wgrad_entry(int kind, const void* x, const void* dy, float* dwpk, int
   memset(&d, 0, sizeof(d));
   d.partials = partials;
   d.slabs_out = slabs_out;
+  {
+    static const int cap = [] {
+      const char* e = getenv("SG2_WGRAD_LANE_CAP");
+      return e ? atoi(e) : 0;
+    }();
+    d.lane_cap = cap;
+  }
   d.B = B;
   d.Cout = Cout;
   d.Cin = Cin;

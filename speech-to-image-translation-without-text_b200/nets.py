@@ -150,6 +150,7 @@ class GradSink:
         # next layer's wgrad then runs beside the previous layer's optimiser work instead of behind it
         self.opt = opt_stream if side_stream is not None else None
         self.keep = []
+        self.started = set()   # conv operands whose accumulator has been opened (several backward passes may add to it)
 
     def slot(self, p):
         """(tensor, accumulate_flag) for a small gradient written by a kernel."""
@@ -195,7 +196,12 @@ class GradSink:
 
     def _wgrad(self, op, x, dy):
         if self.on_ready is not None:
-            op.wgrad_begin(x.device, self.prezeroed)
+            # the layer's LAST backward pass of this sink (earlier passes, run with on_ready = None, only accumulated)
+            if op not in self.started:
+                op.wgrad_begin(x.device, self.prezeroed)
+                self.started.add(op)
+            if op in self.pending:
+                self.pending.remove(op)
             op.wgrad_add(x, dy)
             if self.opt is not None:
                 ev = torch.cuda.Event()
@@ -208,8 +214,10 @@ class GradSink:
             self.g[op.weight] = op.wgrad_finish(self.views.get(op.weight))
             self.on_ready(op.weight)
             return
-        if op not in self.pending:
+        if op not in self.started:
             op.wgrad_begin(x.device, self.prezeroed)
+            self.started.add(op)
+        if op not in self.pending:
             self.pending.append(op)
         op.wgrad_add(x, dy)
 
@@ -496,7 +504,9 @@ class GEngine:
         return ops_
 
     # ------------------------------------------------------------------ forward
-    def forward(self, z, emb, eps, training):
+    def forward(self, z, emb, eps, training, on_mu=None):
+        """on_mu(mu): called as soon as CA_NET has produced mu (the discriminators' conditioning, trainer.py:383), so that
+        work which needs mu but not the fake images can be issued while the rest of the generator runs."""
         net = self.net
         B = z.shape[0]
         T = {}
@@ -505,6 +515,8 @@ class GEngine:
         T["fc_ca"] = ops.linear_fwd(emb, None, ca.weight.detach(), ca.bias.detach(), False)
         mu, logvar, c = ops.ca_glu_reparam_fwd(T["fc_ca"], eps)
         T["c"] = c
+        if on_mu is not None:
+            on_mu(mu)
         fc, bn = net.h_net1.fc[0], net.h_net1.fc[1]
         h32 = ops.linear_fwd(c, z, fc.weight.detach(), None, False)                    # (B, ngf*32) fp32
         if training:
@@ -651,7 +663,7 @@ class DEngine:
     def conv_ops(self):
         return [self.stem.op, self.joint.op] + [b.op for b in self.trunk]
 
-    def forward(self, img, c, training, out_cond=None, out_uncond=None, groups=1, stem_col=None):
+    def forward(self, img, c, training, out_cond=None, out_uncond=None, groups=1, stem_col=None, want_features=True):
         """groups > 1: img / c hold `groups` equal sub-batches that the reference runs as separate D passes (separate
         BatchNorm batches, trainer.py:390-392); everything else is per sample, so one pass over the concatenation
         gives the same result."""
@@ -662,7 +674,8 @@ class DEngine:
             x, sv = blk.fwd(x, training, groups=groups)
             T["trunk"].append(sv)
         T["x_code"] = x
-        x_imm = ops.nhwc_to_nchw_f32(x)
+        # x_immediate (model.py:427-428) is only consumed by the class-aware loss of the G step (trainer.py:438-446)
+        x_imm = ops.nhwc_to_nchw_f32(x) if want_features else None
         cat = ops.concat_c(c, x)
         h, T["joint"] = self.joint.fwd(cat, training, groups=groups)
         T["h"] = h

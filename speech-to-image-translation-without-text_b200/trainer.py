@@ -375,7 +375,7 @@ class FusedTrainer:
                     ops.stem_im2col(fake[i], out=col3[i][2])
                     probs = torch.empty(2, 3 * B, device=self.dev, dtype=torch.float32)
                     _, _, _, T3 = D.forward((3 * B, fake[i].shape[2]), mu3, True, probs[0], probs[1], groups=3,
-                                            stem_col=col3[i].view(1, 1, -1, 64))
+                                            stem_col=col3[i].view(1, 1, -1, 64), want_features=False)
                     # rows of probs.view(6, B): cond(real, wrong, fake), uncond(real, wrong, fake)
                     # targets: real -> 1,1 ; wrong -> cond 0, uncond 1 (trainer.py:400-401) ; fake -> 0,0
                     dprobs = self._bce(probs.view(6, B), (1, 0, 0, 1, 1, 0), (1, 1, 1, u, u, u), self.losses[i:i + 1])
@@ -389,7 +389,7 @@ class FusedTrainer:
                     tapes = []
                     probs = torch.empty(6, B, device=self.dev, dtype=torch.float32)
                     for k, img in enumerate((real[i], wrong[i], fake[i])):
-                        _, _, _, T = D.forward(img, mu, True, probs[2 * k], probs[2 * k + 1])
+                        _, _, _, T = D.forward(img, mu, True, probs[2 * k], probs[2 * k + 1], want_features=False)
                         tapes.append(T)
                     # targets: real -> 1,1 ; wrong -> cond 0, uncond 1 (trainer.py:400-401) ; fake -> 0,0
                     dprobs = self._bce(probs, (1, 1, 0, 1, 0, 0), (1, u, 1, u, 1, u), self.losses[i:i + 1])
@@ -405,7 +405,8 @@ class FusedTrainer:
                     bucket.adam(self.lr_d)
                 # ---------------- (3a) D_i's share of the G step, trainer.py:436-446 (updated D weights, live fake, mu)
                 probs = torch.empty(2, B, device=self.dev, dtype=torch.float32)
-                _, _, x_imm, T = D.forward(fake[i], mu, True, probs[0], probs[1], stem_col=fake_col)
+                _, _, x_imm, T = D.forward(fake[i], mu, True, probs[0], probs[1], stem_col=fake_col,
+                                           want_features=self.cal > 0)
                 dprobs = self._bce(probs, (1, 1), (1, u), parts[i:i + 1])
                 dx_imm = None
                 if self.cal > 0:
