@@ -157,9 +157,19 @@ struct GatherDesc {
   int epi_mode;         // 0 none, SG2_EPI_ADD, SG2_EPI_LRELU_MASK
 };
 
-template <int BN, int BK>
+// two pixel tiles per CTA on the gather kernels' 256-channel instances (FpropCfg). Off by default: measured 8.05 vs 7.70
+// ms/step (fewer, longer CTAs and a higher split factor cost more than the saved weight bytes); SG2_IGEMM_MT2=1 enables it
+static bool igemm_mt2() {
+  static const bool on = [] {
+    const char* e = getenv("SG2_IGEMM_MT2");
+    return e ? atoi(e) != 0 : false;
+  }();
+  return on;
+}
+
+template <int BN, int BK, int MT = 1>
 static int launch_fprop_t(const GatherDesc& d, cudaStream_t st) {
-  using Cfg = FpropCfg<BN, BK>;
+  using Cfg = FpropCfg<BN, BK, MT>;
   FpropParams p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -196,7 +206,8 @@ static int launch_fprop_t(const GatherDesc& d, cudaStream_t st) {
   p.act = d.act;
   if (d.stats && d.stats_bg > 0 && (d.stats_bg % p.nb))
     SG2_FAIL(SG2_ENOFUSE, "fused BN statistics: a %d-image tile would straddle statistics groups of %d images", p.nb, d.stats_bg);
-  const int smax = max_stages(Cfg::kStageBytes);
+  // MT = 2 fills the 512 TMEM columns of an SM by itself: one CTA per SM, as deep a ring as shared memory allows
+  const int smax = MT == 2 ? (int)((200 * 1024) / Cfg::kStageBytes) : max_stages(Cfg::kStageBytes);
   int stages = smax;
   if (stages > KB / p.splitk + 1) stages = KB / p.splitk + 1;
   if (stages < 2) stages = 2;
@@ -204,22 +215,23 @@ static int launch_fprop_t(const GatherDesc& d, cudaStream_t st) {
   const size_t smem = Cfg::smem_bytes(stages);
   static bool attr_done[64] = {};
   if (attr_needed(attr_done)) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_kernel<BN, BK, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::smem_bytes(smax));
     if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(fprop<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
   }
-  dim3 grid(p.tiles_x * p.tiles_y * p.tiles_b, d.N / BN, p.ngroups * p.splitk);
-  igemm_fprop_kernel<BN, BK><<<grid, kNumThreads, smem, st>>>(p);
+  const int pix_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  dim3 grid((pix_tiles + MT - 1) / MT, d.N / BN, p.ngroups * p.splitk);
+  igemm_fprop_kernel<BN, BK, MT><<<grid, kNumThreads, smem, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) SG2_FAIL((int)e, "fprop<%d,%d> launch: %s", BN, BK, cudaGetErrorString(e));
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------ cluster split-K launch
-template <int BN, int BK>
+template <int BN, int BK, int MT = 1>
 static int launch_fprop_cluster_t(const GatherDesc& d, cudaStream_t st) {
-  using Cfg = FpropCfg<BN, BK>;
-  using CC = ClusterCfg<BN, BK>;
+  using Cfg = FpropCfg<BN, BK, MT>;
+  using CC = ClusterCfg<BN, BK, MT>;
   FpropParams p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -262,15 +274,15 @@ static int launch_fprop_cluster_t(const GatherDesc& d, cudaStream_t st) {
   p.stages = stages;
   static bool attr_done[64] = {};
   if (attr_needed(attr_done)) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_cluster_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_cluster_kernel<BN, BK, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)CC::smem_bytes(8 < (int)((200 * 1024) / Cfg::kStageBytes) ? 8 : (int)((200 * 1024) / Cfg::kStageBytes)));
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(igemm_fprop_cluster_kernel<BN, BK>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      e = cudaFuncSetAttribute(igemm_fprop_cluster_kernel<BN, BK, MT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(fprop_cluster<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(p.tiles_x * p.tiles_y * p.tiles_b, d.N / BN, p.ngroups * p.splitk);
+  cfg.gridDim = dim3((p.tiles_x * p.tiles_y * p.tiles_b + MT - 1) / MT, d.N / BN, p.ngroups * p.splitk);
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = CC::smem_bytes(stages);
   cfg.stream = st;
@@ -281,7 +293,7 @@ static int launch_fprop_cluster_t(const GatherDesc& d, cudaStream_t st) {
   attr[0].val.clusterDim.z = p.splitk;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_fprop_cluster_kernel<BN, BK>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_fprop_cluster_kernel<BN, BK, MT>, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     SG2_FAIL((int)e, "fprop_cluster<%d,%d> launch (cluster %d): %s", BN, BK, p.splitk, cudaGetErrorString(e));
@@ -510,6 +522,13 @@ static int launch_tile(const GatherDesc& d, cudaStream_t st) {
   return 1;
 }
 
+// pixel tiles (128 GEMM rows each) of a gather launch
+static int gather_tiles(const GatherDesc& d) {
+  int tw, th, nb;
+  if (pick_tile(d.Wg, d.Hg, kBlockM, &tw, &th, &nb)) return 0;
+  return ((d.Wg + tw - 1) / tw) * ((d.Hg + th - 1) / th) * ((d.B + nb - 1) / nb);
+}
+
 static int launch_fprop(const GatherDesc& d, cudaStream_t st) {
   if (d.Cin % 16) SG2_FAIL(SG2_EINVAL, "K per tap (%d) must be a multiple of 16", d.Cin);
   if (d.N % 16) SG2_FAIL(SG2_EINVAL, "N (%d) must be a multiple of 16", d.N);
@@ -524,12 +543,14 @@ static int launch_fprop(const GatherDesc& d, cudaStream_t st) {
   }
   if (d.bias9) SG2_FAIL(SG2_EINVAL, "conv_fprop: the region bias needs a tile-resident shape (Cin %d, N %d)", d.Cin, d.N);
   if (d.out_mode == OUT_BF16 && d.splitk > 1) {   // split-K with an in-cluster reduction (bf16 out, statistics, epilogue operand)
+    if (bk == 64 && bn == 256 && igemm_mt2() && gather_tiles(d) >= 2) return launch_fprop_cluster_t<256, 64, 2>(d, st);
     if (bk == 64 && bn == 256) return launch_fprop_cluster_t<256, 64>(d, st);
     if (bk == 64 && bn == 128) return launch_fprop_cluster_t<128, 64>(d, st);
     if (bk == 64 && bn == 64) return launch_fprop_cluster_t<64, 64>(d, st);
     SG2_FAIL(SG2_ENOFUSE, "cluster split-K: no instance for BN=%d BK=%d", bn, bk);
   }
   if (d.epi_mode) SG2_FAIL(SG2_ENOFUSE, "epilogue operand: this shape runs on the gather kernel (K %d, N %d)", d.Cin, d.N);
+  if (bn == 256 && bk == 64 && igemm_mt2() && gather_tiles(d) >= 2) return launch_fprop_t<256, 64, 2>(d, st);
 #define SG2_CASE(BN_, BK_) \
   if (bn == BN_ && bk == BK_) return launch_fprop_t<BN_, BK_>(d, st);
   SG2_CASE(256, 64) SG2_CASE(128, 64) SG2_CASE(64, 64) SG2_CASE(32, 64)

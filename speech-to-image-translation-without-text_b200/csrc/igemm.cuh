@@ -51,19 +51,24 @@ struct FpropParams {
                            // the slabs are summed in split order by sg2_splitk_finish (deterministic, no atomics)
 };
 
-template <int BN, int BK>
+// MT = pixel tiles (of 128 GEMM rows) per CTA. The main loop of these kernels is bound by the bytes TMA can bring into
+// one SM (~42 B/cycle): a 128 x 256 tile needs 48 KB per 64-deep K block against 512 tensor cycles (96 B/cycle, so the
+// tensor pipe cannot exceed ~44 %). With MT = 2 the two tiles share every weight stage (two accumulators, all 512 TMEM
+// columns at BN = 256): 64 KB per 1024 tensor cycles, i.e. two thirds of the operand bytes per output tile.
+template <int BN, int BK, int MT = 1>
 struct FpropCfg {
   static constexpr int kSw = BK * 2;  // swizzle span in bytes (128/64/32)
-  static constexpr int kABytes = kBlockM * BK * 2;
+  static constexpr int kABytes = kBlockM * BK * 2;   // one pixel tile
   static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int kStageBytes = MT * kABytes + kBBytes;
+  static constexpr int kCols = MT * BN;
+  static constexpr int kTmemCols = kCols <= 32 ? 32 : (kCols <= 64 ? 64 : (kCols <= 128 ? 128 : (kCols <= 256 ? 256 : 512)));
   static size_t smem_bytes(int stages) { return size_t(stages) * kStageBytes + 1024 + 256; }
 };
 
-template <int BN, int BK>
+template <int BN, int BK, int MT = 1>
 __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_constant__ FpropParams p) {
-  using Cfg = FpropCfg<BN, BK>;
+  using Cfg = FpropCfg<BN, BK, MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.stages;
@@ -76,13 +81,19 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // ---- tile coordinates
-  int t = blockIdx.x;
-  const int tx = t % p.tiles_x;
-  t /= p.tiles_x;
-  const int ty = t % p.tiles_y;
-  const int tb = t / p.tiles_y;
-  const int x0 = tx * p.tw, y0 = ty * p.th, b0 = tb * p.nb;
+  // ---- tile coordinates: blockIdx.x = unit of MT consecutive pixel tiles. A unit's tile past the last one decodes to
+  // an image index >= B: its TMA boxes are zero filled, its MMAs are skipped and none of its rows is stored
+  int x0[MT], y0[MT], b0[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    int t = blockIdx.x * MT + m;
+    const int tx = t % p.tiles_x;
+    t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int tb = t / p.tiles_y;
+    x0[m] = tx * p.tw, y0[m] = ty * p.th, b0[m] = tb * p.nb;
+  }
+  const int ntile = (MT == 2 && b0[MT - 1] >= p.B) ? 1 : MT;   // tiles of this unit that exist
   const int n0 = blockIdx.y * BN;
   const int g = blockIdx.z / p.splitk;
   const int split = blockIdx.z % p.splitk;
@@ -125,8 +136,10 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
         const int ch = kb - tap * p.kchunks;
         const TapF tp = p.taps[g][tap];
         uint8_t* sa = smem + size_t(s) * Cfg::kStageBytes;
-        uint8_t* sb = sa + Cfg::kABytes;
-        tma_load_4d(&p.tmA[tp.map], &full[s], sa, ch * BK, x0 + tp.dx, y0 + tp.dy, b0);
+        uint8_t* sb = sa + MT * Cfg::kABytes;
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+          tma_load_4d(&p.tmA[tp.map], &full[s], sa + m * Cfg::kABytes, ch * BK, x0[m] + tp.dx, y0[m] + tp.dy, b0[m]);
         tma_load_2d(&p.tmB, &full[s], sb, kb * BK, n0 + g * p.N);
       }
       __syncwarp();
@@ -139,7 +152,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
     constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 0, 0);
     constexpr uint32_t swc = swizzle_code(Cfg::kSw);
     const uint64_t adesc0 = make_smem_desc(smem_u32(smem), 16, 8 * Cfg::kSw, swc);
-    const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + Cfg::kABytes, 16, 8 * Cfg::kSw, swc);
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + MT * Cfg::kABytes, 16, 8 * Cfg::kSw, swc);
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < nkb; ++it) {
@@ -151,6 +164,12 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)
           umma_f16(tmem_base, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        if (MT == 2 && ntile == 2) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16(tmem_base + uint32_t(BN), adesc + uint64_t((Cfg::kABytes >> 4) + k * 2), bdesc + uint64_t(k * 2), idesc,
+                     (it > 0 || k > 0) ? 1u : 0u);
+        }
         umma_commit(&empty[s]);
       }
       __syncwarp();
@@ -168,16 +187,20 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
     const int xi = row % p.tw;
     const int yi = (row / p.tw) % p.th;
     const int bi = row / (p.tw * p.th);
-    const int x = x0 + xi, y = y0 + yi, b = b0 + bi;
-    const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
-    const long long off = p.out_off[g] + (long long)b * p.sb + (long long)y * p.sy + (long long)x * p.sx + n0 +
-                          (p.out_mode == OUT_F32_STORE ? (long long)split * p.split_stride : 0);
     const bool do_stats = (p.stats != nullptr) && (p.out_mode == OUT_BF16);
     const int et = threadIdx.x - 64;  // 0..127 within the epilogue warps
     constexpr int SN = BN < 32 ? 32 : BN;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
+#pragma unroll 1
+    for (int m = 0; m < ntile; ++m) {
+    const bool second = MT == 2 && m == 1;
+    const int x0m = second ? x0[MT - 1] : x0[0], y0m = second ? y0[MT - 1] : y0[0], b0m = second ? b0[MT - 1] : b0[0];
+    const int x = x0m + xi, y = y0m + yi, b = b0m + bi;
+    const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
+    const long long off = p.out_off[g] + (long long)b * p.sb + (long long)y * p.sy + (long long)x * p.sx + n0 +
+                          (p.out_mode == OUT_F32_STORE ? (long long)split * p.split_stride : 0);
+    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(m * BN);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
@@ -240,7 +263,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
     }
     if (do_stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      double* st = p.stats + (p.stats_bg > 0 ? (long long)(b0 / p.stats_bg) * 2 * p.N : 0);
+      double* st = p.stats + (p.stats_bg > 0 ? (long long)(b0m / p.stats_bg) * 2 * p.N : 0);
       for (int i = et; i < BN; i += 128) {
         float cs = 0.f, cq = 0.f;
 #pragma unroll
@@ -251,6 +274,8 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
         atomicAdd(&st[n0 + i], (double)cs);
         atomicAdd(&st[p.N + n0 + i], (double)cq);
       }
+      if (MT == 2) asm volatile("bar.sync 1, 128;" ::: "memory");   // the next tile overwrites the partial sums
+    }
     }
     tc_fence_before();
   }
@@ -269,20 +294,22 @@ __global__ void __launch_bounds__(kNumThreads) igemm_fprop_kernel(const __grid_c
 // the tile over all peers' shared memory in RANK ORDER (deterministic), applies the epilogue (dgrad operand, bf16
 // rounding, BatchNorm statistics) and stores bf16. No fp32 slab round trip through HBM, no separate finish launch.
 constexpr int kPartPad = 4;   // floats of padding per partial-tile row (bank spread for the 128-bit reads)
-template <int BN, int BK>
+template <int BN, int BK, int MT = 1>
 struct ClusterCfg {
   static constexpr int kPartRow = BN + kPartPad;
   static constexpr size_t kPartBytes = size_t(kBlockM) * kPartRow * sizeof(float);
   static size_t smem_bytes(int stages) {
-    const size_t ring = size_t(stages) * FpropCfg<BN, BK>::kStageBytes;
+    const size_t ring = size_t(stages) * FpropCfg<BN, BK, MT>::kStageBytes;
     return (ring > kPartBytes ? ring : kPartBytes) + 1024 + 512 + 8192 + 256;   // align slack, barriers, statistics partials
   }
 };
 
-template <int BN, int BK>
+// MT = 2: two pixel tiles per CTA share every weight stage (see FpropCfg); their partial tiles are exchanged one after
+// the other through the same shared-memory buffer.
+template <int BN, int BK, int MT = 1>
 __global__ void __launch_bounds__(kNumThreads, 1) igemm_fprop_cluster_kernel(const __grid_constant__ FpropParams p) {
-  using Cfg = FpropCfg<BN, BK>;
-  using CC = ClusterCfg<BN, BK>;
+  using Cfg = FpropCfg<BN, BK, MT>;
+  using CC = ClusterCfg<BN, BK, MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.stages;
@@ -297,12 +324,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_fprop_cluster_kernel(con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  int t = blockIdx.x;
-  const int tx = t % p.tiles_x;
-  t /= p.tiles_x;
-  const int ty = t % p.tiles_y;
-  const int tb = t / p.tiles_y;
-  const int x0 = tx * p.tw, y0 = ty * p.th, b0 = tb * p.nb;
+  int x0[MT], y0[MT], b0[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    int t = blockIdx.x * MT + m;
+    const int tx = t % p.tiles_x;
+    t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int tb = t / p.tiles_y;
+    x0[m] = tx * p.tw, y0[m] = ty * p.th, b0[m] = tb * p.nb;
+  }
+  const int ntile = (MT == 2 && b0[MT - 1] >= p.B) ? 1 : MT;   // same for every CTA of the cluster (same blockIdx.x)
   const int n0 = blockIdx.y * BN;
   const int g = blockIdx.z / p.splitk;
   const int split = blockIdx.z % p.splitk;       // == rank in the cluster (cluster dims (1, 1, splitk))
@@ -342,8 +374,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_fprop_cluster_kernel(con
         const int ch = kb - tap * p.kchunks;
         const TapF tp = p.taps[g][tap];
         uint8_t* sa = smem + size_t(s) * Cfg::kStageBytes;
-        uint8_t* sb = sa + Cfg::kABytes;
-        tma_load_4d(&p.tmA[tp.map], &full[s], sa, ch * BK, x0 + tp.dx, y0 + tp.dy, b0);
+        uint8_t* sb = sa + MT * Cfg::kABytes;
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+          tma_load_4d(&p.tmA[tp.map], &full[s], sa + m * Cfg::kABytes, ch * BK, x0[m] + tp.dx, y0[m] + tp.dy, b0[m]);
         tma_load_2d(&p.tmB, &full[s], sb, kb * BK, n0 + g * p.N);
       }
       __syncwarp();
@@ -356,7 +390,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_fprop_cluster_kernel(con
     constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 0, 0);
     constexpr uint32_t swc = swizzle_code(Cfg::kSw);
     const uint64_t adesc0 = make_smem_desc(smem_u32(smem), 16, 8 * Cfg::kSw, swc);
-    const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + Cfg::kABytes, 16, 8 * Cfg::kSw, swc);
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + MT * Cfg::kABytes, 16, 8 * Cfg::kSw, swc);
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < nkb; ++it) {
@@ -368,6 +402,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_fprop_cluster_kernel(con
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)
           umma_f16(tmem_base, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        if (MT == 2 && ntile == 2) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16(tmem_base + uint32_t(BN), adesc + uint64_t((Cfg::kABytes >> 4) + k * 2), bdesc + uint64_t(k * 2), idesc,
+                     (it > 0 || k > 0) ? 1u : 0u);
+        }
         umma_commit(&empty[s]);
       }
       __syncwarp();
@@ -378,115 +418,122 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_fprop_cluster_kernel(con
     }
     if (elect_one()) umma_commit(tmem_full);
     __syncwarp();
-  } else {
-    // ---- phase 1: my partial tile TMEM -> my shared memory (the operand ring is idle once tmem_full has fired: every
-    // MMA that read it has completed)
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
-    float* prow = part + (size_t)row * CC::kPartRow;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                               __uint_as_float(v[j + 3]));
-        if (nkb <= 0) o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c0 + j < BN) *reinterpret_cast<float4*>(prow + c0 + j) = o;
-      }
-    }
-    tc_fence_before();
   }
-  cluster_sync_all();   // all partial tiles of the cluster are in shared memory
-
   if (warp >= 2) {
-    // ---- phase 2: CTA `split` owns column units [u0, u1) of 8 channels; thread = (row slot, unit): it walks its rows,
-    // sums the S partials of its 8 columns in rank order, applies the epilogue and stores 16 bytes of bf16
-    constexpr int U = BN / 8;
-    const int Sx = p.splitk;
-    const int u0 = split * U / Sx, u1 = (split + 1) * U / Sx;
-    const int nu = u1 - u0;
-    const int et = threadIdx.x - 64;
-    const bool do_stats = p.stats != nullptr;
-    float cs[8], cq[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) cs[j] = cq[j] = 0.f;
-    int slots = 0, slot = 0, uu = 0;
-    if (nu > 0) {
-      slots = 128 / nu;
-      slot = et / nu;
-      uu = et - slot * nu;
-    }
-    const bool active = nu > 0 && slot < slots;
-    if (active) {
-      const int col = (u0 + uu) * 8;
-      const uint32_t my_off = smem_u32(part) + uint32_t(col) * 4u;
-      for (int r = slot; r < kBlockM; r += slots) {
-        const int xi = r % p.tw, yi = (r / p.tw) % p.th, bi = r / (p.tw * p.th);
-        const int x = x0 + xi, y = y0 + yi, b = b0 + bi;
-        if (!((x < p.Wo) && (y < p.Ho) && (b < p.B))) continue;
-        float a[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = 0.f;
-        const uint32_t roff = my_off + uint32_t(r) * uint32_t(CC::kPartRow * 4);
-        for (int s2 = 0; s2 < Sx; ++s2) {
-          const uint32_t ra = dsmem_addr(roff, (uint32_t)s2);
-          const float4 lo = dsmem_ld_f4(ra), hi = dsmem_ld_f4(ra + 16);
-          a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += lo.w;
-          a[4] += hi.x; a[5] += hi.y; a[6] += hi.z; a[7] += hi.w;
-        }
-        const long long off = p.out_off[g] + (long long)b * p.sb + (long long)y * p.sy + (long long)x * p.sx + n0 + col;
-        if (p.epi_mode != 0) {
-          const uint4 sv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.epi_src) + off));
-          const uint32_t w4[4] = {sv.x, sv.y, sv.z, sv.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float elo = bf16_lo(w4[k]), ehi = bf16_hi(w4[k]);
-            if (p.epi_mode == 1) { a[2 * k] += elo; a[2 * k + 1] += ehi; }
-            else { a[2 * k] = elo > 0.f ? a[2 * k] : 0.2f * a[2 * k]; a[2 * k + 1] = ehi > 0.f ? a[2 * k + 1] : 0.2f * a[2 * k + 1]; }
-          }
-        }
-        if (p.act == 2) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) a[j] = a[j] > 0.f ? a[j] : 0.2f * a[j];
-        }
-        uint4 o;
-        o.x = pack_bf16x2(a[0], a[1]); o.y = pack_bf16x2(a[2], a[3]);
-        o.z = pack_bf16x2(a[4], a[5]); o.w = pack_bf16x2(a[6], a[7]);
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = o;
-        if (do_stats) {
-          const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float f0 = bf16_lo(w4[k]), f1 = bf16_hi(w4[k]);
-            cs[2 * k] += f0; cq[2 * k] = fmaf(f0, f0, cq[2 * k]);
-            cs[2 * k + 1] += f1; cq[2 * k + 1] = fmaf(f1, f1, cq[2 * k + 1]);
-          }
-        }
-      }
-    }
-    if (do_stats) {
-      // ordered combine of the row slots: s_red[et][16]; thread (uu, j) of slot 0 sums the slots in order
-      float* mine = s_red + et * 16;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { mine[j] = cs[j]; mine[8 + j] = cq[j]; }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int task = et; task < nu * 16; task += 128) {     // nu can exceed 8 units for clusters of 2 or 3
-        const int u2 = task / 16, k = task % 16;
-        float tsum = 0.f;
-        for (int sl = 0; sl < slots; ++sl) tsum += s_red[(sl * nu + u2) * 16 + k];
-        double* st = p.stats + (p.stats_bg > 0 ? (long long)(b0 / p.stats_bg) * 2 * p.N : 0);
-        const int c = n0 + (u0 + u2) * 8 + (k & 7);
-        atomicAdd(&st[(k < 8 ? 0 : p.N) + c], (double)tsum);
-      }
-    }
+    mbar_wait(tmem_full, 0);   // every MMA that read the operand ring has completed: the ring is idle from here on
+    tc_fence_after();
   }
-  cluster_sync_all();   // nobody leaves (and frees its shared memory) while a peer may still read it
+#pragma unroll 1
+  for (int m = 0; m < ntile; ++m) {
+    const bool second = MT == 2 && m == 1;
+    const int x0m = second ? x0[MT - 1] : x0[0], y0m = second ? y0[MT - 1] : y0[0], b0m = second ? b0[MT - 1] : b0[0];
+    if (warp >= 2) {
+      // ---- phase 1: my partial tile TMEM -> my shared memory (over the idle operand ring)
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(m * BN);
+      float* prow = part + (size_t)row * CC::kPartRow;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                 __uint_as_float(v[j + 3]));
+          if (nkb <= 0) o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c0 + j < BN) *reinterpret_cast<float4*>(prow + c0 + j) = o;
+        }
+      }
+      tc_fence_before();
+    }
+    cluster_sync_all();   // all partial tiles of the cluster are in shared memory
+
+    if (warp >= 2) {
+      // ---- phase 2: CTA `split` owns column units [u0, u1) of 8 channels; thread = (row slot, unit): it walks its rows,
+      // sums the S partials of its 8 columns in rank order, applies the epilogue and stores 16 bytes of bf16
+      constexpr int U = BN / 8;
+      const int Sx = p.splitk;
+      const int u0 = split * U / Sx, u1 = (split + 1) * U / Sx;
+      const int nu = u1 - u0;
+      const int et = threadIdx.x - 64;
+      const bool do_stats = p.stats != nullptr;
+      float cs[8], cq[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs[j] = cq[j] = 0.f;
+      int slots = 0, slot = 0, uu = 0;
+      if (nu > 0) {
+        slots = 128 / nu;
+        slot = et / nu;
+        uu = et - slot * nu;
+      }
+      const bool active = nu > 0 && slot < slots;
+      if (active) {
+        const int col = (u0 + uu) * 8;
+        const uint32_t my_off = smem_u32(part) + uint32_t(col) * 4u;
+        for (int r = slot; r < kBlockM; r += slots) {
+          const int xi = r % p.tw, yi = (r / p.tw) % p.th, bi = r / (p.tw * p.th);
+          const int x = x0m + xi, y = y0m + yi, b = b0m + bi;
+          if (!((x < p.Wo) && (y < p.Ho) && (b < p.B))) continue;
+          float a[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = 0.f;
+          const uint32_t roff = my_off + uint32_t(r) * uint32_t(CC::kPartRow * 4);
+          for (int s2 = 0; s2 < Sx; ++s2) {
+            const uint32_t ra = dsmem_addr(roff, (uint32_t)s2);
+            const float4 lo = dsmem_ld_f4(ra), hi = dsmem_ld_f4(ra + 16);
+            a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += lo.w;
+            a[4] += hi.x; a[5] += hi.y; a[6] += hi.z; a[7] += hi.w;
+          }
+          const long long off = p.out_off[g] + (long long)b * p.sb + (long long)y * p.sy + (long long)x * p.sx + n0 + col;
+          if (p.epi_mode != 0) {
+            const uint4 sv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.epi_src) + off));
+            const uint32_t w4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float elo = bf16_lo(w4[k]), ehi = bf16_hi(w4[k]);
+              if (p.epi_mode == 1) { a[2 * k] += elo; a[2 * k + 1] += ehi; }
+              else { a[2 * k] = elo > 0.f ? a[2 * k] : 0.2f * a[2 * k]; a[2 * k + 1] = ehi > 0.f ? a[2 * k + 1] : 0.2f * a[2 * k + 1]; }
+            }
+          }
+          if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = a[j] > 0.f ? a[j] : 0.2f * a[j];
+          }
+          uint4 o;
+          o.x = pack_bf16x2(a[0], a[1]); o.y = pack_bf16x2(a[2], a[3]);
+          o.z = pack_bf16x2(a[4], a[5]); o.w = pack_bf16x2(a[6], a[7]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = o;
+          if (do_stats) {
+            const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float f0 = bf16_lo(w4[k]), f1 = bf16_hi(w4[k]);
+              cs[2 * k] += f0; cq[2 * k] = fmaf(f0, f0, cq[2 * k]);
+              cs[2 * k + 1] += f1; cq[2 * k + 1] = fmaf(f1, f1, cq[2 * k + 1]);
+            }
+          }
+        }
+      }
+      if (do_stats) {
+        // ordered combine of the row slots: s_red[et][16]; thread (uu, j) of slot 0 sums the slots in order
+        float* mine = s_red + et * 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { mine[j] = cs[j]; mine[8 + j] = cq[j]; }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int task = et; task < nu * 16; task += 128) {     // nu can exceed 8 units for clusters of 2 or 3
+          const int u2 = task / 16, k = task % 16;
+          float tsum = 0.f;
+          for (int sl = 0; sl < slots; ++sl) tsum += s_red[(sl * nu + u2) * 16 + k];
+          double* st = p.stats + (p.stats_bg > 0 ? (long long)(b0m / p.stats_bg) * 2 * p.N : 0);
+          const int c = n0 + (u0 + u2) * 8 + (k & 7);
+          atomicAdd(&st[(k < 8 ? 0 : p.N) + c], (double)tsum);
+        }
+      }
+    }
+    cluster_sync_all();   // nobody overwrites its partial tile (or leaves and frees its shared memory) while a peer reads it
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);

@@ -143,7 +143,16 @@ def _out_hw(kind, H, W):
     return H, W
 
 
-def _auto_split(m_rows, n_cols, k_blocks, groups=1, cap=None):
+# gather kernels: two pixel tiles per CTA on the 256-channel instances (csrc/igemm.cuh FpropCfg; same switch as the C side)
+IGEMM_MT2 = os.environ.get("SG2_IGEMM_MT2", "0") == "1"     # off: measured slower (conv.cu igemm_mt2)
+
+
+def _gather_grid(Hg, Wg):
+    """True when a conv with this per-group output grid runs on the gather kernel (conv.cu tile_eligible)."""
+    return Hg < 16 or Wg < 8
+
+
+def _auto_split(m_rows, n_cols, k_blocks, groups=1, cap=None, mt2=False):
     """Split-K factor for GEMMs whose 128 x BN output tiles cannot fill the 148 SMs.
 
     One CTA per (tile, split): the launch runs in ceil(tiles * s / 148) waves and a CTA's time is its K range plus a fixed
@@ -152,7 +161,10 @@ def _auto_split(m_rows, n_cols, k_blocks, groups=1, cap=None):
     a factor that spills a few CTAs into a second wave costs a whole extra wave."""
     bn = n_cols if n_cols in (160, 192) else (
         256 if n_cols % 256 == 0 else (128 if n_cols % 128 == 0 else (64 if n_cols % 64 == 0 else 32)))
-    tiles = -(-m_rows // 128) * max(1, n_cols // bn)
+    m_tiles = -(-m_rows // 128)
+    if mt2 and IGEMM_MT2 and bn == 256 and m_tiles >= 2:
+        m_tiles = -(-m_tiles // 2)                    # units of two pixel tiles that share every weight stage
+    tiles = m_tiles * max(1, n_cols // bn)
     if tiles >= 96 or k_blocks < 8:
         return 1
     if os.environ.get("SG2_SPLIT_OLD", "0") == "1":
@@ -187,7 +199,9 @@ def conv_fprop(kind, x, wpk, Cout, splitk=None, flop_scale=1.0, stats=None, grou
     taps = {CONV3: 9, UPCONV: 4, CONV4S2: 16, GEMM: 1}[kind]
     pgroups = 4 if kind == UPCONV else 1          # output parity groups (separate GEMMs)
     if splitk is None:
-        splitk = 1 if (act or bias9 is not None) else _auto_split(B * Ho * Wo // pgroups, Cout, taps * max(1, Cin // 64), pgroups)
+        gather = _gather_grid(*((H, W) if kind == UPCONV else (Ho, Wo))) and Cin % 64 == 0
+        splitk = 1 if (act or bias9 is not None) else _auto_split(B * Ho * Wo // pgroups, Cout, taps * max(1, Cin // 64), pgroups,
+                                                                  mt2=gather)
     splitk = max(1, min(splitk, _k_blocks(taps, Cin)))
     if 1 < splitk <= CLUSTER_SPLITK and Cin % 64 == 0 and Cout % 64 == 0:
         y = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
@@ -239,7 +253,8 @@ def conv_dgrad(kind, dy, wpkT, B, H, W, Cin, splitk=None, flop_scale=1.0, epi=No
     taps = {CONV3: 9, UPCONV: 16, CONV4S2: 4, GEMM: 1}[kind]
     groups = 4 if kind == CONV4S2 else 1
     if splitk is None:
-        splitk = _auto_split(B * H * W // groups, Cin, taps * max(1, Cout // 64), groups)
+        gather = _gather_grid(*((H // 2, W // 2) if kind == CONV4S2 else (H, W))) and Cout % 64 == 0
+        splitk = _auto_split(B * H * W // groups, Cin, taps * max(1, Cout // 64), groups, mt2=gather)
     splitk = max(1, min(splitk, _k_blocks(taps, Cout)))
     if 1 < splitk <= CLUSTER_SPLITK and Cin % 64 == 0 and Cout % 64 == 0:
         dx = torch.empty((B, H, W, Cin), device=dy.device, dtype=torch.bfloat16)
