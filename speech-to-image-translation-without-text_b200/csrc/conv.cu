@@ -12,6 +12,7 @@
 #endif
 #include "common.cuh"
 #include "igemm.cuh"
+#include "igemm_pair.cuh"
 #ifdef SG2_BUILD_PROBES
 #include "halo_probe.cuh"
 #endif
@@ -301,6 +302,97 @@ static int launch_fprop_cluster_t(const GatherDesc& d, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ CTA-pair launch (cta_group::2)
+// SG2_PAIR=0 switches the pair kernel off (the cluster / plain gather kernels take its layers again).
+static bool igemm_pair() {
+  static const bool on = [] {
+    const char* e = getenv("SG2_PAIR");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on;
+}
+
+static bool igemm_pair_wgrad() {
+  static const bool on = [] {
+    const char* e = getenv("SG2_PAIR_WGRAD");
+    return e ? atoi(e) != 0 : igemm_pair();
+  }();
+  return on;
+}
+
+template <int BN, int BK, bool kDirect>
+static int launch_fprop_pair_t(const GatherDesc& d, cudaStream_t st) {
+  using Cfg = PairCfg<BN, BK>;
+  FpropParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = pick_tile(d.Wg, d.Hg, kBlockM, &p.tw, &p.th, &p.nb))) return rc;
+  for (int i = 0; i < d.nmaps; ++i)
+    if ((rc = make_act_map(&p.tmA[i], d.a[i], BK, p.tw, p.th, p.nb))) return rc;
+  const long long K = (long long)d.ntaps * d.Cin;
+  if ((rc = make_w_map(&p.tmB, d.w, (long long)d.ngroups * d.N, K, BK, BN / 2))) return rc;   // each CTA stages half of the channels
+  memcpy(p.taps, d.taps, sizeof(p.taps));
+  p.ntaps = d.ntaps;
+  p.kchunks = d.Cin / BK;
+  p.ngroups = d.ngroups;
+  const int KB = p.ntaps * p.kchunks;
+  p.splitk = d.splitk < 1 ? 1 : (d.splitk > KB ? KB : d.splitk);
+  if (p.splitk > 8 || (kDirect && p.splitk != 1)) SG2_FAIL(SG2_ENOFUSE, "pair kernel: %d splits", p.splitk);
+  p.tiles_x = (d.Wg + p.tw - 1) / p.tw;
+  p.tiles_y = (d.Hg + p.th - 1) / p.th;
+  p.tiles_b = (d.B + p.nb - 1) / p.nb;
+  p.Wo = d.Wg;
+  p.Ho = d.Hg;
+  p.B = d.B;
+  p.N = d.N;
+  for (int g = 0; g < 4; ++g) p.out_off[g] = d.out_off[g];
+  p.sb = d.osb;
+  p.sy = d.osy;
+  p.sx = d.osx;
+  p.out = d.out;
+  p.out_mode = OUT_BF16;
+  p.stats = d.stats;
+  p.stats_bg = d.stats_bg;
+  p.act = d.act;
+  p.epi_src = d.epi_src;
+  p.epi_mode = d.epi_mode;
+  if (d.stats && d.stats_bg > 0 && (d.stats_bg % p.nb))
+    SG2_FAIL(SG2_ENOFUSE, "fused BN statistics: a %d-image tile would straddle statistics groups of %d images", p.nb, d.stats_bg);
+  const int smax = kDirect ? Cfg::kDirectStages : Cfg::kMaxStages;
+  int stages = smax;
+  if (stages > KB / p.splitk + 1) stages = KB / p.splitk + 1;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  static bool attr_done[64] = {};
+  if (attr_needed(attr_done)) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_pair_kernel<BN, BK, kDirect>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(kDirect ? Cfg::smem_bytes_direct(smax) : Cfg::smem_bytes(smax)));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(igemm_fprop_pair_kernel<BN, BK, kDirect>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(fprop_pair<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
+  }
+  const int pix_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * ((pix_tiles + 1) / 2), d.N / BN, p.ngroups * p.splitk);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = kDirect ? Cfg::smem_bytes_direct(stages) : Cfg::smem_bytes(stages);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = p.splitk;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_fprop_pair_kernel<BN, BK, kDirect>, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    SG2_FAIL((int)e, "fprop_pair<%d,%d> launch (cluster 2x%d): %s", BN, BK, p.splitk, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ tile-resident launch
 static long long* g_tile_dbg = nullptr;
 static int tile_mode() {
@@ -542,6 +634,14 @@ static int launch_fprop(const GatherDesc& d, cudaStream_t st) {
     if (rc != 1) return rc;
   }
   if (d.bias9) SG2_FAIL(SG2_EINVAL, "conv_fprop: the region bias needs a tile-resident shape (Cin %d, N %d)", d.Cin, d.N);
+  if (d.out_mode == OUT_BF16 && bk == 64 && bn == 256 && d.splitk <= 4 && igemm_pair() && gather_tiles(d) >= 2) {
+    // CTA pairs (half of the weight tile per SM) unless the phantom tile of an odd tile count costs an extra wave
+    const int tiles = gather_tiles(d), sk = d.splitk < 1 ? 1 : d.splitk;
+    const long long per = (long long)(d.N / 256) * d.ngroups * sk;
+    const long long cap = (long long)num_sms() * (sk == 1 ? 2 : 1);   // CTAs that run at once (ring-only kernels: two per SM)
+    const long long w_plain = (tiles * per + cap - 1) / cap, w_pair = (2 * ((tiles + 1) / 2) * per + cap - 1) / cap;
+    if (w_pair <= w_plain) return sk == 1 ? launch_fprop_pair_t<256, 64, true>(d, st) : launch_fprop_pair_t<256, 64, false>(d, st);
+  }
   if (d.out_mode == OUT_BF16 && d.splitk > 1) {   // split-K with an in-cluster reduction (bf16 out, statistics, epilogue operand)
     if (bk == 64 && bn == 256 && igemm_mt2() && gather_tiles(d) >= 2) return launch_fprop_cluster_t<256, 64, 2>(d, st);
     if (bk == 64 && bn == 256) return launch_fprop_cluster_t<256, 64>(d, st);
@@ -775,6 +875,65 @@ static int launch_tile_wgrad(const WgradDesc& d, cudaStream_t st) {
   return 0;
 }
 
+// igemm_wgrad_kernel<256, 64, 64> on CTA pairs (igemm_pair.cuh): 256 x 256 channels per pair, half of the activation tile per SM
+static int launch_wgrad_pair(const WgradDesc& d, cudaStream_t st) {
+  using Cfg = WgradPairCfg;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = pick_tile(d.Wg, d.Hg, kWgradBKP, &p.tw, &p.th, &p.nb))) return rc;
+  if (d.slabs_out) {
+    const int pt = ((d.Wg + p.tw - 1) / p.tw) * ((d.Hg + p.th - 1) / p.th) * ((d.B + p.nb - 1) / p.nb);
+    *d.slabs_out = d.splitk < 1 ? 1 : (d.splitk > pt ? pt : d.splitk);
+    return 0;
+  }
+  for (int i = 0; i < d.namaps; ++i)
+    if ((rc = make_act_map(&p.tmA[i], d.a[i], Cfg::kCW, p.tw, p.th, p.nb))) return rc;
+  for (int i = 0; i < d.nbmaps; ++i)
+    if ((rc = make_act_map(&p.tmB[i], d.b[i], Cfg::kCW, p.tw, p.th, p.nb))) return rc;
+  memcpy(p.jobs, d.jobs, sizeof(p.jobs));
+  p.njobs = d.njobs;
+  p.tiles_x = (d.Wg + p.tw - 1) / p.tw;
+  p.tiles_y = (d.Hg + p.th - 1) / p.th;
+  p.tiles_b = (d.B + p.nb - 1) / p.nb;
+  const int PT = p.tiles_x * p.tiles_y * p.tiles_b;
+  p.splitk = d.splitk < 1 ? 1 : (d.splitk > PT ? PT : d.splitk);
+  p.Cout = d.Cout;
+  p.Cin = d.Cin;
+  p.dw = d.dw;
+  p.partials = d.partials;
+  p.slab = (long long)d.Cout * d.njobs * d.Cin;
+  int stages = Cfg::kStages;
+  if (stages > PT / p.splitk + 1) stages = PT / p.splitk + 1;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  static bool attr_done[64] = {};
+  if (attr_needed(attr_done)) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::smem_bytes(Cfg::kStages));
+    if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(wgrad_pair): %s", cudaGetErrorString(e));
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((d.Cout / kBlockM) * (d.Cin / Cfg::kBN), d.njobs, p.splitk);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::smem_bytes(stages);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_wgrad_pair_kernel, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    SG2_FAIL((int)e, "wgrad_pair launch: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
 static int launch_wgrad(const WgradDesc& d, cudaStream_t st) {
   {
     const int rc = launch_tile_wgrad(d, st);
@@ -784,6 +943,7 @@ static int launch_wgrad(const WgradDesc& d, cudaStream_t st) {
   const int cwa = (d.Cout % 64 == 0) ? 64 : 32;
   const int cwb = (d.Cin % 64 == 0) ? 64 : ((d.Cin % 32 == 0) ? 32 : 16);
   const int bn = d.Cin <= 16 ? 16 : (d.Cin <= 32 ? 32 : (d.Cin <= 64 ? 64 : (d.Cin <= 128 ? 128 : 256)));
+  if (igemm_pair_wgrad() && d.Cout % 256 == 0 && d.Cin % 256 == 0) return launch_wgrad_pair(d, st);
 #define SG2_CASE(BN_, A_, B_) \
   if (bn == BN_ && cwa == A_ && cwb == B_) return launch_wgrad_t<BN_, A_, B_>(d, st);
   SG2_CASE(256, 64, 64) SG2_CASE(128, 64, 64) SG2_CASE(64, 64, 64)

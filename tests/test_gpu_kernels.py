@@ -30,6 +30,8 @@ CONV_CASES = [  # kind, B, H, W, Cin, Cout
     # tile-resident kernel (output grid >= 16 x 8): partial edge tiles, four parity-plane sources, every swizzle width
     (0, 1, 24, 20, 32, 96), (2, 2, 32, 32, 64, 128), (2, 1, 48, 40, 32, 64), (1, 1, 24, 20, 64, 32),
     (0, 2, 32, 16, 128, 256), (2, 1, 32, 32, 16, 32),
+    # CTA-pair gather kernel (256-channel tiles, >= 2 pixel tiles): odd tile count (phantom peer), parity groups, N > 256
+    (2, 12, 16, 16, 128, 256), (0, 20, 4, 4, 256, 512), (1, 24, 4, 4, 256, 256),
 ]
 
 
@@ -163,7 +165,8 @@ def test_concat_c_and_backward():
     assert _rel(dc, dcat[..., :E].float().sum((1, 2))) < 1e-5
 
 
-@pytest.mark.parametrize("kind,B,H,W,Ci,Co", [(0, 2, 32, 32, 32, 64), (2, 2, 32, 32, 64, 128), (0, 3, 4, 4, 128, 256)])
+@pytest.mark.parametrize("kind,B,H,W,Ci,Co", [(0, 2, 32, 32, 32, 64), (2, 2, 32, 32, 64, 128), (0, 3, 4, 4, 128, 256),
+                                                  (0, 20, 4, 4, 256, 512)])
 def test_conv_dgrad_epilogue_operand(kind, B, H, W, Ci, Co):
     """dgrad with a residual gradient added / a LeakyReLU mask applied in the epilogue (or, for shapes on the gather
     kernel, by the separate kernel) equals dgrad followed by the separate kernel up to one bf16 rounding (2^-8)."""
