@@ -303,13 +303,30 @@ static int launch_fprop_cluster_t(const GatherDesc& d, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------ CTA-pair launch (cta_group::2)
-// SG2_PAIR=0 switches the pair kernel off (the cluster / plain gather kernels take its layers again).
+// OFF by default (SG2_PAIR=1 / SG2_PAIR_WGRAD=1 opt in): in the multi-stream train step, where the three discriminators'
+// branches run pair kernels next to each other and next to the persistent / cluster kernels, the pair kernels deadlock
+// about once in a few hundred steps (tools/stress_replay.py with LOAD=1 hangs within 500 replays with either pair kernel
+// on, never in 2 500 replays with both off, never on a single stream; forcing one pair CTA per SM through the shared
+// memory request below did not cure it). Alone on the GPU they are correct (tests/test_gpu_kernels.py pair cases) and
+// took the step's conv launches from 5.64 to 5.49 ms, the step itself from 7.69 to 7.66 ms.
 static bool igemm_pair() {
   static const bool on = [] {
     const char* e = getenv("SG2_PAIR");
-    return e ? atoi(e) != 0 : true;
+    return e ? atoi(e) != 0 : false;
   }();
   return on;
+}
+
+// One hypothesis for that deadlock: a cta_group::2 TMEM allocation takes columns on both SMs of the pair, so two pair CTAs
+// resident on the same SM couple could each hold one SM's columns while waiting for the other's. Every pair launch asks for
+// more than half of an SM's shared memory (at most one pair CTA per SM; SG2_PAIR_SMEM_KB). Kept as a precaution: the hang
+// persisted with it, so this is not (the whole) cause.
+static size_t pair_exclusive_smem(size_t need) {
+  static const size_t floor_ = [] {
+    const char* e = getenv("SG2_PAIR_SMEM_KB");
+    return (size_t)(e ? atoi(e) : 118) * 1024;
+  }();
+  return need > floor_ ? need : floor_;
 }
 
 static bool igemm_pair_wgrad() {
@@ -366,7 +383,7 @@ static int launch_fprop_pair_t(const GatherDesc& d, cudaStream_t st) {
   static bool attr_done[64] = {};
   if (attr_needed(attr_done)) {
     cudaError_t e = cudaFuncSetAttribute(igemm_fprop_pair_kernel<BN, BK, kDirect>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(kDirect ? Cfg::smem_bytes_direct(smax) : Cfg::smem_bytes(smax)));
+                                         (int)pair_exclusive_smem(kDirect ? Cfg::smem_bytes_direct(smax) : Cfg::smem_bytes(smax)));
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(igemm_fprop_pair_kernel<BN, BK, kDirect>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(fprop_pair<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
@@ -376,7 +393,7 @@ static int launch_fprop_pair_t(const GatherDesc& d, cudaStream_t st) {
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * ((pix_tiles + 1) / 2), d.N / BN, p.ngroups * p.splitk);
   cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = kDirect ? Cfg::smem_bytes_direct(stages) : Cfg::smem_bytes(stages);
+  cfg.dynamicSmemBytes = pair_exclusive_smem(kDirect ? Cfg::smem_bytes_direct(stages) : Cfg::smem_bytes(stages));
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -910,14 +927,14 @@ static int launch_wgrad_pair(const WgradDesc& d, cudaStream_t st) {
   static bool attr_done[64] = {};
   if (attr_needed(attr_done)) {
     cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::smem_bytes(Cfg::kStages));
+                                         (int)pair_exclusive_smem(Cfg::smem_bytes(Cfg::kStages)));
     if (e != cudaSuccess) SG2_FAIL((int)e, "cudaFuncSetAttribute(wgrad_pair): %s", cudaGetErrorString(e));
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((d.Cout / kBlockM) * (d.Cin / Cfg::kBN), d.njobs, p.splitk);
   cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = Cfg::smem_bytes(stages);
+  cfg.dynamicSmemBytes = pair_exclusive_smem(Cfg::smem_bytes(stages));
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

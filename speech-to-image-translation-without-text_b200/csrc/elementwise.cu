@@ -994,63 +994,85 @@ __global__ void head_tanh_bwd_kernel(const float* __restrict__ dimg, const float
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, uint4* __restrict__ col, int B,
                                                           int S) {
   // one block = one output row (b, oy): the 4 input rows x 3 channels it reads are staged in shared memory with
-  // coalesced loads (+1 zero column each side = the conv padding); every thread then emits 16-byte col vectors.
-  extern __shared__ float rows[];   // [3][4][S + 2]
+  // coalesced loads (+1 zero column each side = the conv padding). The col row is assembled in shared memory as bf16
+  // pairs — item = (pair q of k, ox) with q uniform over a warp, so the k -> (c, kh, kw) decode is one broadcast table
+  // read instead of eight run-time divisions per vector — and leaves with coalesced 16-byte stores.
+  extern __shared__ float rows[];   // [3][4][S + 2] floats | [So][33] words | [48] offsets
   const int So = S / 2, SP = S + 2;
+  uint32_t* outw = reinterpret_cast<uint32_t*>(rows + 12 * SP);
+  int* off = reinterpret_cast<int*>(outw + So * 33);
+  if (threadIdx.x < 48) {
+    const int k = threadIdx.x, c = k % 3, t = k / 3;
+    off[k] = (c * 4 + (t >> 2)) * SP + (t & 3);
+  }
   for (int blk = blockIdx.x; blk < B * So; blk += gridDim.x) {
     const int b = blk / So, oy = blk % So;
+    __syncthreads();
     for (int e = threadIdx.x; e < 12 * SP; e += blockDim.x) {
-      const int xx = e % SP, rr = (e / SP) & 3, c = e / (4 * SP);
+      const int cr = e / SP, xx = e - cr * SP, rr = cr & 3, c = cr >> 2;
       const int y = 2 * oy + rr - 1, x = xx - 1;
-      rows[e] = (y >= 0 && y < S && x >= 0 && x < S) ? img[(((long long)b * 3 + c) * S + y) * S + x] : 0.f;
+      rows[e] = (y >= 0 && y < S && x >= 0 && x < S) ? __ldg(img + (((long long)b * 3 + c) * S + y) * S + x) : 0.f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 24 * So; e += blockDim.x) {
+      const int q = e / So, ox = e - q * So;
+      const float v0 = rows[off[2 * q] + 2 * ox], v1 = rows[off[2 * q + 1] + 2 * ox];
+      outw[ox * 33 + q] = pack_bf16x2(v0, v1);
     }
     __syncthreads();
     for (int e = threadIdx.x; e < So * 8; e += blockDim.x) {
       const int v = e & 7, ox = e >> 3;
-      float f[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = v * 8 + j;
-        float val = 0.f;
-        if (k < 48) {
-          const int c = k % 3, t = k / 3, kh = t >> 2, kw = t & 3;
-          val = rows[(c * 4 + kh) * SP + 2 * ox + kw];
-        }
-        f[j] = val;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (v < 6) {
+        const uint32_t* w = outw + ox * 33 + 4 * v;
+        o = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      col[((long long)blk * So + ox) * 8 + v] = pack8(f);
+      col[((long long)blk * So + ox) * 8 + v] = o;
     }
-    __syncthreads();
   }
 }
 
-// dimg fp32 NCHW (=, not +=) from dcol [P][64] bf16 (gather form: no atomics)
-__global__ void stem_col2im_kernel(const __nv_bfloat16* __restrict__ dcol, float* __restrict__ dimg, int B, int S) {
+// dimg fp32 NCHW (=, not +=) from dcol [P][64] bf16 (gather form: no atomics).
+// Image rows y = 2t+1 and 2t+2 read exactly the dcol rows oy = t and t+1 (kh = y + 1 - 2 oy in 0..3), so one block per
+// (b, t), t = -1 .. So-1, stages those two dcol rows (48 used columns of each im2col row, 16-byte coalesced loads, rows
+// padded to 33 words: conflict-free stores) and writes the two image rows of the three channels with coalesced stores.
+// The first form gathered four scattered 2-byte values per pixel straight from global memory: 122 us for D256's 50 MB.
+__global__ void __launch_bounds__(256) stem_col2im_kernel(const __nv_bfloat16* __restrict__ dcol, float* __restrict__ dimg,
+                                                          int B, int S) {
+  extern __shared__ uint32_t crow[];   // [2][So][33] words (bf16 pairs)
   const int So = S / 2;
-  const long long total = (long long)B * 3 * S * S;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % S);
-    const int y = (int)((i / S) % S);
-    const int c = (int)((i / ((long long)S * S)) % 3);
-    const int b = (int)(i / ((long long)3 * S * S));
-    float acc = 0.f;
-#pragma unroll
-    for (int kh = 0; kh < 4; ++kh) {
-      const int ty = y + 1 - kh;
-      if (ty < 0 || (ty & 1)) continue;
-      const int oy = ty >> 1;
-      if (oy >= So) continue;
-#pragma unroll
-      for (int kw = 0; kw < 4; ++kw) {
-        const int tx = x + 1 - kw;
-        if (tx < 0 || (tx & 1)) continue;
-        const int ox = tx >> 1;
-        if (ox >= So) continue;
-        acc += __bfloat162float(dcol[(((long long)b * So + oy) * So + ox) * 64 + (kh * 4 + kw) * 3 + c]);
-      }
+  const int nt = So + 1;
+  for (int blk = blockIdx.x; blk < B * nt; blk += gridDim.x) {
+    const int b = blk / nt, t = blk % nt - 1;
+    __syncthreads();
+    for (int e = threadIdx.x; e < 2 * So * 6; e += blockDim.x) {   // 6 x 16 bytes = the 48 used columns
+      const int j = e % 6, r = e / 6, oi = r / So, ox = r - oi * So, oy = t + oi;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (oy >= 0 && oy < So) v = __ldg(reinterpret_cast<const uint4*>(dcol + (((long long)b * So + oy) * So + ox) * 64) + j);
+      uint32_t* d = crow + r * 33 + 4 * j;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
-    dimg[i] = acc;
+    __syncthreads();
+    for (int e = threadIdx.x; e < 2 * 3 * S; e += blockDim.x) {
+      const int x = e % S, c = (e / S) % 3, yi = e / (3 * S);
+      const int y = 2 * t + 1 + yi;
+      if (y < 0 || y >= S) continue;
+      float acc = 0.f;
+#pragma unroll
+      for (int oi = 1; oi >= 0; --oi) {               // kh ascending, like the reference's accumulation order
+        const int kh = y + 1 - 2 * (t + oi);          // oi = 1: yi (0 | 1);  oi = 0: 2 + yi (2 | 3)
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const int kw = ((x + 1) & 1) + 2 * kk;      // x + 1 - kw even
+          const int ox = (x + 1 - kw) >> 1;
+          if (ox < 0 || ox >= So) continue;
+          const int k = (kh * 4 + kw) * 3 + c;
+          const uint32_t w = crow[(oi * So + ox) * 33 + (k >> 1)];
+          acc += (k & 1) ? bf16_hi(w) : bf16_lo(w);
+        }
+      }
+      dimg[(((long long)b * 3 + c) * S + y) * S + x] = acc;
+    }
   }
 }
 
@@ -1397,13 +1419,17 @@ int sg2_stem_im2col(const float* img, void* col, int B, int S, void* stream) {
   if (S % 2) EW_FAIL(SG2_EINVAL, "stem_im2col: odd image size");
   long long nblk = (long long)B * (S / 2);
   if (nblk > 148 * 16) nblk = 148 * 16;
-  stem_im2col_kernel<<<(unsigned)nblk, 256, 12 * (S + 2) * sizeof(float), (cudaStream_t)stream>>>(img, (uint4*)col, B, S);
+  stem_im2col_kernel<<<(unsigned)nblk, 256, (12 * (S + 2) + (S / 2) * 33 + 48) * sizeof(float), (cudaStream_t)stream>>>(img, (uint4*)col, B, S);
   return launch_ok("stem_im2col");
 }
 
 int sg2_stem_col2im(const void* dcol, float* dimg, int B, int S, void* stream) {
-  stem_col2im_kernel<<<grid1d((long long)B * 3 * S * S), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dcol,
-                                                                                        dimg, B, S);
+  if (S % 2) EW_FAIL(SG2_EINVAL, "stem_col2im: odd image size");
+  const int So = S / 2;
+  long long nblk = (long long)B * (So + 1);
+  if (nblk > 148 * 16) nblk = 148 * 16;
+  stem_col2im_kernel<<<(unsigned)nblk, 256, (size_t)2 * So * 33 * sizeof(uint32_t), (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dcol, dimg, B, S);
   return launch_ok("stem_col2im");
 }
 

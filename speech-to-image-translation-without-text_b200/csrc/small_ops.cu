@@ -115,32 +115,50 @@ __device__ __forceinline__ float warp_reduce8(float (&v)[8], int lane) {
   return v[0];   // every lane: the sum of row ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)
 }
 constexpr int kRtF = 4;   // features in flight per warp step
-template <bool OUT_BF16>
-__global__ void __launch_bounds__(256) linear_fwd_rt_kernel(const float* __restrict__ x1, int K1, const float* __restrict__ x2,
-                                                            int K2, const float* __restrict__ w,
-                                                            const float* __restrict__ bias, void* __restrict__ out, int M,
-                                                            int N, int Kp) {
-  extern __shared__ float xs[];   // [32][Kp]
+// RPW = batch rows per warp: 8 (M up to 32) or 6 (M <= 24: all four m-groups carry rows, and x (8 x 6) + weights (4 x 8) +
+// accumulators (4 x 6) fit the 128 registers of two resident blocks per SM — the 8-row form needs 147, i.e. one block per
+// SM and two waves for the 296-block grid of the 30 MB fc).
+template <bool OUT_BF16, int RPW>
+__global__ void __launch_bounds__(256, 2) linear_fwd_rt_kernel(const float* __restrict__ x1, int K1, const float* __restrict__ x2,
+                                                               int K2, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, void* __restrict__ out, int M,
+                                                               int N, int Kp) {
+  extern __shared__ __align__(16) float xs[];   // [4 * RPW][Kp]
+  constexpr int kRows = 4 * RPW;
   const int K = K1 + K2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mg = warp & 3, fs = warp >> 2;
   const int nchunks = (Kp + 255) / 256;
   const int ngroups = (N + kRtF - 1) / kRtF;
   const int row = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-  for (int m0 = 0; m0 < M; m0 += 32) {
+  const bool vec = ((K1 | K2) & 3) == 0 && ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2)) & 15) == 0;
+  for (int m0 = 0; m0 < M; m0 += kRows) {
     __syncthreads();
-    for (int e = threadIdx.x; e < 32 * Kp; e += 256) {
-      const int m = m0 + e / Kp, k = e % Kp;
-      xs[e] = (m < M && k < K) ? lin_x(x1, K1, x2, K2, m, k) : 0.f;
+    if (vec) {
+      // 16-byte loads, every load of the thread in flight at once (the scalar loop was a chain of ~128 dependent round trips)
+      const int kq = Kp >> 2;
+      for (int e = threadIdx.x; e < kRows * kq; e += 256) {
+        const int r = e / kq, k = (e - r * kq) << 2, m = m0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < M && k < K)
+          v = k < K1 ? __ldg(reinterpret_cast<const float4*>(x1 + (long long)m * K1 + k))
+                     : __ldg(reinterpret_cast<const float4*>(x2 + (long long)m * K2 + (k - K1)));
+        *reinterpret_cast<float4*>(xs + r * Kp + k) = v;
+      }
+    } else {
+      for (int e = threadIdx.x; e < kRows * Kp; e += 256) {
+        const int m = m0 + e / Kp, k = e % Kp;
+        xs[e] = (m < M && k < K) ? lin_x(x1, K1, x2, K2, m, k) : 0.f;
+      }
     }
     __syncthreads();
-    float xr[8][8];
+    float xr[8][RPW];
     auto load_x = [&](int ch) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int k = ch * 256 + j * 32 + lane;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) xr[j][r] = k < Kp ? xs[(mg * 8 + r) * Kp + k] : 0.f;
+        for (int r = 0; r < RPW; ++r) xr[j][r] = k < Kp ? xs[(mg * RPW + r) * Kp + k] : 0.f;
       }
     };
     if (nchunks == 1) load_x(0);
@@ -159,20 +177,20 @@ __global__ void __launch_bounds__(256) linear_fwd_rt_kernel(const float* __restr
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int k = ch * 256 + j * 32 + lane;
-            wv[f][j] = (n + f < N && k < K) ? w[(long long)(n + f) * K + k] : 0.f;
+            wv[f][j] = (n + f < N && k < K) ? __ldg(w + (long long)(n + f) * K + k) : 0.f;
           }
 #pragma unroll
         for (int f = 0; f < kRtF; ++f)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
 #pragma unroll
-            for (int r = 0; r < 8; ++r) acc[f][r] = fmaf(wv[f][j], xr[j][r], acc[f][r]);
+            for (int r = 0; r < RPW; ++r) acc[f][r] = fmaf(wv[f][j], xr[j][r], acc[f][r]);
       }
 #pragma unroll
       for (int f = 0; f < kRtF; ++f) {
         const float s = warp_reduce8(acc[f], lane);
-        const int m = m0 + mg * 8 + row;
-        if ((lane & 3) == 0 && n + f < N && m < M) {
+        const int m = m0 + mg * RPW + row;
+        if ((lane & 3) == 0 && row < RPW && n + f < N && m < M) {
           const float v = s + (bias ? bias[n + f] : 0.f);
           if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[(long long)m * N + n + f] = __float2bfloat16_rn(v);
           else reinterpret_cast<float*>(out)[(long long)m * N + n + f] = v;
@@ -762,22 +780,29 @@ int sg2_linear_fwd(const float* x1, int K1, const float* x2, int K2, const float
   if (M < 1 || M > 4096) SG2_FAIL(SG2_EINVAL, "linear_fwd: M=%d", M);
   if (K1 + K2 <= 1024) {
     const int Kp = (K1 + K2 + 31) / 32 * 32;
-    const size_t smem = (size_t)32 * Kp * sizeof(float);
     static bool attr_done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-      cudaFuncSetAttribute(linear_fwd_rt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4);
-      cudaFuncSetAttribute(linear_fwd_rt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4);
+      cudaFuncSetAttribute(linear_fwd_rt_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4);
+      cudaFuncSetAttribute(linear_fwd_rt_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4);
+      cudaFuncSetAttribute(linear_fwd_rt_kernel<true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4);
+      cudaFuncSetAttribute(linear_fwd_rt_kernel<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4);
       attr_done[dev] = true;
     }
     const int ngroups = (N + kRtF - 1) / kRtF;
     int blocks = (ngroups + 1) / 2;                 // two feature slots per block
     if (blocks > 148 * 2) blocks = 148 * 2;
-    if (out_bf16)
-      linear_fwd_rt_kernel<true><<<blocks, 256, smem, (cudaStream_t)stream>>>(x1, K1, x2, K2, w, bias, out, M, N, Kp);
-    else
-      linear_fwd_rt_kernel<false><<<blocks, 256, smem, (cudaStream_t)stream>>>(x1, K1, x2, K2, w, bias, out, M, N, Kp);
+    const bool r6 = M <= 24;                        // four m-groups of 6 rows (batch 24) instead of 8
+    const size_t smem = (size_t)(r6 ? 24 : 32) * Kp * sizeof(float);
+    auto s_ = (cudaStream_t)stream;
+    if (out_bf16) {
+      if (r6) linear_fwd_rt_kernel<true, 6><<<blocks, 256, smem, s_>>>(x1, K1, x2, K2, w, bias, out, M, N, Kp);
+      else linear_fwd_rt_kernel<true, 8><<<blocks, 256, smem, s_>>>(x1, K1, x2, K2, w, bias, out, M, N, Kp);
+    } else {
+      if (r6) linear_fwd_rt_kernel<false, 6><<<blocks, 256, smem, s_>>>(x1, K1, x2, K2, w, bias, out, M, N, Kp);
+      else linear_fwd_rt_kernel<false, 8><<<blocks, 256, smem, s_>>>(x1, K1, x2, K2, w, bias, out, M, N, Kp);
+    }
     SG2_LAUNCH_OK("linear_fwd_rt");
   }
   // feature groups per warp: enough to amortise the activation staging, few enough to fill the SMs (8 warps per block)

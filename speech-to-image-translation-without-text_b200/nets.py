@@ -504,9 +504,11 @@ class GEngine:
         return ops_
 
     # ------------------------------------------------------------------ forward
-    def forward(self, z, emb, eps, training, on_mu=None):
+    def forward(self, z, emb, eps, training, on_mu=None, on_img=None):
         """on_mu(mu): called as soon as CA_NET has produced mu (the discriminators' conditioning, trainer.py:383), so that
-        work which needs mu but not the fake images can be issued while the rest of the generator runs."""
+        work which needs mu but not the fake images can be issued while the rest of the generator runs.
+        on_img(i, img): called as soon as stage i's image has been issued (the smaller discriminators' updates only need
+        their own scale: they can start while the later generator stages are still running)."""
         net = self.net
         B = z.shape[0]
         T = {}
@@ -537,6 +539,8 @@ class GEngine:
         imgs = []
         img, hsv = self.heads[0].fwd(x)
         imgs.append(img)
+        if on_img is not None:
+            on_img(0, img)
         T["heads"] = [hsv]
         T["stages"] = []
         for si, (joint, res, up) in enumerate(self.stages):
@@ -550,6 +554,8 @@ class GEngine:
             T["stages"].append((sj, sres, su))
             img, hsv = self.heads[si + 1].fwd(x)
             imgs.append(img)
+            if on_img is not None:
+                on_img(si + 1, img)
             T["heads"].append(hsv)
         T["imgs"] = imgs
         return imgs, mu, logvar, T
