@@ -521,8 +521,12 @@ __device__ __forceinline__ uint2 pack4(const float (&f)[4]) {
   return make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
 }
 // 1 / (1 + 2^t): the sigmoid of x when t = -x * log2(e) (the scale is folded into the per-channel constants)
+// t is clamped so that e = 2^t stays finite: the backward pass forms 1 - s as e * s, and a gate pre-activation far
+// below zero (a few outlier pixels of a sharply peaked channel reach |z| ~ sqrt(pixels) after BatchNorm) gave
+// e = inf, s = 0, e * s = NaN — one NaN channel, then every generator gradient (found at step 189 of a run on
+// three rotating batches; tests/test_gpu_kernels.py::test_glu_backward_extreme_gate). 2^-100 is zero at bf16 output scale.
 __device__ __forceinline__ float sigmoid_from_t(float t, float& e) {
-  e = exp2f(t);
+  e = exp2f(fminf(t, 100.f));
   return __fdividef(1.f, 1.f + e);
 }
 

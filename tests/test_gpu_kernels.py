@@ -149,6 +149,38 @@ def test_bn_act_forward_backward(act, P, C):
     assert _rel(dg, 2 * dg_ref) < 2e-3
 
 
+def test_glu_backward_extreme_gate():
+    """A sharply peaked gate channel with a few outlier pixels: after BatchNorm the outliers sit hundreds of standard
+    deviations below zero (|z| ~ sqrt(pixels)), exp(-z) overflows fp32 and a backward pass that forms 1 - sigmoid as
+    exp(-z) * sigmoid returned NaN for the whole channel (rotating-batch run, step 189: every generator gradient NaN
+    while the fp32 oracle stayed finite). Forward and backward must stay finite and match torch."""
+    from sg2b200 import ops
+    P, C = 4096 * 16, 64
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(P, C, generator=g) * 1e-3
+    x[:3, C // 2 + 5] = -40.0            # gate half, channel 5: z ~ -150 after normalisation (2^216 as exp2 argument)
+    x[:3, C // 2 + 9] = 40.0             # and the saturated-open side
+    x = _bf(x).cuda()
+    gamma, beta = torch.ones(C).cuda(), torch.zeros(C).cuda()
+    dout = _bf(torch.randn(P, C // 2, generator=g)).cuda()
+    xb = x.bfloat16()
+    st = ops.bn_stats32(C, xb.device)
+    ops.bn_stats(xb, st)
+    out, mean, rstd = ops.bn_act_fwd(xb, gamma, beta, 1, None, stats=st)
+    dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    dx = ops.bn_act_bwd(xb, dout.bfloat16(), mean, rstd, gamma, beta, 1, dg, db, False)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(dx.float()).all()
+    assert torch.isfinite(dg).all() and torch.isfinite(db).all()
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    z = F.batch_norm(xr, None, None, gr, br, True, 0.1, 1e-5)
+    o_ref = z[:, :C // 2] * torch.sigmoid(z[:, C // 2:])
+    dx_ref, dg_ref, db_ref = torch.autograd.grad(o_ref, (xr, gr, br), dout)
+    assert _rel(out.float(), o_ref) < 4e-3
+    assert _rel(dx.float(), dx_ref) < 6e-3
+    assert _rel(dg, dg_ref) < 2e-3 and _rel(db, db_ref) < 2e-3
+
+
 def test_concat_c_and_backward():
     from sg2b200 import ops
     g = torch.Generator().manual_seed(1)
