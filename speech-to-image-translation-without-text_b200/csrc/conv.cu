@@ -303,16 +303,16 @@ static int launch_fprop_cluster_t(const GatherDesc& d, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------ CTA-pair launch (cta_group::2)
-// OFF by default (SG2_PAIR=1 / SG2_PAIR_WGRAD=1 opt in): in the multi-stream train step, where the three discriminators'
-// branches run pair kernels next to each other and next to the persistent / cluster kernels, the pair kernels deadlock
-// about once in a few hundred steps (tools/stress_replay.py with LOAD=1 hangs within 500 replays with either pair kernel
-// on, never in 2 500 replays with both off, never on a single stream; forcing one pair CTA per SM through the shared
-// memory request below did not cure it). Alone on the GPU they are correct (tests/test_gpu_kernels.py pair cases) and
-// took the step's conv launches from 5.64 to 5.49 ms, the step itself from 7.69 to 7.66 ms.
+// SG2_PAIR=0 / SG2_PAIR_WGRAD=0 switch the pair kernels off (the cluster / plain gather kernels take their layers again).
+// History (profiles/r02_pair_deadlock.md): in the multi-stream train step the first version deadlocked about once in a few
+// hundred steps — the two CTAs of a pair issued tcgen05.alloc.cta_group::2 as soon as each of them started, and next to
+// other streams' kernels the CTAs of a cluster start at different times. With a cluster barrier in front of the
+// allocation (igemm_pair.cuh) tools/stress_replay.py LOAD=1 ran 2 x 2 500 replays clean where every earlier process
+// hung within 500.
 static bool igemm_pair() {
   static const bool on = [] {
     const char* e = getenv("SG2_PAIR");
-    return e ? atoi(e) != 0 : false;
+    return e ? atoi(e) != 0 : true;
   }();
   return on;
 }

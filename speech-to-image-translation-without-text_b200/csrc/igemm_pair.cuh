@@ -85,6 +85,9 @@ __global__ void __launch_bounds__(kNumThreads, kDirect ? 2 : 1) igemm_fprop_pair
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
+  // both CTAs of the pair are running before either issues the two-SM TMEM allocation: the CTAs of a cluster are
+  // co-scheduled but, next to other streams' kernels, start at different times
+  cluster_sync_all();
   if (warp == 1) {
     tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish_pair();
@@ -417,6 +420,7 @@ __global__ void __launch_bounds__(kNumThreads, 2) igemm_wgrad_pair_kernel(const 
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
+  cluster_sync_all();   // see igemm_fprop_pair_kernel: the peer is running before the two-SM allocation is issued
   if (warp == 1) {
     tmem_alloc_pair(tmem_slot, BN);
     tmem_relinquish_pair();

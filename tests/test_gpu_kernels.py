@@ -442,15 +442,15 @@ def test_bn_groups_equal_separate_calls(act, P1, C):
     assert _rel(dg3, dg) < 1e-5 and _rel(db3, db) < 1e-5
 
 
-def test_pair_kernels_opt_in():
-    """The CTA-pair (cta_group::2) gather kernels are off by default (csrc/conv.cu igemm_pair: they deadlock in the
-    multi-stream step). They stay parity-tested: the pair-shaped conv cases and the epilogue-operand case run once more in
-    a child process with SG2_PAIR=1 (the switch is read once per process), on one stream."""
+def test_pair_kernels_switched_off():
+    """SG2_PAIR=0 (read once per process) hands the pair-shaped layers back to the cluster / plain gather kernels: the
+    same parity cases must hold on that path too — it is the fallback if the CTA-pair kernels ever have to be disabled
+    again (profiles/r02_pair_deadlock.md). Runs in a child process."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, SG2_PAIR="1")
+    env = dict(os.environ, SG2_PAIR="0")
     sel = ("test_conv_fprop_dgrad_wgrad and (2-12-16-16-128-256 or 0-20-4-4-256-512 or 1-24-4-4-256-256) "
            "or test_conv_dgrad_epilogue_operand and 0-20-4-4-256-512")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_kernels.py"), "-q", "-x", "-m", "gpu",
