@@ -524,9 +524,9 @@ def run_ours(args):
 def main():
     args = parse()
     # a run that stalls dumps every thread's Python stack and exits instead of hanging the caller (SG2_BENCH_WATCHDOG
-    # seconds; the default run takes ~1 minute including the CPU baseline)
+    # seconds, default 600 + 4 x --sustain; the default run takes ~1 minute including the CPU baseline)
     import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get("SG2_BENCH_WATCHDOG", "900")), exit=True)
+    faulthandler.dump_traceback_later(int(os.environ.get("SG2_BENCH_WATCHDOG", str(int(600 + 4 * args.sustain)))), exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:
