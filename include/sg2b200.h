@@ -38,6 +38,10 @@ const char* sg2_last_error(void);
  * CTAs (trainer.py:165-171's DataParallel gradient exchange, here one ncclAllReduce per gradient bucket slice) can run
  * beside them. 0 (default): use every SM. Process-wide. */
 int sg2_set_sm_reserve(int n_sms);
+/* CTA-pair (cta_group::2) gather kernels on (1) / off (0: their layers run on the cluster / plain gather kernels) /
+ * as the environment says (-1, default: SG2_PAIR, SG2_PAIR_WGRAD; on). Process-wide. The data-parallel trainer switches
+ * them off unless SG2_PAIR is set: every multi-GPU configuration of the round was validated and measured that way. */
+int sg2_set_pair_kernels(int on);
 
 /* ---- weights ------------------------------------------------------------------------------------------
  * fp32 OIHW master weights (the nn.Conv2d .weight the optimiser owns) -> bf16 operand packs.

@@ -309,12 +309,13 @@ static int launch_fprop_cluster_t(const GatherDesc& d, cudaStream_t st) {
 // other streams' kernels the CTAs of a cluster start at different times. With a cluster barrier in front of the
 // allocation (igemm_pair.cuh) tools/stress_replay.py LOAD=1 ran 2 x 2 500 replays clean where every earlier process
 // hung within 500.
+static int g_pair_override = -1;   // sg2_set_pair_kernels: -1 = the environment decides
 static bool igemm_pair() {
   static const bool on = [] {
     const char* e = getenv("SG2_PAIR");
     return e ? atoi(e) != 0 : true;
   }();
-  return on;
+  return g_pair_override >= 0 ? g_pair_override != 0 : on;
 }
 
 // One hypothesis for that deadlock: a cta_group::2 TMEM allocation takes columns on both SMs of the pair, so two pair CTAs
@@ -330,11 +331,11 @@ static size_t pair_exclusive_smem(size_t need) {
 }
 
 static bool igemm_pair_wgrad() {
-  static const bool on = [] {
+  static const int env = [] {
     const char* e = getenv("SG2_PAIR_WGRAD");
-    return e ? atoi(e) != 0 : igemm_pair();
+    return e ? (atoi(e) != 0 ? 1 : 0) : -1;
   }();
-  return on;
+  return g_pair_override >= 0 ? g_pair_override != 0 : (env >= 0 ? env != 0 : igemm_pair());
 }
 
 template <int BN, int BK, bool kDirect>
@@ -986,6 +987,11 @@ int sg2_version(void) { return 2; }
 int sg2_set_sm_reserve(int n_sms) {
   if (n_sms < 0 || n_sms > 64) SG2_FAIL(SG2_EINVAL, "set_sm_reserve: %d", n_sms);
   g_sm_reserve = n_sms;
+  return 0;
+}
+int sg2_set_pair_kernels(int on) {
+  if (on < -1 || on > 1) SG2_FAIL(SG2_EINVAL, "set_pair_kernels: %d", on);
+  g_pair_override = on;
   return 0;
 }
 const char* sg2_last_error(void) { return g_err; }

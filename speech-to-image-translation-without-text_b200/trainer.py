@@ -181,6 +181,10 @@ class FusedTrainer:
         if all_reduce is not None:
             from . import _lib
             _lib.call("sg2_set_sm_reserve", int(os.environ.get("SG2_SM_RESERVE", "8")))
+            if "SG2_PAIR" not in os.environ:
+                # the CTA-pair kernels' cure (cluster barrier before the two-SM TMEM allocation) was stress-tested on one
+                # GPU only; every 2 / 4 / 8-GPU line and the 2-GPU parity test of the round ran with them off
+                _lib.call("sg2_set_pair_kernels", 0)
         self.concurrent = os.environ.get("SG2_CONCURRENT", "1") != "0"   # one stream per discriminator (see step())
         self.batched_d = os.environ.get("SG2_BATCHED_D", "1") != "0"     # real/wrong/fake D passes as one 3B pass
         # per-layer Adam (+ re-pack) on the wgrad side streams while backward is still running; data parallel: the large
