@@ -1421,6 +1421,8 @@ int sg2_head_tanh_bwd(const float* dimg, const float* img, void* dy, int B, int 
 
 int sg2_stem_im2col(const float* img, void* col, int B, int S, void* stream) {
   if (S % 2) EW_FAIL(SG2_EINVAL, "stem_im2col: odd image size");
+  if ((12 * (S + 2) + (S / 2) * 33 + 48) * sizeof(float) > 48 * 1024)
+    EW_FAIL(SG2_EINVAL, "stem_im2col: image size %d needs more than 48 KB of shared memory (the path's scales are 64 / 128 / 256)", S);
   long long nblk = (long long)B * (S / 2);
   if (nblk > 148 * 16) nblk = 148 * 16;
   stem_im2col_kernel<<<(unsigned)nblk, 256, (12 * (S + 2) + (S / 2) * 33 + 48) * sizeof(float), (cudaStream_t)stream>>>(img, (uint4*)col, B, S);
@@ -1429,6 +1431,8 @@ int sg2_stem_im2col(const float* img, void* col, int B, int S, void* stream) {
 
 int sg2_stem_col2im(const void* dcol, float* dimg, int B, int S, void* stream) {
   if (S % 2) EW_FAIL(SG2_EINVAL, "stem_col2im: odd image size");
+  if ((size_t)S * 33 * sizeof(uint32_t) > 48 * 1024)
+    EW_FAIL(SG2_EINVAL, "stem_col2im: image size %d needs more than 48 KB of shared memory (the path's scales are 64 / 128 / 256)", S);
   const int So = S / 2;
   long long nblk = (long long)B * (So + 1);
   if (nblk > 148 * 16) nblk = 148 * 16;
